@@ -1,0 +1,146 @@
+// Shared host/device helpers for the mirror_b200 kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mirror_b200.h"
+
+namespace mb {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error reporting (thread-local, SURVEY.md §8b "Error convention") ----
+void set_error(const char* fmt, ...);
+enum { MB_ERR_ARG = -1, MB_ERR_ALIGN = -2, MB_ERR_DRIVER = -3, MB_ERR_UNSUPPORTED = -4 };
+
+#define MB_CHECK_ARG(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      mb::set_error(__VA_ARGS__);    \
+      return mb::MB_ERR_ARG;         \
+    }                                \
+  } while (0)
+
+#define MB_CUDA(call)                                                              \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      mb::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return (int)e__;                                                             \
+    }                                                                              \
+  } while (0)
+
+#define MB_LAUNCH_CHECK() MB_CUDA(cudaGetLastError())
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- stateless counter-based uniform in [0,1): keep-mask of the fused dropout ----
+__host__ __device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t idx) {
+  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ULL + 0x632BE59BD9B4E019ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum / max for blockDim.x <= 1024 (multiple of 32); `sh` holds >= 32 floats
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) v = warp_sum(v);
+  if (threadIdx.x == 0) sh[0] = v;
+  __syncthreads();
+  return sh[0];
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : -INFINITY;
+  if (w == 0) v = warp_max(v);
+  if (threadIdx.x == 0) sh[0] = v;
+  __syncthreads();
+  return sh[0];
+}
+
+// ---- GEMM epilogue shared by the tcgen05 kernel and the SIMT cross-check kernel ----
+struct Epi {
+  int M, N, batch1;
+  float alpha;
+  const float* bias;
+  int act;
+  float drop_p, drop_scale;
+  uint64_t drop_seed;
+  const void* res;
+  int res_is_bf16;
+  float gamma;
+  long long ldr, r_bs1, r_bs2;
+  float beta;
+  float* o32;
+  long long ldc32, c32_bs1, c32_bs2;
+  bf16* o16;
+  long long ldc16, c16_bs1, c16_bs2;
+  int atomic;  // split-K partial: atomically add alpha*acc into o32
+};
+
+__device__ __forceinline__ void epi_store_scalar(const Epi& e, float acc, int b1, int b2, int row, int col) {
+  if (e.atomic) {
+    atomicAdd(e.o32 + b2 * e.c32_bs2 + b1 * e.c32_bs1 + (long long)row * e.ldc32 + col, e.alpha * acc);
+    return;
+  }
+  float v = e.alpha * acc;
+  if (e.bias) v += e.bias[col];
+  if (e.act == MIRROR_ACT_RELU) v = fmaxf(v, 0.f);
+  else if (e.act == MIRROR_ACT_GELU) v = gelu_erf(v);
+  if (e.drop_p > 0.f) {
+    const uint64_t idx = ((uint64_t)(b2 * e.batch1 + b1) * e.M + row) * e.N + col;
+    v = hash_u01(e.drop_seed, idx) >= e.drop_p ? v * e.drop_scale : 0.f;
+  }
+  if (e.res) {
+    const long long off = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)row * e.ldr + col;
+    v += e.gamma * (e.res_is_bf16 ? __bfloat162float(((const bf16*)e.res)[off]) : ((const float*)e.res)[off]);
+  }
+  if (e.o32) {
+    float* p = e.o32 + b2 * e.c32_bs2 + b1 * e.c32_bs1 + (long long)row * e.ldc32 + col;
+    if (e.beta != 0.f) v += e.beta * *p;
+    *p = v;
+  }
+  if (e.o16) e.o16[b2 * e.c16_bs2 + b1 * e.c16_bs1 + (long long)row * e.ldc16 + col] = __float2bfloat16(v);
+}
+
+}  // namespace mb

@@ -1,0 +1,386 @@
+// HBM-bound glue kernels of the MIRROR step: casts, activation fwd/bwd with the fused dropout
+// mask, token assembly (cls + wrap-around padding), mask/pos-embed, rank-based random masking,
+// landmark means and their backward, column sums, reparameterisation.  All are coalesced,
+// vectorised where the layout allows, and sized as grid-stride loops over a multiple of the SM count.
+#include "common.cuh"
+
+namespace mb {
+namespace {
+
+inline int grid_for(long long n, int block, int per_thread = 1) {
+  long long g = (n + (long long)block * per_thread - 1) / ((long long)block * per_thread);
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// dst[r, 0:cols_out] = bf16(src[r, 0:cols]) zero padded
+__global__ void cast_pad_kernel(const float* __restrict__ src, long long rows, int cols, long long lds,
+                                bf16* __restrict__ dst, int cols_out, long long ldd) {
+  const long long total = rows * cols_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols_out;
+    const int c = (int)(i - r * cols_out);
+    dst[r * ldd + c] = __float2bfloat16(c < cols ? src[r * lds + c] : 0.f);
+  }
+}
+// contiguous fast path, 8 elements per thread
+__global__ void cast_vec_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = src[2 * i], b = src[2 * i + 1];
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+    h[0] = __floats2bfloat162_rn(a.x, a.y);
+    h[1] = __floats2bfloat162_rn(a.z, a.w);
+    h[2] = __floats2bfloat162_rn(b.x, b.y);
+    h[3] = __floats2bfloat162_rn(b.z, b.w);
+    dst[i] = u;
+  }
+}
+
+__global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n, float alpha) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] += alpha * src[i];
+}
+
+// out = dropout(act(pre)) as bf16 (and optionally f32)
+__global__ void act_fwd_kernel(const float* __restrict__ pre, long long n, int act, float drop_p, float drop_scale,
+                               uint64_t seed, bf16* __restrict__ o16, float* __restrict__ o32) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = pre[i];
+    if (act == MIRROR_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == MIRROR_ACT_GELU) v = gelu_erf(v);
+    if (drop_p > 0.f) v = hash_u01(seed, (uint64_t)i) >= drop_p ? v * drop_scale : 0.f;
+    if (o16) o16[i] = __float2bfloat16(v);
+    if (o32) o32[i] = v;
+  }
+}
+// dx = dy * dropmask * act'(pre); rows x cols with independent row strides so that padded layouts work.
+__global__ void act_bwd_kernel(const float* __restrict__ dy, long long ld_dy, const float* __restrict__ pre,
+                               long long ld_pre, long long rows, int cols, int act, float drop_p, float drop_scale,
+                               uint64_t seed, bf16* __restrict__ o16, long long ld16, float* __restrict__ o32,
+                               long long ld32) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    float g = dy[r * ld_dy + c];
+    if (drop_p > 0.f) g = hash_u01(seed, (uint64_t)i) >= drop_p ? g * drop_scale : 0.f;
+    if (act != MIRROR_ACT_NONE) {
+      const float x = pre[r * ld_pre + c];
+      if (act == MIRROR_ACT_RELU) g = x > 0.f ? g : 0.f;
+      else g *= gelu_erf_grad(x);
+    }
+    if (o16) o16[r * ld16 + c] = __float2bfloat16(g);
+    if (o32) o32[r * ld32 + c] = g;
+  }
+}
+
+// h[b,0,:] = cls ; h[b,1+N+j,:] = h[b,1+j,:] for j < add      (models/mirror.py:656-665)
+__global__ void assemble_fwd_kernel(float* __restrict__ h, const float* __restrict__ cls, int B, int N, int add, int E) {
+  const int S = 1 + N + add;
+  const long long total = (long long)B * (1 + add) * E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % E);
+    const int j = (int)((i / E) % (1 + add));
+    const int b = (int)(i / ((long long)E * (1 + add)));
+    float* hb = h + (long long)b * S * E;
+    if (j == 0) hb[e] = cls[e];
+    else hb[(long long)(N + j) * E + e] = hb[(long long)j * E + e];
+  }
+}
+// dh[b,1+j] += dh[b,1+N+j];  dcls[e] += sum_b dh[b,0,e]
+__global__ void assemble_bwd_kernel(float* __restrict__ dh, float* __restrict__ dcls, int B, int N, int add, int E) {
+  const int S = 1 + N + add;
+  const long long total = (long long)(1 + add) * E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % E);
+    const int j = (int)(i / E);
+    if (j == 0) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += dh[(long long)b * S * E + e];
+      dcls[e] += s;
+    } else {
+      for (int b = 0; b < B; ++b) {
+        float* hb = dh + (long long)b * S * E;
+        hb[(long long)j * E + e] += hb[(long long)(N + j) * E + e];
+      }
+    }
+  }
+}
+
+// mask[b,j] = rank_j >= keep, rank_j = #{i : noise_i < noise_j or (== and i < j)}  (argsort of argsort,
+// models/mirror.py:516-531, 630-647)
+__global__ void rank_mask_kernel(const float* __restrict__ noise, int N, int keep, float* __restrict__ mask) {
+  extern __shared__ float sn[];
+  const int b = blockIdx.x;
+  const float* nb = noise + (long long)b * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sn[i] = nb[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float v = sn[j];
+    int rank = 0;
+    for (int i = 0; i < N; ++i) {
+      const float u = sn[i];
+      rank += (u < v) || (u == v && i < j);
+    }
+    mask[(long long)b * N + j] = rank >= keep ? 1.f : 0.f;
+  }
+}
+
+// r[b,t,e] = (t >= first && mask[b,t-first] ? tok[e*tok_stride] : r[b,t,e]) + pos[t,e]
+__global__ void mask_pos_fwd_kernel(float* __restrict__ r, const float* __restrict__ mask, const float* __restrict__ tok,
+                                    int tok_stride, const float* __restrict__ pos, int B, int T, int E, int first) {
+  const long long total = (long long)B * T * E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % E);
+    const int t = (int)((i / E) % T);
+    const int b = (int)(i / ((long long)E * T));
+    const bool m = t >= first && mask[(long long)b * (T - first) + (t - first)] != 0.f;
+    r[i] = (m ? tok[(long long)e * tok_stride] : r[i]) + pos[(long long)t * E + e];
+  }
+}
+// dr = masked ? 0 : dy (in place);  dpos[t,e] += sum_b dy;  dtok[e*tok_stride] += sum over masked slots
+__global__ void mask_pos_bwd_kernel(float* __restrict__ dy, const float* __restrict__ mask, float* __restrict__ dtok,
+                                    int tok_stride, float* __restrict__ dpos, int B, int T, int E, int first) {
+  const long long total = (long long)T * E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % E);
+    const int t = (int)(i / E);
+    float sp = 0.f, st = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const long long o = ((long long)b * T + t) * E + e;
+      const float g = dy[o];
+      sp += g;
+      if (t >= first && mask[(long long)b * (T - first) + (t - first)] != 0.f) {
+        st += g;
+        dy[o] = 0.f;
+      }
+    }
+    dpos[i] += sp;
+    if (st != 0.f) atomicAdd(dtok + (long long)e * tok_stride, st);
+  }
+}
+
+// lm[b,j,c] = mean_{s<seg} qkv[b, j*seg+s, c]  for c < 2E (q and k slots)
+__global__ void landmark_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ lm, int B, int n, int m, int seg,
+                                    int E) {
+  const int C2 = 2 * E;
+  const long long total = (long long)B * m * (C2 / 2);
+  const float inv = 1.f / seg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c2 = (int)(i % (C2 / 2));
+    const int j = (int)((i / (C2 / 2)) % m);
+    const int b = (int)(i / ((long long)(C2 / 2) * m));
+    const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(qkv + ((long long)b * n + (long long)j * seg) * 3 * E) + c2;
+    float sx = 0.f, sy = 0.f;
+    for (int s = 0; s < seg; ++s) {
+      const float2 f = __bfloat1622float2(src[(long long)s * 3 * E / 2]);
+      sx += f.x;
+      sy += f.y;
+    }
+    reinterpret_cast<__nv_bfloat162*>(lm + ((long long)b * m + j) * C2)[c2] = __floats2bfloat162_rn(sx * inv, sy * inv);
+  }
+}
+// dqkv16[b,t,c] = bf16(dqkv32[b,t,c] + (c < 2E ? dlm32[b,t/seg,c]/seg : 0))
+__global__ void dqkv_finish_kernel(const float* __restrict__ dqkv32, const float* __restrict__ dlm32,
+                                   bf16* __restrict__ dqkv16, int B, int n, int m, int seg, int E) {
+  const int C3 = 3 * E, C2 = 2 * E;
+  const long long total = (long long)B * n * (C3 / 2);
+  const float inv = 1.f / seg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = 2 * (int)(i % (C3 / 2));
+    const long long bt = i / (C3 / 2);
+    const int t = (int)(bt % n);
+    const int b = (int)(bt / n);
+    float2 v = *reinterpret_cast<const float2*>(dqkv32 + bt * C3 + c);
+    if (c < C2) {
+      const float2 l = *reinterpret_cast<const float2*>(dlm32 + ((long long)b * m + t / seg) * C2 + c);
+      v.x += l.x * inv;
+      v.y += l.y * inv;
+    }
+    *reinterpret_cast<__nv_bfloat162*>(dqkv16 + bt * C3 + c) = __floats2bfloat162_rn(v.x, v.y);
+  }
+}
+
+// out[c] += sum_r x[r, c]   (bias gradients).  Block = 32 x 8 threads over a [rows_chunk, 32-col] tile.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long long rows, int cols, long long ld, float* __restrict__ out,
+                              int rows_per_block) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) s += (float)x[r * ld + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+// z = mu + exp(0.5*logvar)*eps   (models/mirror.py:830-833)
+__global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ eps,
+                                   long long n, bf16* __restrict__ z16) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    z16[i] = __float2bfloat16(mu[i] + __expf(0.5f * lv[i]) * eps[i]);
+}
+// dmu += dz ; dlv += dz * eps * 0.5 * exp(0.5*logvar)
+__global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ lv, const float* __restrict__ eps,
+                                   long long n, float* __restrict__ dmu, float* __restrict__ dlv) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = dz[i];
+    dmu[i] += g;
+    dlv[i] += g * eps[i] * 0.5f * __expf(0.5f * lv[i]);
+  }
+}
+
+}  // namespace
+}  // namespace mb
+
+using namespace mb;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int mirror_cast_f32_bf16(const float* src, int64_t rows, int32_t cols, int64_t lds, void* dst, int32_t cols_out,
+                                    int64_t ldd, mirror_stream_t stream) {
+  MB_CHECK_ARG(src && dst && rows >= 0 && cols > 0 && cols_out >= cols && ldd >= cols_out && lds >= cols, "cast: bad args");
+  if (rows == 0) return 0;
+  const long long n = rows * (long long)cols;
+  if (cols == cols_out && lds == cols && ldd == cols && n % 8 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0) {
+    cast_vec_kernel<<<grid_for(n / 8, 256), 256, 0, STREAM>>>(reinterpret_cast<const float4*>(src),
+                                                              reinterpret_cast<uint4*>(dst), n / 8);
+  } else {
+    cast_pad_kernel<<<grid_for(rows * (long long)cols_out, 256), 256, 0, STREAM>>>(src, rows, cols, lds,
+                                                                                 reinterpret_cast<bf16*>(dst), cols_out, ldd);
+  }
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_axpy_f32(float* dst, const float* src, int64_t n, float alpha, mirror_stream_t stream) {
+  MB_CHECK_ARG(dst && src && n >= 0, "axpy: bad args");
+  if (n == 0) return 0;
+  axpy_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(dst, src, n, alpha);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_act_fwd(const float* pre, int64_t n, int32_t act, float drop_p, uint64_t seed, void* out_bf16,
+                              float* out_f32, mirror_stream_t stream) {
+  MB_CHECK_ARG(pre && n > 0 && (out_bf16 || out_f32) && drop_p >= 0.f && drop_p < 1.f, "act_fwd: bad args");
+  act_fwd_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(pre, n, act, drop_p, 1.f / (1.f - drop_p), seed,
+                                                       reinterpret_cast<bf16*>(out_bf16), out_f32);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_act_bwd(const float* dy, int64_t ld_dy, const float* pre, int64_t ld_pre, int64_t rows, int32_t cols,
+                              int32_t act, float drop_p, uint64_t seed, void* out_bf16, int64_t ld16, float* out_f32,
+                              int64_t ld32, mirror_stream_t stream) {
+  MB_CHECK_ARG(dy && rows > 0 && cols > 0 && (out_bf16 || out_f32) && (act == 0 || pre) && drop_p >= 0.f && drop_p < 1.f,
+               "act_bwd: bad args");
+  act_bwd_kernel<<<grid_for(rows * (long long)cols, 256), 256, 0, STREAM>>>(
+      dy, ld_dy, pre, ld_pre, rows, cols, act, drop_p, 1.f / (1.f - drop_p), seed, reinterpret_cast<bf16*>(out_bf16), ld16,
+      out_f32, ld32);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_wsi_assemble_fwd(float* h, const float* cls, int32_t B, int32_t N, int32_t add, int32_t E,
+                                       mirror_stream_t stream) {
+  MB_CHECK_ARG(h && cls && B > 0 && N > 0 && add >= 0 && add <= N && E > 0, "assemble_fwd: bad args");
+  assemble_fwd_kernel<<<grid_for((long long)B * (1 + add) * E, 256), 256, 0, STREAM>>>(h, cls, B, N, add, E);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mirror_wsi_assemble_bwd(float* dh, float* dcls, int32_t B, int32_t N, int32_t add, int32_t E,
+                                       mirror_stream_t stream) {
+  MB_CHECK_ARG(dh && dcls && B > 0 && N > 0 && add >= 0 && add <= N && E > 0, "assemble_bwd: bad args");
+  assemble_bwd_kernel<<<grid_for((long long)(1 + add) * E, 128), 128, 0, STREAM>>>(dh, dcls, B, N, add, E);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_rank_mask(const float* noise, int32_t B, int32_t N, int32_t keep, float* mask, mirror_stream_t stream) {
+  MB_CHECK_ARG(noise && mask && B > 0 && N > 0 && keep >= 0 && keep <= N, "rank_mask: bad args");
+  const size_t smem = (size_t)N * sizeof(float);
+  MB_CHECK_ARG(smem <= 200 * 1024, "rank_mask: N=%d too large for the shared-memory row", N);
+  static bool configured = false;
+  if (!configured) {
+    MB_CUDA(cudaFuncSetAttribute(rank_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  rank_mask_kernel<<<B, 512, smem, STREAM>>>(noise, N, keep, mask);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_mask_pos_fwd(float* r, const float* mask, const float* tok, int32_t tok_stride, const float* pos,
+                                   int32_t B, int32_t T, int32_t E, int32_t first, mirror_stream_t stream) {
+  MB_CHECK_ARG(r && mask && tok && pos && B > 0 && T > first && E > 0 && first >= 0, "mask_pos_fwd: bad args");
+  mask_pos_fwd_kernel<<<grid_for((long long)B * T * E, 256), 256, 0, STREAM>>>(r, mask, tok, tok_stride, pos, B, T, E, first);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mirror_mask_pos_bwd(float* dy, const float* mask, float* dtok, int32_t tok_stride, float* dpos, int32_t B,
+                                   int32_t T, int32_t E, int32_t first, mirror_stream_t stream) {
+  MB_CHECK_ARG(dy && mask && dtok && dpos && B > 0 && T > first && E > 0 && first >= 0, "mask_pos_bwd: bad args");
+  mask_pos_bwd_kernel<<<grid_for((long long)T * E, 128), 128, 0, STREAM>>>(dy, mask, dtok, tok_stride, dpos, B, T, E, first);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_landmark_fwd(const void* qkv, void* lm, int32_t B, int32_t n, int32_t m, int32_t seg, int32_t E,
+                                   mirror_stream_t stream) {
+  MB_CHECK_ARG(qkv && lm && B > 0 && m > 0 && seg > 0 && n == m * seg && E % 2 == 0, "landmark_fwd: bad args (n=%d m=%d seg=%d)",
+               n, m, seg);
+  landmark_fwd_kernel<<<grid_for((long long)B * m * E, 256), 256, 0, STREAM>>>(reinterpret_cast<const bf16*>(qkv),
+                                                                             reinterpret_cast<bf16*>(lm), B, n, m, seg, E);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mirror_dqkv_finish(const float* dqkv32, const float* dlm32, void* dqkv16, int32_t B, int32_t n, int32_t m,
+                                  int32_t seg, int32_t E, mirror_stream_t stream) {
+  MB_CHECK_ARG(dqkv32 && dlm32 && dqkv16 && B > 0 && n == m * seg && E % 2 == 0, "dqkv_finish: bad args");
+  dqkv_finish_kernel<<<grid_for((long long)B * n * 3 * E / 2, 256), 256, 0, STREAM>>>(
+      dqkv32, dlm32, reinterpret_cast<bf16*>(dqkv16), B, n, m, seg, E);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_colsum(const void* x, int32_t is_bf16, int64_t rows, int32_t cols, int64_t ld, float* out,
+                             mirror_stream_t stream) {
+  MB_CHECK_ARG(x && out && rows > 0 && cols > 0 && ld >= cols, "colsum: bad args");
+  const int gx = (cols + 31) / 32;
+  long long gy = (long long)num_sms() * 8 / gx;
+  if (gy < 1) gy = 1;
+  long long rpb = (rows + gy - 1) / gy;
+  if (rpb < 64) rpb = 64;
+  gy = (rows + rpb - 1) / rpb;
+  dim3 grid(gx, (unsigned)gy), block(32, 8);
+  if (is_bf16) colsum_kernel<bf16><<<grid, block, 0, STREAM>>>(reinterpret_cast<const bf16*>(x), rows, cols, ld, out, (int)rpb);
+  else colsum_kernel<float><<<grid, block, 0, STREAM>>>(reinterpret_cast<const float*>(x), rows, cols, ld, out, (int)rpb);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_reparam_fwd(const float* mu, const float* logvar, const float* eps, int64_t n, void* z_bf16,
+                                  mirror_stream_t stream) {
+  MB_CHECK_ARG(mu && logvar && eps && z_bf16 && n > 0, "reparam_fwd: bad args");
+  reparam_fwd_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(mu, logvar, eps, n, reinterpret_cast<bf16*>(z_bf16));
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mirror_reparam_bwd(const float* dz, const float* logvar, const float* eps, int64_t n, float* dmu, float* dlogvar,
+                                  mirror_stream_t stream) {
+  MB_CHECK_ARG(dz && logvar && eps && dmu && dlogvar && n > 0, "reparam_bwd: bad args");
+  reparam_bwd_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(dz, logvar, eps, n, dmu, dlogvar);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
