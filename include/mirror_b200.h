@@ -84,6 +84,130 @@ int mirror_gemm_bf16(const mirror_gemm_args* args, mirror_stream_t stream);
  * GPU unit tests to cross-check the tensor-core kernel at sizes where a host reference is slow. */
 int mirror_gemm_bf16_simt(const mirror_gemm_args* args, mirror_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * HBM-bound glue (elementwise.cu).  `ld*` are row strides in elements.
+ * ---------------------------------------------------------------------------------------------- */
+/* dst[r,0:cols_out] = bf16(src[r,0:cols]), zero padded.  Replaces the implicit autocast casts
+ * (train_mirror.py:1145) and `h.float()` (models/mirror.py:652). */
+int mirror_cast_f32_bf16(const float* src, int64_t rows, int32_t cols, int64_t lds, void* dst, int32_t cols_out, int64_t ldd,
+                         mirror_stream_t stream);
+/* dst[r,0:cols] = src[r,0:cols] with row strides: gathers `wsi_emb[:, 0, :]` (models/mirror.py:896) into a dense block */
+int mirror_copy_rows_f32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd, mirror_stream_t stream);
+/* dst += alpha*src  (gradient accumulation of the autograd graph) */
+int mirror_axpy_f32(float* dst, const float* src, int64_t n, float alpha, mirror_stream_t stream);
+/* out = dropout(act(pre)); keep(idx)=hash(seed,idx)>=p.  GELU of timm Mlp / Block (models/mirror.py:138-143,217-224). */
+int mirror_act_fwd(const float* pre, int64_t n, int32_t act, float drop_p, uint64_t seed, void* out_bf16, float* out_f32,
+                   mirror_stream_t stream);
+/* dx = dy * dropmask * act'(pre) on [B,T,C] views (bs* = batch strides, ld* = row strides; dropout index = dense (b,t,c));
+ * for ReLU `pre` may be the saved OUTPUT (same sign test). */
+int mirror_act_bwd(const float* dy, int64_t bs_dy, int64_t ld_dy, const float* pre, int64_t bs_pre, int64_t ld_pre, int32_t B,
+                   int32_t T, int32_t C, int32_t act, float drop_p, uint64_t seed, void* out_bf16, int64_t bs16, int64_t ld16,
+                   float* out_f32, int64_t bs32, int64_t ld32, mirror_stream_t stream);
+/* h:[B,1+N+add,E]; h[b,0]=cls, h[b,1+N+j]=h[b,1+j] (wrap-around square padding + cls, models/mirror.py:656-665) */
+int mirror_wsi_assemble_fwd(float* h, const float* cls, int32_t B, int32_t N, int32_t add, int32_t E, mirror_stream_t stream);
+/* backward of fc1+ReLU+assemble: dpre[b,j,:] = (h[b,1+j,:]>0) * (dh[b,1+j,:] + (j<add ? dh[b,1+N+j,:] : 0)) as bf16 [B,N,E];
+ * dcls[e] += sum_b dh[b,0,e] */
+int mirror_wsi_embed_bwd(const float* dh, const float* h, int32_t B, int32_t N, int32_t add, int32_t E, void* dpre_bf16, float* dcls,
+                         mirror_stream_t stream);
+/* mask[b,j] = rank(noise[b,j]) >= keep ? 1 : 0 -- argsort(argsort(noise)) of random_masking (models/mirror.py:516-531,630-647) */
+int mirror_rank_mask(const float* noise, int32_t B, int32_t N, int32_t keep, float* mask, mirror_stream_t stream);
+/* r[b,t,e] = (t>=first && mask[b,t-first] ? tok[e*tok_stride] : r[b,t,e]) + pos[t,e]  (models/mirror.py:521-527,636-643,692-693,549) */
+int mirror_mask_pos_fwd(float* r, const float* mask, const float* tok, int32_t tok_stride, const float* pos, int32_t B, int32_t T,
+                        int32_t E, int32_t first, mirror_stream_t stream);
+int mirror_mask_pos_bwd(float* dy, const float* mask, float* dtok, int32_t tok_stride, float* dpos, int32_t B, int32_t T, int32_t E,
+                        int32_t first, mirror_stream_t stream);
+/* Nyström landmarks: lm[b,j,0:2E] = mean of `seg` consecutive rows of the q and k slots of qkv[B,n,3E] */
+int mirror_landmark_fwd(const void* qkv_bf16, void* lm_bf16, int32_t B, int32_t n, int32_t m, int32_t seg, int32_t E,
+                        mirror_stream_t stream);
+/* dqkv16 = bf16(dqkv32 + broadcast(dlm32)/seg) : landmark backward fused with the cast for the qkv weight/data gradients */
+int mirror_dqkv_finish(const float* dqkv32, const float* dlm32, void* dqkv_bf16, int32_t B, int32_t n, int32_t m, int32_t seg,
+                       int32_t E, mirror_stream_t stream);
+/* out[c] += sum_r x[r,c] (bias gradients) */
+int mirror_colsum(const void* x, int32_t is_bf16, int64_t rows, int32_t cols, int64_t ld, float* out, mirror_stream_t stream);
+/* z = mu + exp(0.5*logvar)*eps (Normal.rsample with injected eps, models/mirror.py:830-833) and its backward */
+int mirror_reparam_fwd(const float* mu, const float* logvar, const float* eps, int64_t n, void* z_bf16, float* z_f32,
+                       mirror_stream_t stream);
+int mirror_reparam_bwd(const float* dz, const float* logvar, const float* eps, int64_t n, float* dmu, float* dlogvar,
+                       mirror_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm / softmax / L2-normalise (norm_softmax.cu)
+ * ---------------------------------------------------------------------------------------------- */
+/* x:[B,S,E] f32 -> outputs in a padded layout [B,n_out,E] at row offset `pad` (rows<pad zero): the Nyström layer front-pads
+ * with zero rows.  nn.LayerNorm at models/mirror.py:298,350,604 (eps 1e-5) and :122,137,255,494 (eps 1e-6). */
+int mirror_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t B, int32_t S, int32_t E,
+                         int32_t n_out, int32_t pad, void* out_bf16, float* out_f32, float* mean, float* rstd, mirror_stream_t stream);
+/* dx = (add ? add : 0) + LN-gradient; `add` may alias dx (the residual branch of models/mirror.py:312) */
+int mirror_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int32_t B,
+                         int32_t S, int32_t E, int32_t n_out, int32_t pad, float* dx, const float* add, float* dgamma,
+                         float* dbeta, mirror_stream_t stream);
+/* row softmax of the three Nyström similarity matrices */
+int mirror_softmax_fwd(const float* x, int64_t rows, int32_t cols, void* y_bf16, float* y_f32, mirror_stream_t stream);
+int mirror_softmax_bwd(const void* y_bf16, const float* dy, int64_t rows, int32_t cols, float scale, void* dx_bf16, float* dx_f32,
+                       mirror_stream_t stream);
+/* F.normalize(x, dim=-1, eps) of the alignment heads (models/mirror.py:539-540,682-683); rows may be strided */
+int mirror_l2norm_fwd(const float* x, int64_t ldx, int32_t rows, int32_t cols, float eps, void* y_bf16, float* y_f32, int64_t ldy,
+                      float* norm, mirror_stream_t stream);
+int mirror_l2norm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* norm, int32_t rows, int32_t cols,
+                      float* dx, int64_t lddx, int32_t accumulate, mirror_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Nyström attention specifics (nystrom.cu); algorithm of nystrom_attention~=0.0.14, call site models/mirror.py:299-312
+ * ---------------------------------------------------------------------------------------------- */
+/* out[b,t,c] = sum_j w[h(c),j] * v[b,t+j-16,c]  (res_conv: Conv2d(h,h,(33,1),groups=h,bias=False) on the value slot) */
+int mirror_res_conv_fwd(const void* qkv_bf16, const float* w, int32_t B, int32_t n, int32_t E, void* out_bf16, mirror_stream_t stream);
+/* dqkv32[..,2E:3E] += conv^T(dout);  dw[8,33] += weight gradient */
+int mirror_res_conv_bwd(const void* dout_bf16, const void* qkv_bf16, const float* w, int32_t B, int32_t n, int32_t E, float* dqkv32,
+                        float* dw, mirror_stream_t stream);
+/* z0 = a2^T / (max_rowsum * max_colsum), maxima over the WHOLE [BH,m,m] tensor (moore_penrose_iter_pinv init).
+ * scratch32: 32 bytes of device memory kept by the caller until the backward call. */
+int mirror_pinv_init(const float* a2, int32_t BH, int32_t m, void* scratch32, float* z_f32, void* z_bf16, mirror_stream_t stream);
+int mirror_pinv_init_bwd(const float* gz0, const float* z0_f32, int32_t BH, int32_t m, void* scratch32, float* gx, int32_t accumulate,
+                         mirror_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PPEG (ppeg.cu): models/mirror.py:317-331.  wm[49*E], bm[E], dwm[49*E], dbm[E] are caller-owned scratch.
+ * ---------------------------------------------------------------------------------------------- */
+int mirror_ppeg_fwd(const float* x, const float* w7, const float* w5, const float* w3, const float* b7, const float* b5,
+                    const float* b3, int32_t B, int32_t H, int32_t E, float* wm, float* bm, float* y, mirror_stream_t stream);
+int mirror_ppeg_bwd(const float* dy, const float* x, const float* wm, int32_t B, int32_t H, int32_t E, float* dx, int32_t accumulate,
+                    float* dwm, float* dbm, float* dw7, float* dw5, float* dw3, float* db7, float* db5, float* db3,
+                    mirror_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RNA attention over the 12 chunks of one embedding (rna_attn.cu): models/mirror.py:77-102
+ * ---------------------------------------------------------------------------------------------- */
+int mirror_rna_attn_fwd(const float* qkv, int32_t B, int32_t E, void* out_bf16, float* out_f32, mirror_stream_t stream);
+int mirror_rna_attn_bwd(const float* qkv, const float* dout, int32_t B, int32_t E, void* dqkv_bf16, float* dqkv_f32,
+                        mirror_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Losses (loss.cu).  Loss values, the temperature scale and upstream gradients are DEVICE scalars.
+ * ---------------------------------------------------------------------------------------------- */
+/* ClipLoss (losses/mirror_loss.py:37-52; w_row=w_col=0.5) / InfoNCE (losses/info_nce.py:144-164; symmetric 0.5/0.5, else 1/0)
+ * on raw = W.R^T (unscaled, from mirror_gemm_bf16); logits = (*scale) * raw. */
+int mirror_clip_loss_fwd(const float* raw, int32_t B, const float* scale, float w_row, float w_col, float* row_lse, float* col_lse,
+                         float* loss, mirror_stream_t stream);
+/* G = d loss / d raw (bf16, operand of dW = G.R and dR = G^T.W); dscale += d loss / d scale */
+int mirror_clip_loss_bwd(const float* raw, int32_t B, const float* scale, float w_row, float w_col, const float* row_lse,
+                         const float* col_lse, const float* gout, void* G_bf16, float* dscale, mirror_stream_t stream);
+/* retention terms, losses/mirror_loss.py:98-103: out = sum_rows mask*mean_e (a-b)^2 / sum mask; batches strided by a_bs / b_bs */
+int mirror_masked_mse_fwd(const float* a, int64_t a_bs, const float* b, int64_t b_bs, const float* mask, int32_t B, int32_t T,
+                          int32_t E, float* scratch2, float* out, mirror_stream_t stream);
+int mirror_masked_mse_bwd(const float* a, int64_t a_bs, const float* b, int64_t b_bs, const float* mask, int32_t B, int32_t T,
+                          int32_t E, const float* scratch2, const float* gout, float gw, float* da, int64_t da_bs, int32_t acc_a,
+                          float* db, int64_t db_bs, int32_t acc_b, mirror_stream_t stream);
+/* style term, losses/mirror_loss.py:105-112, both modalities stacked ([2B,L], n = 2B*L) */
+int mirror_gauss_kl_fwd(const float* mu, const float* logvar, int64_t n, int32_t B, float* out, mirror_stream_t stream);
+int mirror_gauss_kl_bwd(const float* mu, const float* logvar, int64_t n, int32_t B, const float* gout, float gw, float* dmu,
+                        float* dlogvar, mirror_stream_t stream);
+/* cluster term, losses/mirror_loss.py:114-119: scores [2B,P], rows 0..B-1 WSI and B..2B-1 RNA */
+int mirror_sym_kl_fwd(const float* scores, int32_t B, int32_t P, float* out, mirror_stream_t stream);
+int mirror_sym_kl_bwd(const float* scores, int32_t B, int32_t P, const float* gout, float gw, float* dscores_f32, void* dscores_bf16,
+                      mirror_stream_t stream);
+/* total = sum_i w_i*term_i, losses/mirror_loss.py:121-127 (weights are host floats) */
+int mirror_loss_combine(const float* terms5, const float* weights5_host, float* total, mirror_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

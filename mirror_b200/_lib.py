@@ -51,3 +51,58 @@ def lib():
 def check(rc: int, what: str):
     if rc != 0:
         raise RuntimeError(f"mirror_b200 {what} failed (code {rc}): {lib().mirror_last_error().decode()}")
+
+
+# ---- argument tables for the non-GEMM entry points (see include/mirror_b200.h) ----
+_P, _I32, _I64, _F, _U64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_uint64
+SIGNATURES = {
+    "mirror_gemm_bf16": [_P, _P],
+    "mirror_gemm_bf16_simt": [_P, _P],
+    "mirror_cast_f32_bf16": [_P, _I64, _I32, _I64, _P, _I32, _I64, _P],
+    "mirror_copy_rows_f32": [_P, _I64, _I64, _I32, _P, _I64, _P],
+    "mirror_axpy_f32": [_P, _P, _I64, _F, _P],
+    "mirror_act_fwd": [_P, _I64, _I32, _F, _U64, _P, _P, _P],
+    "mirror_act_bwd": [_P, _I64, _I64, _P, _I64, _I64, _I32, _I32, _I32, _I32, _F, _U64, _P, _I64, _I64, _P, _I64, _I64, _P],
+    "mirror_wsi_assemble_fwd": [_P, _P, _I32, _I32, _I32, _I32, _P],
+    "mirror_wsi_embed_bwd": [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P],
+    "mirror_rank_mask": [_P, _I32, _I32, _I32, _P, _P],
+    "mirror_mask_pos_fwd": [_P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P],
+    "mirror_mask_pos_bwd": [_P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P],
+    "mirror_landmark_fwd": [_P, _P, _I32, _I32, _I32, _I32, _I32, _P],
+    "mirror_dqkv_finish": [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P],
+    "mirror_colsum": [_P, _I32, _I64, _I32, _I64, _P, _P],
+    "mirror_reparam_fwd": [_P, _P, _P, _I64, _P, _P, _P],
+    "mirror_reparam_bwd": [_P, _P, _P, _I64, _P, _P, _P],
+    "mirror_layernorm_fwd": [_P, _P, _P, _F, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "mirror_layernorm_bwd": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "mirror_softmax_fwd": [_P, _I64, _I32, _P, _P, _P],
+    "mirror_softmax_bwd": [_P, _P, _I64, _I32, _F, _P, _P, _P],
+    "mirror_l2norm_fwd": [_P, _I64, _I32, _I32, _F, _P, _P, _I64, _P, _P],
+    "mirror_l2norm_bwd": [_P, _I64, _P, _I64, _P, _I32, _I32, _P, _I64, _I32, _P],
+    "mirror_res_conv_fwd": [_P, _P, _I32, _I32, _I32, _P, _P],
+    "mirror_res_conv_bwd": [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P],
+    "mirror_pinv_init": [_P, _I32, _I32, _P, _P, _P, _P],
+    "mirror_pinv_init_bwd": [_P, _P, _I32, _I32, _P, _P, _I32, _P],
+    "mirror_ppeg_fwd": [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P],
+    "mirror_ppeg_bwd": [_P, _P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "mirror_rna_attn_fwd": [_P, _I32, _I32, _P, _P, _P],
+    "mirror_rna_attn_bwd": [_P, _P, _I32, _I32, _P, _P, _P],
+    "mirror_clip_loss_fwd": [_P, _I32, _P, _F, _F, _P, _P, _P, _P],
+    "mirror_clip_loss_bwd": [_P, _I32, _P, _F, _F, _P, _P, _P, _P, _P, _P],
+    "mirror_masked_mse_fwd": [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P],
+    "mirror_masked_mse_bwd": [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _F, _P, _I64, _I32, _P, _I64, _I32, _P],
+    "mirror_gauss_kl_fwd": [_P, _P, _I64, _I32, _P, _P],
+    "mirror_gauss_kl_bwd": [_P, _P, _I64, _I32, _P, _F, _P, _P, _P],
+    "mirror_sym_kl_fwd": [_P, _I32, _I32, _P, _P],
+    "mirror_sym_kl_bwd": [_P, _I32, _I32, _P, _F, _P, _P, _P],
+    "mirror_loss_combine": [_P, _P, _P, _P],
+}
+EXPORTS = ["mirror_last_error", "mirror_abi_version", "mirror_device_supported"] + list(SIGNATURES)
+
+
+def fn(name):
+    f = getattr(lib(), name)
+    if f.argtypes is None:
+        f.argtypes = SIGNATURES[name]
+        f.restype = ctypes.c_int
+    return f

@@ -39,6 +39,17 @@ __global__ void cast_vec_kernel(const float4* __restrict__ src, uint4* __restric
   }
 }
 
+// strided 2-D copy (gathers e.g. the cls rows of [B,N+1,E] into a dense [B,E] block)
+__global__ void copy_rows_kernel(const float* __restrict__ src, long long lds, long long rows, int cols, float* __restrict__ dst,
+                                 long long ldd) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    dst[r * ldd + c] = src[r * lds + c];
+  }
+}
+
 __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n, float alpha) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] += alpha * src[i];
@@ -56,24 +67,26 @@ __global__ void act_fwd_kernel(const float* __restrict__ pre, long long n, int a
     if (o32) o32[i] = v;
   }
 }
-// dx = dy * dropmask * act'(pre); rows x cols with independent row strides so that padded layouts work.
-__global__ void act_bwd_kernel(const float* __restrict__ dy, long long ld_dy, const float* __restrict__ pre,
-                               long long ld_pre, long long rows, int cols, int act, float drop_p, float drop_scale,
-                               uint64_t seed, bf16* __restrict__ o16, long long ld16, float* __restrict__ o32,
-                               long long ld32) {
-  const long long total = rows * cols;
+// dx = dy * dropmask * act'(pre) on [B,T,C] views with independent batch / row strides (padded layouts).
+__global__ void act_bwd_kernel(const float* __restrict__ dy, long long bs_dy, long long ld_dy, const float* __restrict__ pre,
+                               long long bs_pre, long long ld_pre, int B, int T, int C, int act, float drop_p, float drop_scale,
+                               uint64_t seed, bf16* __restrict__ o16, long long bs16, long long ld16, float* __restrict__ o32,
+                               long long bs32, long long ld32) {
+  const long long total = (long long)B * T * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / cols;
-    const int c = (int)(i - r * cols);
-    float g = dy[r * ld_dy + c];
+    const int c = (int)(i % C);
+    const long long bt = i / C;
+    const int t = (int)(bt % T);
+    const long long b = bt / T;
+    float g = dy[b * bs_dy + t * ld_dy + c];
     if (drop_p > 0.f) g = hash_u01(seed, (uint64_t)i) >= drop_p ? g * drop_scale : 0.f;
     if (act != MIRROR_ACT_NONE) {
-      const float x = pre[r * ld_pre + c];
+      const float x = pre[b * bs_pre + t * ld_pre + c];
       if (act == MIRROR_ACT_RELU) g = x > 0.f ? g : 0.f;
       else g *= gelu_erf_grad(x);
     }
-    if (o16) o16[r * ld16 + c] = __float2bfloat16(g);
-    if (o32) o32[r * ld32 + c] = g;
+    if (o16) o16[b * bs16 + t * ld16 + c] = __float2bfloat16(g);
+    if (o32) o32[b * bs32 + t * ld32 + c] = g;
   }
 }
 
@@ -90,23 +103,30 @@ __global__ void assemble_fwd_kernel(float* __restrict__ h, const float* __restri
     else hb[(long long)(N + j) * E + e] = hb[(long long)j * E + e];
   }
 }
-// dh[b,1+j] += dh[b,1+N+j];  dcls[e] += sum_b dh[b,0,e]
-__global__ void assemble_bwd_kernel(float* __restrict__ dh, float* __restrict__ dcls, int B, int N, int add, int E) {
-  const int S = 1 + N + add;
-  const long long total = (long long)(1 + add) * E;
+// dpre[b,j,:] = relu'(h[b,1+j,:]) * (dh[b,1+j,:] + (j<add ? dh[b,1+N+j,:] : 0));  dcls[e] += sum_b dh[b,0,e]
+__global__ void wsi_embed_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ h, int B, int N, int add, int E,
+                                     bf16* __restrict__ dpre, float* __restrict__ dcls) {
+  const int S = 1 + N + add, E2 = E / 2;
+  const long long total = (long long)B * N * E2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int e = (int)(i % E);
-    const int j = (int)(i / E);
-    if (j == 0) {
-      float s = 0.f;
-      for (int b = 0; b < B; ++b) s += dh[(long long)b * S * E + e];
-      dcls[e] += s;
-    } else {
-      for (int b = 0; b < B; ++b) {
-        float* hb = dh + (long long)b * S * E;
-        hb[(long long)j * E + e] += hb[(long long)(N + j) * E + e];
-      }
+    const int e = 2 * (int)(i % E2);
+    const long long bj = i / E2;
+    const int j = (int)(bj % N);
+    const long long b = bj / N;
+    const long long o = (b * S + 1 + j) * E + e;
+    float2 g = *reinterpret_cast<const float2*>(dh + o);
+    if (j < add) {
+      const float2 w = *reinterpret_cast<const float2*>(dh + (b * S + 1 + N + j) * E + e);
+      g.x += w.x;
+      g.y += w.y;
     }
+    const float2 y = *reinterpret_cast<const float2*>(h + o);
+    *reinterpret_cast<__nv_bfloat162*>(dpre + bj * E + e) = __floats2bfloat162_rn(y.x > 0.f ? g.x : 0.f, y.y > 0.f ? g.y : 0.f);
+  }
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dh[(long long)b * S * E + e];
+    dcls[e] += s;
   }
 }
 
@@ -227,9 +247,12 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long rows, int cols,
 
 // z = mu + exp(0.5*logvar)*eps   (models/mirror.py:830-833)
 __global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ eps,
-                                   long long n, bf16* __restrict__ z16) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    z16[i] = __float2bfloat16(mu[i] + __expf(0.5f * lv[i]) * eps[i]);
+                                   long long n, bf16* __restrict__ z16, float* __restrict__ z32) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float z = mu[i] + __expf(0.5f * lv[i]) * eps[i];
+    if (z16) z16[i] = __float2bfloat16(z);
+    if (z32) z32[i] = z;
+  }
 }
 // dmu += dz ; dlv += dz * eps * 0.5 * exp(0.5*logvar)
 __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ lv, const float* __restrict__ eps,
@@ -263,6 +286,14 @@ extern "C" int mirror_cast_f32_bf16(const float* src, int64_t rows, int32_t cols
   return 0;
 }
 
+extern "C" int mirror_copy_rows_f32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd,
+                                    mirror_stream_t stream) {
+  MB_CHECK_ARG(src && dst && rows > 0 && cols > 0, "copy_rows: bad args");
+  copy_rows_kernel<<<grid_for(rows * (long long)cols, 256), 256, 0, STREAM>>>(src, lds, rows, cols, dst, ldd);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int mirror_axpy_f32(float* dst, const float* src, int64_t n, float alpha, mirror_stream_t stream) {
   MB_CHECK_ARG(dst && src && n >= 0, "axpy: bad args");
   if (n == 0) return 0;
@@ -280,14 +311,14 @@ extern "C" int mirror_act_fwd(const float* pre, int64_t n, int32_t act, float dr
   return 0;
 }
 
-extern "C" int mirror_act_bwd(const float* dy, int64_t ld_dy, const float* pre, int64_t ld_pre, int64_t rows, int32_t cols,
-                              int32_t act, float drop_p, uint64_t seed, void* out_bf16, int64_t ld16, float* out_f32,
-                              int64_t ld32, mirror_stream_t stream) {
-  MB_CHECK_ARG(dy && rows > 0 && cols > 0 && (out_bf16 || out_f32) && (act == 0 || pre) && drop_p >= 0.f && drop_p < 1.f,
+extern "C" int mirror_act_bwd(const float* dy, int64_t bs_dy, int64_t ld_dy, const float* pre, int64_t bs_pre, int64_t ld_pre,
+                              int32_t B, int32_t T, int32_t C, int32_t act, float drop_p, uint64_t seed, void* out_bf16,
+                              int64_t bs16, int64_t ld16, float* out_f32, int64_t bs32, int64_t ld32, mirror_stream_t stream) {
+  MB_CHECK_ARG(dy && B > 0 && T > 0 && C > 0 && (out_bf16 || out_f32) && (act == 0 || pre) && drop_p >= 0.f && drop_p < 1.f,
                "act_bwd: bad args");
-  act_bwd_kernel<<<grid_for(rows * (long long)cols, 256), 256, 0, STREAM>>>(
-      dy, ld_dy, pre, ld_pre, rows, cols, act, drop_p, 1.f / (1.f - drop_p), seed, reinterpret_cast<bf16*>(out_bf16), ld16,
-      out_f32, ld32);
+  act_bwd_kernel<<<grid_for((long long)B * T * C, 256), 256, 0, STREAM>>>(
+      dy, bs_dy, ld_dy, pre, bs_pre, ld_pre, B, T, C, act, drop_p, 1.f / (1.f - drop_p), seed, reinterpret_cast<bf16*>(out_bf16),
+      bs16, ld16, out_f32, bs32, ld32);
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -299,10 +330,11 @@ extern "C" int mirror_wsi_assemble_fwd(float* h, const float* cls, int32_t B, in
   MB_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int mirror_wsi_assemble_bwd(float* dh, float* dcls, int32_t B, int32_t N, int32_t add, int32_t E,
-                                       mirror_stream_t stream) {
-  MB_CHECK_ARG(dh && dcls && B > 0 && N > 0 && add >= 0 && add <= N && E > 0, "assemble_bwd: bad args");
-  assemble_bwd_kernel<<<grid_for((long long)(1 + add) * E, 128), 128, 0, STREAM>>>(dh, dcls, B, N, add, E);
+extern "C" int mirror_wsi_embed_bwd(const float* dh, const float* h, int32_t B, int32_t N, int32_t add, int32_t E, void* dpre_bf16,
+                                    float* dcls, mirror_stream_t stream) {
+  MB_CHECK_ARG(dh && h && dpre_bf16 && dcls && B > 0 && N > 0 && add >= 0 && add <= N && E % 2 == 0, "wsi_embed_bwd: bad args");
+  wsi_embed_bwd_kernel<<<grid_for((long long)B * N * E / 2, 256), 256, 0, STREAM>>>(dh, h, B, N, add, E,
+                                                                                 reinterpret_cast<bf16*>(dpre_bf16), dcls);
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -370,10 +402,10 @@ extern "C" int mirror_colsum(const void* x, int32_t is_bf16, int64_t rows, int32
   return 0;
 }
 
-extern "C" int mirror_reparam_fwd(const float* mu, const float* logvar, const float* eps, int64_t n, void* z_bf16,
+extern "C" int mirror_reparam_fwd(const float* mu, const float* logvar, const float* eps, int64_t n, void* z_bf16, float* z_f32,
                                   mirror_stream_t stream) {
-  MB_CHECK_ARG(mu && logvar && eps && z_bf16 && n > 0, "reparam_fwd: bad args");
-  reparam_fwd_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(mu, logvar, eps, n, reinterpret_cast<bf16*>(z_bf16));
+  MB_CHECK_ARG(mu && logvar && eps && (z_bf16 || z_f32) && n > 0, "reparam_fwd: bad args");
+  reparam_fwd_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(mu, logvar, eps, n, reinterpret_cast<bf16*>(z_bf16), z_f32);
   MB_LAUNCH_CHECK();
   return 0;
 }

@@ -21,6 +21,7 @@ constexpr int kAccStages = 2;
 struct KParams {
   Epi e;
   int K, batch1, batch2, tiles_m, tiles_n, split_k;
+  int a_b1, a_b2, b_b1, b_b2;  // 0 where an operand is broadcast along that batch dim (batch stride 0), else 1
 };
 
 template <int BN>
@@ -185,15 +186,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint8_t* b = sB + stage * C::B_BYTES;
           if (A_MN) {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) tma_load_4d(&tmA, &full[stage], a + i * (BK * 128), m0 + i * 64, kb * BK, b1, b2);
+            for (int i = 0; i < BM / 64; ++i) tma_load_4d(&tmA, &full[stage], a + i * (BK * 128), m0 + i * 64, kb * BK, b1 * p.a_b1, b2 * p.a_b2);
           } else {
-            tma_load_4d(&tmA, &full[stage], a, kb * BK, m0, b1, b2);
+            tma_load_4d(&tmA, &full[stage], a, kb * BK, m0, b1 * p.a_b1, b2 * p.a_b2);
           }
           if (B_MN) {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_4d(&tmB, &full[stage], b + i * (BK * 128), n0 + i * 64, kb * BK, b1, b2);
+            for (int i = 0; i < BN / 64; ++i) tma_load_4d(&tmB, &full[stage], b + i * (BK * 128), n0 + i * 64, kb * BK, b1 * p.b_b1, b2 * p.b_b2);
           } else {
-            tma_load_4d(&tmB, &full[stage], b, kb * BK, n0, b1, b2);
+            tma_load_4d(&tmB, &full[stage], b, kb * BK, n0, b1 * p.b_b1, b2 * p.b_b2);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -418,10 +419,17 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
   p.tiles_m = (g->M + BM - 1) / BM;
   p.tiles_n = (g->N + BN - 1) / BN;
   p.split_k = g->split_k > 1 ? g->split_k : 1;
+  // a batch stride of 0 broadcasts that operand (e.g. one weight matrix for every slide)
+  p.a_b1 = (g->batch1 > 1 && g->a_bs1 == 0) ? 0 : 1;
+  p.a_b2 = (g->batch2 > 1 && g->a_bs2 == 0) ? 0 : 1;
+  p.b_b1 = (g->batch1 > 1 && g->b_bs1 == 0) ? 0 : 1;
+  p.b_b2 = (g->batch2 > 1 && g->b_bs2 == 0) ? 0 : 1;
   CUtensorMap tmA, tmB;
-  rc = make_operand_map(&tmA, g->a, g->a_mn_major, g->M, g->K, g->lda, g->a_bs1, g->batch1, g->a_bs2, g->batch2, BM);
+  rc = make_operand_map(&tmA, g->a, g->a_mn_major, g->M, g->K, g->lda, g->a_bs1, p.a_b1 ? g->batch1 : 1, g->a_bs2,
+                        p.a_b2 ? g->batch2 : 1, BM);
   if (rc) return rc;
-  rc = make_operand_map(&tmB, g->b, g->b_mn_major, g->N, g->K, g->ldb, g->b_bs1, g->batch1, g->b_bs2, g->batch2, BN);
+  rc = make_operand_map(&tmB, g->b, g->b_mn_major, g->N, g->K, g->ldb, g->b_bs1, p.b_b1 ? g->batch1 : 1, g->b_bs2,
+                        p.b_b2 ? g->batch2 : 1, BN);
   if (rc) return rc;
   const int vec = epi_vec_ok(g) ? 1 : 0;
   const int key = (BN == 256 ? 4 : 0) | (g->a_mn_major ? 2 : 0) | (g->b_mn_major ? 1 : 0);

@@ -1,0 +1,300 @@
+// Loss reductions of the MIRROR step (losses/mirror_loss.py:37-135, losses/info_nce.py:144-164).
+// Scalars (losses, the temperature scale, upstream gradients) live in DEVICE memory so that no entry
+// point forces a host synchronisation.
+#include "common.cuh"
+
+namespace mb {
+namespace {
+
+// ------------------------------------------------------------------ contrastive (ClipLoss / InfoNCE)
+// raw: [B,B] f32 dot products W.R^T (unscaled); logits = s*raw with s = *scale.
+// row_lse[i] = logsumexp_j logits[i,j];  col_lse[j] = logsumexp_i logits[i,j].   One warp per row / thread per column.
+__global__ void clip_row_lse_kernel(const float* __restrict__ raw, int B, const float* __restrict__ scale, float* __restrict__ row_lse) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= B) return;
+  const float s = *scale;
+  const float* r = raw + (long long)i * B;
+  float mx = -INFINITY;
+  for (int j = lane; j < B; j += 32) mx = fmaxf(mx, s * r[j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < B; j += 32) sum += __expf(s * r[j] - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) row_lse[i] = mx + __logf(sum);
+}
+__global__ void clip_col_lse_kernel(const float* __restrict__ raw, int B, const float* __restrict__ scale, float* __restrict__ col_lse) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= B) return;
+  const float s = *scale;
+  float mx = -INFINITY, sum = 0.f;
+  for (int i = 0; i < B; ++i) {  // online max/sum; loads coalesced across the warp
+    const float v = s * raw[(long long)i * B + j];
+    if (v > mx) {
+      sum = sum * __expf(mx - v) + 1.f;
+      mx = v;
+    } else {
+      sum += __expf(v - mx);
+    }
+  }
+  col_lse[j] = mx + __logf(sum);
+}
+// loss = mean_i( wr*(row_lse_i - l_ii) + wc*(col_lse_i - l_ii) )      (wr=wc=0.5 symmetric; wr=1,wc=0 one-sided)
+__global__ void clip_loss_kernel(const float* __restrict__ raw, int B, const float* __restrict__ scale,
+                                 const float* __restrict__ row_lse, const float* __restrict__ col_lse, float wr, float wc,
+                                 float* __restrict__ loss) {
+  __shared__ float sh[32];
+  const float s = *scale;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float d = s * raw[(long long)i * B + i];
+    acc += wr * (row_lse[i] - d) + wc * (col_lse[i] - d);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) *loss = acc / B;
+}
+// G[i,j] = g * s * ( (wr*e^{l-rl_i} + wc*e^{l-cl_j}) - (wr+wc)*[i==j] ) / B   as bf16 (operand of dW = G R, dR = G^T W)
+// dscale += sum_ij (G/s) * raw
+__global__ void clip_grad_kernel(const float* __restrict__ raw, int B, const float* __restrict__ scale,
+                                 const float* __restrict__ row_lse, const float* __restrict__ col_lse, float wr, float wc,
+                                 const float* __restrict__ gout, bf16* __restrict__ G, float* __restrict__ dscale) {
+  __shared__ float sh[32];
+  const float s = *scale, g = *gout / B;
+  float acc = 0.f;
+  const long long total = (long long)B * B;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / B), j = (int)(idx % B);
+    const float r = raw[idx], l = s * r;
+    float p = wr * __expf(l - row_lse[i]);
+    if (wc != 0.f) p += wc * __expf(l - col_lse[j]);
+    if (i == j) p -= wr + wc;
+    p *= g;
+    acc += p * r;
+    G[idx] = __float2bfloat16(p * s);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0 && dscale) atomicAdd(dscale, acc);
+}
+
+// ------------------------------------------------------------------ masked MSE (retention losses)
+// scratch[0] += sum mask[row] * (a-b)^2 / E ; scratch[1] += sum mask[row]     rows = B*T
+__global__ void masked_mse_fwd_kernel(const float* __restrict__ a, long long a_bs, const float* __restrict__ b, long long b_bs,
+                                      const float* __restrict__ mask, int B, int T, int E, float* __restrict__ scratch) {
+  __shared__ float sh[32];
+  const long long total = (long long)B * T * E;
+  float num = 0.f, den = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % E);
+    const long long row = i / E;
+    const int t = (int)(row % T);
+    const long long bb = row / T;
+    const float m = mask[row];
+    if (e == 0) den += m;
+    if (m != 0.f) {
+      const float d = a[bb * a_bs + (long long)t * E + e] - b[bb * b_bs + (long long)t * E + e];
+      num += m * d * d;
+    }
+  }
+  num = block_sum(num, sh);
+  den = block_sum(den, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(scratch, num / E);
+    atomicAdd(scratch + 1, den);
+  }
+}
+__global__ void ratio_kernel(const float* __restrict__ scratch, float* __restrict__ out) { *out = scratch[0] / scratch[1]; }
+// da (+)= g * mask * 2 (a-b) / (E * den) ; db (+)= -that
+__global__ void masked_mse_bwd_kernel(const float* __restrict__ a, long long a_bs, const float* __restrict__ b, long long b_bs,
+                                      const float* __restrict__ mask, int B, int T, int E, const float* __restrict__ scratch,
+                                      const float* __restrict__ gout, float gw, float* __restrict__ da, long long da_bs, int acc_a,
+                                      float* __restrict__ db, long long db_bs, int acc_b) {
+  const long long total = (long long)B * T * E;
+  const float k = *gout * gw * 2.f / (E * scratch[1]);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % E);
+    const long long row = i / E;
+    const int t = (int)(row % T);
+    const long long bb = row / T;
+    const float m = mask[row];
+    const float v = m != 0.f ? k * m * (a[bb * a_bs + (long long)t * E + e] - b[bb * b_bs + (long long)t * E + e]) : 0.f;
+    if (da) {
+      float* p = da + bb * da_bs + (long long)t * E + e;
+      *p = acc_a ? *p + v : v;
+    }
+    if (db) {
+      float* p = db + bb * db_bs + (long long)t * E + e;
+      *p = acc_b ? *p - v : -v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ Gaussian KL ("style" term)
+// out = 0.5/B * sum_{r,d} (exp(lv) + mu^2 - 1 - lv)   over R rows (both modalities stacked: R = 2B)
+__global__ void gauss_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, long long n, float inv_b,
+                                    float* __restrict__ out) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += __expf(lv[i]) + mu[i] * mu[i] - 1.f - lv[i];
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(out, 0.5f * inv_b * acc);
+}
+__global__ void gauss_kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, long long n, float inv_b,
+                                    const float* __restrict__ gout, float gw, float* __restrict__ dmu, float* __restrict__ dlv) {
+  const float k = *gout * gw * inv_b;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    dmu[i] += k * mu[i];
+    dlv[i] += k * 0.5f * (__expf(lv[i]) - 1.f);
+  }
+}
+
+// ------------------------------------------------------------------ symmetric KL over prototype scores ("cluster" term)
+// scores: [2B, P] (rows 0..B-1 WSI, B..2B-1 RNA).  out += 0.5/B * sum_p (r-w)(log r - log w) per pair.  One CTA per pair.
+__device__ __forceinline__ float block_lse(const float* __restrict__ x, int P, float* sh) {
+  float mx = -INFINITY;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) mx = fmaxf(mx, x[p]);
+  mx = block_max(mx, sh);
+  float s = 0.f;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) s += __expf(x[p] - mx);
+  s = block_sum(s, sh);
+  return mx + __logf(s);
+}
+__global__ void sym_kl_fwd_kernel(const float* __restrict__ scores, int B, int P, float* __restrict__ out) {
+  __shared__ float sh[32];
+  const float* w = scores + (long long)blockIdx.x * P;
+  const float* r = scores + (long long)(B + blockIdx.x) * P;
+  const float lw = block_lse(w, P, sh), lr = block_lse(r, P, sh);
+  float acc = 0.f;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const float a = w[p] - lw, b = r[p] - lr;
+    acc += (__expf(b) - __expf(a)) * (b - a);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(out, 0.5f * acc / B);
+}
+// d/d(lw_p) f = -w_p (lr_p - lw_p) - (r_p - w_p);  through log-softmax: ds = g_l - softmax * sum(g_l)
+__global__ void sym_kl_bwd_kernel(const float* __restrict__ scores, int B, int P, const float* __restrict__ gout, float gw,
+                                  float* __restrict__ dscores32, bf16* __restrict__ dscores16) {
+  __shared__ float sh[32];
+  const float* w = scores + (long long)blockIdx.x * P;
+  const float* r = scores + (long long)(B + blockIdx.x) * P;
+  const float lw = block_lse(w, P, sh), lr = block_lse(r, P, sh);
+  float sw = 0.f, sr = 0.f;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const float a = w[p] - lw, b = r[p] - lr;
+    const float pw = __expf(a), pr = __expf(b);
+    sw += -pw * (b - a) - (pr - pw);
+    sr += pr * (b - a) + (pr - pw);
+  }
+  sw = block_sum(sw, sh);
+  sr = block_sum(sr, sh);
+  const float k = *gout * gw * 0.5f / B;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const float a = w[p] - lw, b = r[p] - lr;
+    const float pw = __expf(a), pr = __expf(b);
+    const float gwv = k * ((-pw * (b - a) - (pr - pw)) - pw * sw);
+    const float grv = k * ((pr * (b - a) + (pr - pw)) - pr * sr);
+    const long long ow = (long long)blockIdx.x * P + p, orr = (long long)(B + blockIdx.x) * P + p;
+    if (dscores32) { dscores32[ow] = gwv; dscores32[orr] = grv; }
+    if (dscores16) { dscores16[ow] = __float2bfloat16(gwv); dscores16[orr] = __float2bfloat16(grv); }
+  }
+}
+
+// total = sum_i w_i * term_i
+__global__ void combine_kernel(const float* __restrict__ terms, float w0, float w1, float w2, float w3, float w4,
+                               float* __restrict__ total) {
+  *total = w0 * terms[0] + w1 * terms[1] + w2 * terms[2] + w3 * terms[3] + w4 * terms[4];
+}
+
+}  // namespace
+}  // namespace mb
+
+using namespace mb;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+static int ew_grid(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)num_sms() * 8;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+/* raw: [B,B] unscaled similarities; scale: device scalar; row_lse/col_lse: [B]; loss: device scalar */
+extern "C" int mirror_clip_loss_fwd(const float* raw, int32_t B, const float* scale, float w_row, float w_col, float* row_lse,
+                                    float* col_lse, float* loss, mirror_stream_t stream) {
+  MB_CHECK_ARG(raw && scale && row_lse && col_lse && loss && B > 0, "clip_loss_fwd: bad args");
+  clip_row_lse_kernel<<<(B + 7) / 8, 256, 0, STREAM>>>(raw, B, scale, row_lse);
+  MB_LAUNCH_CHECK();
+  clip_col_lse_kernel<<<(B + 127) / 128, 128, 0, STREAM>>>(raw, B, scale, col_lse);
+  MB_LAUNCH_CHECK();
+  clip_loss_kernel<<<1, 256, 0, STREAM>>>(raw, B, scale, row_lse, col_lse, w_row, w_col, loss);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mirror_clip_loss_bwd(const float* raw, int32_t B, const float* scale, float w_row, float w_col,
+                                    const float* row_lse, const float* col_lse, const float* gout, void* G_bf16, float* dscale,
+                                    mirror_stream_t stream) {
+  MB_CHECK_ARG(raw && scale && row_lse && col_lse && gout && G_bf16 && B > 0, "clip_loss_bwd: bad args");
+  clip_grad_kernel<<<ew_grid((long long)B * B, 256), 256, 0, STREAM>>>(raw, B, scale, row_lse, col_lse, w_row, w_col, gout,
+                                                                       reinterpret_cast<bf16*>(G_bf16), dscale);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+/* scratch: 2 floats, zeroed here */
+extern "C" int mirror_masked_mse_fwd(const float* a, int64_t a_bs, const float* b, int64_t b_bs, const float* mask, int32_t B,
+                                     int32_t T, int32_t E, float* scratch, float* out, mirror_stream_t stream) {
+  MB_CHECK_ARG(a && b && mask && scratch && out && B > 0 && T > 0 && E > 0, "masked_mse_fwd: bad args");
+  MB_CUDA(cudaMemsetAsync(scratch, 0, 8, STREAM));
+  masked_mse_fwd_kernel<<<ew_grid((long long)B * T * E, 256 * 4), 256, 0, STREAM>>>(a, a_bs, b, b_bs, mask, B, T, E, scratch);
+  MB_LAUNCH_CHECK();
+  ratio_kernel<<<1, 1, 0, STREAM>>>(scratch, out);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mirror_masked_mse_bwd(const float* a, int64_t a_bs, const float* b, int64_t b_bs, const float* mask, int32_t B,
+                                     int32_t T, int32_t E, const float* scratch, const float* gout, float gw, float* da,
+                                     int64_t da_bs, int32_t acc_a, float* db, int64_t db_bs, int32_t acc_b, mirror_stream_t stream) {
+  MB_CHECK_ARG(a && b && mask && scratch && gout && (da || db) && B > 0 && T > 0 && E > 0, "masked_mse_bwd: bad args");
+  masked_mse_bwd_kernel<<<ew_grid((long long)B * T * E, 256 * 2), 256, 0, STREAM>>>(a, a_bs, b, b_bs, mask, B, T, E, scratch, gout,
+                                                                                  gw, da, da_bs, acc_a, db, db_bs, acc_b);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_gauss_kl_fwd(const float* mu, const float* logvar, int64_t n, int32_t B, float* out, mirror_stream_t stream) {
+  MB_CHECK_ARG(mu && logvar && out && n > 0 && B > 0, "gauss_kl_fwd: bad args");
+  MB_CUDA(cudaMemsetAsync(out, 0, 4, STREAM));
+  gauss_kl_fwd_kernel<<<ew_grid(n, 256), 256, 0, STREAM>>>(mu, logvar, n, 1.f / B, out);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mirror_gauss_kl_bwd(const float* mu, const float* logvar, int64_t n, int32_t B, const float* gout, float gw,
+                                   float* dmu, float* dlogvar, mirror_stream_t stream) {
+  MB_CHECK_ARG(mu && logvar && gout && dmu && dlogvar && n > 0 && B > 0, "gauss_kl_bwd: bad args");
+  gauss_kl_bwd_kernel<<<ew_grid(n, 256), 256, 0, STREAM>>>(mu, logvar, n, 1.f / B, gout, gw, dmu, dlogvar);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_sym_kl_fwd(const float* scores, int32_t B, int32_t P, float* out, mirror_stream_t stream) {
+  MB_CHECK_ARG(scores && out && B > 0 && P > 0, "sym_kl_fwd: bad args");
+  MB_CUDA(cudaMemsetAsync(out, 0, 4, STREAM));
+  sym_kl_fwd_kernel<<<B, 256, 0, STREAM>>>(scores, B, P, out);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mirror_sym_kl_bwd(const float* scores, int32_t B, int32_t P, const float* gout, float gw, float* dscores_f32,
+                                 void* dscores_bf16, mirror_stream_t stream) {
+  MB_CHECK_ARG(scores && gout && (dscores_f32 || dscores_bf16) && B > 0 && P > 0, "sym_kl_bwd: bad args");
+  sym_kl_bwd_kernel<<<B, 256, 0, STREAM>>>(scores, B, P, gout, gw, dscores_f32, reinterpret_cast<bf16*>(dscores_bf16));
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_loss_combine(const float* terms5, const float* weights5_host, float* total, mirror_stream_t stream) {
+  MB_CHECK_ARG(terms5 && weights5_host && total, "loss_combine: bad args");
+  combine_kernel<<<1, 1, 0, STREAM>>>(terms5, weights5_host[0], weights5_host[1], weights5_host[2], weights5_host[3],
+                                     weights5_host[4], total);
+  MB_LAUNCH_CHECK();
+  return 0;
+}

@@ -99,3 +99,392 @@ def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NON
     fn = _lib.lib().mirror_gemm_bf16_simt if simt else _lib.lib().mirror_gemm_bf16
     _lib.check(fn(ctypes.byref(g), _stream()), "gemm")
     LAUNCHES[0] += 1
+
+
+# =====================================================================================
+# non-GEMM entry points.  Every function below has a same-named re-statement in
+# tests/emu_backend.py (CPU tests only).
+# =====================================================================================
+import functools
+
+
+def _op(f):
+    @functools.wraps(f)
+    def wrapper(*a, **k):
+        if _TEST_BACKEND is not None:
+            return getattr(_TEST_BACKEND, f.__name__)(*a, **k)
+        return f(*a, **k)
+    return wrapper
+
+
+def _p(t, dtype=None):
+    if t is None:
+        return None
+    _cuda(t, dtype)
+    return t.data_ptr()
+
+
+def _call(name, *args, launches=1):
+    _lib.check(_lib.fn(name)(*args, _stream()), name)
+    LAUNCHES[0] += launches
+
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+def _contig(t):
+    if not t.is_contiguous():
+        raise ValueError("expected a contiguous tensor")
+    return t
+
+
+@_op
+def cast_bf16(src, cols_out=None):
+    """[.., cols] f32 (contiguous, or a 2-D view with unit column stride) -> bf16 [.., cols_out] zero padded."""
+    cols = src.shape[-1]
+    cols_out = cols_out or cols
+    if src.dim() == 2 and src.stride(1) == 1:
+        lds = src.stride(0)
+    else:
+        _contig(src)
+        lds = cols
+    rows = src.numel() // cols
+    dst = torch.empty(*src.shape[:-1], cols_out, device=src.device, dtype=BF16)
+    _call("mirror_cast_f32_bf16", _p(src, F32), rows, cols, lds, _p(dst), cols_out, cols_out)
+    return dst
+
+
+@_op
+def copy_rows_(src, dst):
+    """dst[r,:] = src[r,:] for 2-D f32 views with unit column stride."""
+    rows, cols = src.shape
+    assert dst.shape == src.shape and src.stride(1) == 1 and dst.stride(1) == 1
+    _call("mirror_copy_rows_f32", _p(src, F32), src.stride(0), rows, cols, _p(dst, F32), dst.stride(0))
+    return dst
+
+
+@_op
+def axpy_(dst, src, alpha=1.0):
+    _contig(dst), _contig(src)
+    assert dst.numel() == src.numel()
+    _call("mirror_axpy_f32", _p(dst, F32), _p(src, F32), dst.numel(), alpha)
+    return dst
+
+
+@_op
+def act_fwd(pre, act, drop_p=0.0, seed=0, want_bf16=True, want_f32=False):
+    _contig(pre)
+    o16 = torch.empty_like(pre, dtype=BF16) if want_bf16 else None
+    o32 = torch.empty_like(pre) if want_f32 else None
+    _call("mirror_act_fwd", _p(pre, F32), pre.numel(), act, drop_p, seed, _p(o16), _p(o32))
+    return o16, o32
+
+
+def _v3(t):
+    """(ptr, batch stride, row stride) of a [B,T,C] view with unit stride on C."""
+    if t is None:
+        return None, 0, 0
+    assert t.dim() == 3 and t.stride(2) == 1
+    return t.data_ptr(), t.stride(0), t.stride(1)
+
+
+@_op
+def act_bwd(dy, pre, act, drop_p=0.0, seed=0, out16=None, out32=None):
+    """dy, pre, outputs: [B,T,C] views with unit stride on C (batch / row strides free)."""
+    B, T, C = dy.shape
+    for t in (pre, out16, out32):
+        assert t is None or tuple(t.shape) == (B, T, C)
+    _cuda(dy, F32)
+    a, b, c, d = _v3(dy), _v3(pre), _v3(out16), _v3(out32)
+    _call("mirror_act_bwd", a[0], a[1], a[2], b[0], b[1], b[2], B, T, C, act, drop_p, seed, c[0], c[1], c[2], d[0], d[1], d[2])
+
+
+@_op
+def wsi_assemble_fwd(h, cls, N, add):
+    B, S, E = h.shape
+    assert S == 1 + N + add
+    _call("mirror_wsi_assemble_fwd", _p(_contig(h), F32), _p(_contig(cls), F32), B, N, add, E)
+
+
+@_op
+def wsi_embed_bwd(dh, h, N, add, dcls):
+    """-> dpre16 [B,N,E] (ReLU-masked gradient of the fc1 output incl. the wrap-around rows); dcls accumulated."""
+    B, S, E = dh.shape
+    dpre = torch.empty(B, N, E, device=dh.device, dtype=BF16)
+    _call("mirror_wsi_embed_bwd", _p(_contig(dh), F32), _p(_contig(h), F32), B, N, add, E, _p(dpre), _p(_contig(dcls), F32))
+    return dpre
+
+
+@_op
+def rank_mask(noise, keep):
+    B, N = noise.shape
+    mask = torch.empty(B, N, device=noise.device, dtype=F32)
+    _call("mirror_rank_mask", _p(_contig(noise), F32), B, N, keep, _p(mask))
+    return mask
+
+
+@_op
+def mask_pos_fwd_(r, mask, tok, tok_stride, pos, first):
+    """r: [B,T,E] f32, modified in place."""
+    B, T, E = r.shape
+    _call("mirror_mask_pos_fwd", _p(_contig(r), F32), _p(_contig(mask), F32), _p(tok, F32), tok_stride, _p(_contig(pos), F32), B, T, E, first)
+    return r
+
+
+@_op
+def mask_pos_bwd_(dy, mask, dtok, tok_stride, dpos, first):
+    B, T, E = dy.shape
+    _call("mirror_mask_pos_bwd", _p(_contig(dy), F32), _p(_contig(mask), F32), _p(dtok, F32), tok_stride, _p(_contig(dpos), F32), B, T, E, first)
+    return dy
+
+
+@_op
+def landmark_fwd(qkv, m, seg):
+    B, n, E3 = qkv.shape
+    lm = torch.empty(B, m, 2 * (E3 // 3), device=qkv.device, dtype=BF16)
+    _call("mirror_landmark_fwd", _p(_contig(qkv), BF16), _p(lm), B, n, m, seg, E3 // 3)
+    return lm
+
+
+@_op
+def dqkv_finish(dqkv32, dlm32, seg):
+    B, n, E3 = dqkv32.shape
+    m = dlm32.shape[1]
+    out = torch.empty(B, n, E3, device=dqkv32.device, dtype=BF16)
+    _call("mirror_dqkv_finish", _p(_contig(dqkv32), F32), _p(_contig(dlm32), F32), _p(out), B, n, m, seg, E3 // 3)
+    return out
+
+
+@_op
+def colsum_(x, out):
+    """out[c] += sum_r x[r,c]; x is a 2-D view with unit column stride (bf16 or f32)."""
+    rows, cols = x.shape
+    assert x.stride(1) == 1 and out.numel() == cols
+    _call("mirror_colsum", _p(x), int(x.dtype == BF16), rows, cols, x.stride(0), _p(out, F32))
+    return out
+
+
+@_op
+def reparam_fwd(mu, logvar, eps):
+    z = torch.empty_like(mu)
+    _call("mirror_reparam_fwd", _p(_contig(mu), F32), _p(_contig(logvar), F32), _p(_contig(eps), F32), mu.numel(), None, _p(z))
+    return z
+
+
+@_op
+def reparam_bwd_(dz, logvar, eps, dmu, dlogvar):
+    _call("mirror_reparam_bwd", _p(_contig(dz), F32), _p(logvar, F32), _p(eps, F32), dz.numel(), _p(dmu, F32), _p(dlogvar, F32))
+
+
+@_op
+def layernorm_fwd(x, gamma, beta, eps, n_out=None, pad=0, want_bf16=True, want_f32=False):
+    """x: [B,S,E] f32 -> (y16 [B,n_out,E], y32 [B,n_out,E], mean [B,S], rstd [B,S])."""
+    B, S, E = x.shape
+    n_out = n_out or S
+    y16 = torch.empty(B, n_out, E, device=x.device, dtype=BF16) if want_bf16 else None
+    y32 = torch.empty(B, n_out, E, device=x.device, dtype=F32) if want_f32 else None
+    mean = torch.empty(B, S, device=x.device, dtype=F32)
+    rstd = torch.empty(B, S, device=x.device, dtype=F32)
+    _call("mirror_layernorm_fwd", _p(_contig(x), F32), _p(gamma, F32), _p(beta, F32), eps, B, S, E, n_out, pad, _p(y16), _p(y32),
+          _p(mean), _p(rstd))
+    return y16, y32, mean, rstd
+
+
+@_op
+def layernorm_bwd(dy, x, gamma, mean, rstd, pad, dx, add, dgamma, dbeta):
+    """dy: [B,n_out,E] f32; dx: [B,S,E] f32 = (add or 0) + LN gradient; dgamma/dbeta accumulate."""
+    B, S, E = x.shape
+    _call("mirror_layernorm_bwd", _p(_contig(dy), F32), _p(_contig(x), F32), _p(gamma, F32), _p(mean), _p(rstd), B, S, E, dy.shape[1],
+          pad, _p(_contig(dx), F32), _p(add, F32), _p(dgamma, F32), _p(dbeta, F32))
+
+
+@_op
+def softmax_fwd(x, want_bf16=True, want_f32=False):
+    _contig(x)
+    cols = x.shape[-1]
+    y16 = torch.empty_like(x, dtype=BF16) if want_bf16 else None
+    y32 = torch.empty_like(x) if want_f32 else None
+    _call("mirror_softmax_fwd", _p(x, F32), x.numel() // cols, cols, _p(y16), _p(y32))
+    return y16, y32
+
+
+@_op
+def softmax_bwd(y16, dy, scale=1.0, want_bf16=True, want_f32=False):
+    _contig(y16), _contig(dy)
+    cols = dy.shape[-1]
+    d16 = torch.empty_like(dy, dtype=BF16) if want_bf16 else None
+    d32 = torch.empty_like(dy) if want_f32 else None
+    _call("mirror_softmax_bwd", _p(y16, BF16), _p(dy, F32), dy.numel() // cols, cols, scale, _p(d16), _p(d32))
+    return d16, d32
+
+
+@_op
+def l2norm_fwd(x, eps):
+    """x: [rows, cols] f32 view (unit column stride) -> (y32 contiguous, norm[rows])."""
+    rows, cols = x.shape
+    assert x.stride(1) == 1
+    y = torch.empty(rows, cols, device=x.device, dtype=F32)
+    norm = torch.empty(rows, device=x.device, dtype=F32)
+    _call("mirror_l2norm_fwd", _p(x, F32), x.stride(0), rows, cols, eps, None, _p(y), cols, _p(norm))
+    return y, norm
+
+
+@_op
+def l2norm_bwd(dy, x, norm):
+    rows, cols = x.shape
+    dx = torch.empty(rows, cols, device=x.device, dtype=F32)
+    _call("mirror_l2norm_bwd", _p(_contig(dy), F32), cols, _p(x, F32), x.stride(0), _p(norm), rows, cols, _p(dx), cols, 0)
+    return dx
+
+
+@_op
+def res_conv_fwd(qkv, w):
+    B, n, E3 = qkv.shape
+    out = torch.empty(B, n, E3 // 3, device=qkv.device, dtype=BF16)
+    _call("mirror_res_conv_fwd", _p(_contig(qkv), BF16), _p(_contig(w), F32), B, n, E3 // 3, _p(out))
+    return out
+
+
+@_op
+def res_conv_bwd_(dout16, qkv, w, dqkv32, dw):
+    B, n, E3 = qkv.shape
+    _call("mirror_res_conv_bwd", _p(_contig(dout16), BF16), _p(_contig(qkv), BF16), _p(_contig(w), F32), B, n, E3 // 3,
+          _p(_contig(dqkv32), F32), _p(_contig(dw), F32), launches=2)
+
+
+@_op
+def pinv_init(a2):
+    """a2: [B,h,m,m] f32 -> (z32, z16, scratch) with z0 = a2^T / (max rowsum * max colsum)."""
+    m = a2.shape[-1]
+    BH = a2.numel() // (m * m)
+    z32 = torch.empty_like(a2)
+    z16 = torch.empty_like(a2, dtype=BF16)
+    scratch = torch.empty(8, device=a2.device, dtype=F32)
+    _call("mirror_pinv_init", _p(_contig(a2), F32), BH, m, _p(scratch), _p(z32), _p(z16), launches=2)
+    return z32, z16, scratch
+
+
+@_op
+def pinv_init_bwd(gz0, z0_32, scratch, gx, accumulate):
+    m = gz0.shape[-1]
+    BH = gz0.numel() // (m * m)
+    _call("mirror_pinv_init_bwd", _p(_contig(gz0), F32), _p(_contig(z0_32), F32), BH, m, _p(scratch), _p(_contig(gx), F32),
+          int(accumulate), launches=2)
+
+
+@_op
+def ppeg_fwd(x, w7, w5, w3, b7, b5, b3, H):
+    B, S, E = x.shape
+    assert S == H * H + 1
+    wm = torch.empty(49, E, device=x.device, dtype=F32)
+    bm = torch.empty(E, device=x.device, dtype=F32)
+    y = torch.empty_like(x)
+    _call("mirror_ppeg_fwd", _p(_contig(x), F32), _p(_contig(w7), F32), _p(_contig(w5), F32), _p(_contig(w3), F32), _p(b7, F32),
+          _p(b5, F32), _p(b3, F32), B, H, E, _p(wm), _p(bm), _p(y), launches=2)
+    return y, wm
+
+
+@_op
+def ppeg_bwd(dy, x, wm, H, dw7, dw5, dw3, db7, db5, db3):
+    """returns dx; weight/bias gradients are ACCUMULATED into dw*, db*."""
+    B, S, E = x.shape
+    dx = torch.empty_like(x)
+    dwm = torch.empty(49, E, device=x.device, dtype=F32)
+    dbm = torch.empty(E, device=x.device, dtype=F32)
+    _call("mirror_ppeg_bwd", _p(_contig(dy), F32), _p(_contig(x), F32), _p(wm), B, H, E, _p(dx), 0, _p(dwm), _p(dbm), _p(dw7, F32),
+          _p(dw5, F32), _p(dw3, F32), _p(db7, F32), _p(db5, F32), _p(db3, F32), launches=3)
+    return dx
+
+
+@_op
+def rna_attn_fwd(qkv):
+    B, E3 = qkv.shape
+    out = torch.empty(B, E3 // 3, device=qkv.device, dtype=F32)
+    _call("mirror_rna_attn_fwd", _p(_contig(qkv), F32), B, E3 // 3, None, _p(out))
+    return out
+
+
+@_op
+def rna_attn_bwd(qkv, dout):
+    B, E3 = qkv.shape
+    dqkv = torch.empty_like(qkv)
+    _call("mirror_rna_attn_bwd", _p(_contig(qkv), F32), _p(_contig(dout), F32), B, E3 // 3, None, _p(dqkv))
+    return dqkv
+
+
+@_op
+def clip_loss_fwd(raw, scale, w_row, w_col):
+    B = raw.shape[0]
+    row = torch.empty(B, device=raw.device, dtype=F32)
+    col = torch.empty(B, device=raw.device, dtype=F32)
+    loss = torch.empty((), device=raw.device, dtype=F32)
+    _call("mirror_clip_loss_fwd", _p(_contig(raw), F32), B, _p(scale, F32), w_row, w_col, _p(row), _p(col), _p(loss), launches=3)
+    return loss, row, col
+
+
+@_op
+def clip_loss_bwd(raw, scale, w_row, w_col, row, col, gout, dscale):
+    """returns G (bf16 [B,B]) = d loss / d raw; dscale (0-d f32) is accumulated."""
+    B = raw.shape[0]
+    G = torch.empty(B, B, device=raw.device, dtype=BF16)
+    _call("mirror_clip_loss_bwd", _p(raw, F32), B, _p(scale, F32), w_row, w_col, _p(row), _p(col), _p(gout, F32), _p(G), _p(dscale))
+    return G
+
+
+def _bt_view(t, E):
+    """[B,T,E] view with unit stride on E and row stride E -> (ptr tensor, batch stride)."""
+    assert t.dim() == 3 and t.stride(2) == 1 and (t.stride(1) == E or t.shape[1] == 1)
+    return t.stride(0)
+
+
+@_op
+def masked_mse_fwd(a, b, mask):
+    """a, b: [B,T,E] f32 views (row stride E, free batch stride); mask [B,T] -> (loss 0-d, scratch[2])."""
+    B, T, E = a.shape
+    scratch = torch.empty(2, device=a.device, dtype=F32)
+    out = torch.empty((), device=a.device, dtype=F32)
+    _call("mirror_masked_mse_fwd", _p(a, F32), _bt_view(a, E), _p(b, F32), _bt_view(b, E), _p(_contig(mask), F32), B, T, E, _p(scratch),
+          _p(out), launches=2)
+    return out, scratch
+
+
+@_op
+def masked_mse_bwd(a, b, mask, scratch, gout, gw, da, acc_a, db, acc_b):
+    B, T, E = a.shape
+    _call("mirror_masked_mse_bwd", _p(a, F32), _bt_view(a, E), _p(b, F32), _bt_view(b, E), _p(mask, F32), B, T, E, _p(scratch), _p(gout, F32),
+          gw, _p(da, F32), _bt_view(da, E) if da is not None else 0, int(acc_a), _p(db, F32), _bt_view(db, E) if db is not None else 0,
+          int(acc_b))
+
+
+@_op
+def gauss_kl_fwd(mu, logvar, B):
+    out = torch.empty((), device=mu.device, dtype=F32)
+    _call("mirror_gauss_kl_fwd", _p(_contig(mu), F32), _p(_contig(logvar), F32), mu.numel(), B, _p(out))
+    return out
+
+
+@_op
+def gauss_kl_bwd_(mu, logvar, B, gout, gw, dmu, dlogvar):
+    _call("mirror_gauss_kl_bwd", _p(mu, F32), _p(logvar, F32), mu.numel(), B, _p(gout, F32), gw, _p(_contig(dmu), F32), _p(_contig(dlogvar), F32))
+
+
+@_op
+def sym_kl_fwd(scores, B):
+    out = torch.empty((), device=scores.device, dtype=F32)
+    _call("mirror_sym_kl_fwd", _p(_contig(scores), F32), B, scores.shape[1], _p(out))
+    return out
+
+
+@_op
+def sym_kl_bwd(scores, B, gout, gw):
+    d = torch.empty_like(scores)
+    _call("mirror_sym_kl_bwd", _p(scores, F32), B, scores.shape[1], _p(gout, F32), gw, _p(d), None)
+    return d
+
+
+@_op
+def loss_combine(terms5, weights):
+    total = torch.empty((), device=terms5.device, dtype=F32)
+    w = (ctypes.c_float * 5)(*weights)
+    _call("mirror_loss_combine", _p(_contig(terms5), F32), ctypes.cast(w, ctypes.c_void_p), _p(total))
+    return total

@@ -1,0 +1,473 @@
+"""B200-native MIRROR model — drop-in for the reference ``models/mirror.py``.
+
+Same public API (class names, constructor arguments and defaults, attribute
+names, ``state_dict`` keys and shapes, output tuple order) with
+all device arithmetic routed through the hand-written sm_100a kernels
+(``mirror_b200.ops`` / ``mirror_b200.kernels``).  ``nn.Module`` objects are used
+as *parameter containers* so that ``state_dict()`` is key-compatible with
+reference checkpoints (``tools/split_weights.py``, ``load_checkpoint``); their
+``forward`` methods are never called on the hot path.
+
+Reference lines are cited per class (paths relative to the reference checkout).
+Not supported (the reference never enables them for MIRROR): qk_norm,
+LayerScale init_values, DropPath > 0, pre_norm, attention dropout > 0.
+"""
+import logging
+import math
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import kernels as K
+from .. import ops
+
+_logger = logging.getLogger(__name__)
+
+try:  # the trainers resolve the model through timm's registry (train_mirror.py:689)
+    from timm.models import register_model  # type: ignore
+except Exception:  # timm absent (e.g. this image): keep a local registry with the same decorator shape
+    _REGISTRY = {}
+
+    def register_model(fn):
+        _REGISTRY[fn.__name__] = fn
+        return fn
+
+
+def _norm_eps(norm_layer) -> float:
+    """timm semantics (models/mirror.py:210): get_norm_layer(None) -> LayerNorm(eps=1e-6); 'layernorm' -> timm LayerNorm (1e-6)."""
+    if norm_layer is None or (isinstance(norm_layer, str) and norm_layer.replace("_", "").lower() == "layernorm"):
+        return 1e-6
+    raise NotImplementedError(f"norm layer {norm_layer!r}: only LayerNorm is implemented in the B200 path")
+
+
+def _check_gelu(act_layer):
+    if act_layer is None or (isinstance(act_layer, str) and act_layer.lower() == "gelu"):
+        return
+    raise NotImplementedError(f"activation {act_layer!r}: only (exact) GELU is implemented in the B200 path")
+
+
+class _Mlp(nn.Module):
+    """Parameter container with timm ``Mlp`` key names: fc1, norm (optional), fc2."""
+
+    def __init__(self, in_features, hidden_features, out_features, norm_eps: Optional[float] = None, drop: float = 0.0):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.norm = nn.LayerNorm(hidden_features, eps=norm_eps) if norm_eps is not None else nn.Identity()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = drop
+
+    def forward(self, x, x16=None, row_res=None, residual=None):
+        """[residual +] drop(fc2(norm(drop(GELU(fc1(x)))))) [+ row_res]  (timm Mlp order: fc1, act, drop1, norm, fc2, drop2)."""
+        p = self.drop if self.training else 0.0
+        y = ops.linear(x, self.fc1.weight, self.fc1.bias, x16=x16)
+        y = ops.activation(y, K.ACT_GELU, p)
+        y16 = None
+        if isinstance(self.norm, nn.LayerNorm):
+            y, y16 = ops.layer_norm(y, self.norm.weight, self.norm.bias, self.norm.eps)
+        return ops.linear(y, self.fc2.weight, self.fc2.bias, row_res=row_res, x16=y16, res=residual, drop_p=p)
+
+
+# ===========================================
+#  Transformer for Transcriptomics Data
+# ===========================================
+class Attention(nn.Module):
+    """models/mirror.py:50-102 (parameters qkv, proj)."""
+
+    def __init__(self, dim, num_heads=12, qkv_bias=True, proj_drop=0.0):
+        super().__init__()
+        assert dim % num_heads == 0, "dim should be divisible by num_heads"
+        assert num_heads == 12, "the RNA attention kernel is written for the reference's 12 chunks"
+        self.num_heads = num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = proj_drop
+
+    def forward(self, x, x16=None, residual=None):
+        """[residual +] proj_drop(proj(SDPA(qkv(x))))"""
+        qkv = ops.linear(x, self.qkv.weight, self.qkv.bias, x16=x16)
+        o = ops.RnaAttnFn.apply(qkv)
+        return ops.linear(o, self.proj.weight, self.proj.bias, res=residual, drop_p=self.proj_drop if self.training else 0.0)
+
+
+class Block(nn.Module):
+    """models/mirror.py:105-152: x += attn(LN(x)); x += mlp(LN(x))."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=True, proj_drop=0.0, norm_eps=1e-6):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=norm_eps)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, proj_drop=proj_drop)
+        self.norm2 = nn.LayerNorm(dim, eps=norm_eps)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio), dim, drop=proj_drop)
+
+    def forward(self, x):
+        y, y16 = ops.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        x = self.attn(y, y16, residual=x)
+        y, y16 = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        return self.mlp(y, y16, residual=x)
+
+
+class TransFormer(nn.Module):
+    """models/mirror.py:155-289."""
+
+    def __init__(self, input_dim, embed_dim=768, depth=2, num_heads=12, mlp_ratio=4.0, qkv_bias=True, qk_norm=False,
+                 init_values=None, gene_embed="learn", pre_norm=False, final_norm=True, embed_drop_rate=0.0,
+                 pos_drop_rate=0.0, proj_drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0, weight_init="",
+                 fix_init=False, norm_layer=None, act_layer=None):
+        super().__init__()
+        assert gene_embed in ("", "none", "learn")
+        if qk_norm or init_values or pre_norm or attn_drop_rate > 0 or drop_path_rate > 0 or pos_drop_rate > 0 or not final_norm:
+            raise NotImplementedError("qk_norm / LayerScale / pre_norm / attn-drop / drop-path / pos-drop are not part of the MIRROR hot path")
+        eps = _norm_eps(norm_layer)
+        _check_gelu(act_layer)
+        self.num_features = self.head_hidden_size = self.embed_dim = embed_dim
+        self.embedding = _Mlp(input_dim, embed_dim * 2, embed_dim, norm_eps=eps, drop=embed_drop_rate)
+        self.gene_embed = None if not gene_embed or gene_embed == "none" else nn.Parameter(torch.randn(1, embed_dim) * 0.02)
+        self.blocks = nn.Sequential(*[
+            Block(embed_dim, num_heads, mlp_ratio, qkv_bias, proj_drop_rate, eps) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=eps)
+        if self.gene_embed is not None:
+            nn.init.trunc_normal_(self.gene_embed, std=0.02)
+        if fix_init:
+            for layer_id, layer in enumerate(self.blocks):
+                layer.attn.proj.weight.data.div_(math.sqrt(2.0 * (layer_id + 1)))
+                layer.mlp.fc2.weight.data.div_(math.sqrt(2.0 * (layer_id + 1)))
+
+    def forward(self, x):
+        x = self.embedding(x.float(), row_res=self.gene_embed)
+        for blk in self.blocks:
+            x = blk(x)
+        return ops.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)[0]
+
+
+# ===========================================
+#  TransMIL for Histopathology Data
+# ===========================================
+class _NystromParams(nn.Module):
+    """Parameter container with the key names of ``nystrom_attention.NystromAttention`` (heads 8, landmarks dim//2,
+    6 pinv iterations, 33-tap residual conv, dropout 0.1; models/mirror.py:299-309)."""
+
+    def __init__(self, dim, heads=8, dropout=0.1, kernel=33):
+        super().__init__()
+        assert dim % heads == 0 and dim % 2 == 0
+        self.heads, self.dropout = heads, dropout
+        self.to_qkv = nn.Linear(dim, dim * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(dim, dim), nn.Dropout(dropout))
+        self.res_conv = nn.Conv2d(heads, heads, (kernel, 1), padding=(kernel // 2, 0), groups=heads, bias=False)
+
+
+class TransLayer(nn.Module):
+    """models/mirror.py:295-314."""
+
+    def __init__(self, dim=512):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.attn = _NystromParams(dim)
+
+    def forward(self, x):
+        a = self.attn
+        return ops.nystrom_layer(x, self.norm.weight, self.norm.bias, a.to_qkv.weight, a.to_out[0].weight, a.to_out[0].bias,
+                                 a.res_conv.weight, a.dropout if self.training else 0.0)
+
+
+class PPEG(nn.Module):
+    """models/mirror.py:317-331."""
+
+    def __init__(self, dim=512):
+        super().__init__()
+        self.proj = nn.Conv2d(dim, dim, 7, 1, 7 // 2, groups=dim)
+        self.proj1 = nn.Conv2d(dim, dim, 5, 1, 5 // 2, groups=dim)
+        self.proj2 = nn.Conv2d(dim, dim, 3, 1, 3 // 2, groups=dim)
+
+    def forward(self, x, H=None, W=None):
+        return ops.PpegFn.apply(x, self.proj.weight, self.proj.bias, self.proj1.weight, self.proj1.bias, self.proj2.weight,
+                                self.proj2.bias)
+
+
+class FeatureTransMIL(nn.Module):
+    """models/mirror.py:334-380."""
+
+    def __init__(self, input_dim=1024, embed_dim=512):
+        super().__init__()
+        self.input_dim, self.embed_dim = input_dim, embed_dim
+        self.pos_layer = PPEG(dim=embed_dim)
+        self._fc1 = nn.Sequential(nn.Linear(input_dim, embed_dim), nn.ReLU())
+        self.cls_token = nn.Parameter(torch.randn(1, 1, embed_dim))
+        self.layer1 = TransLayer(dim=embed_dim)
+        self.layer2 = TransLayer(dim=embed_dim)
+        self.norm = nn.LayerNorm(embed_dim)
+
+    def _tokens(self, h):
+        """fc1+ReLU, wrap pad, cls, layer1, PPEG, layer2, final norm -> ([B,S,E] f32, bf16 copy, add_length)."""
+        N = h.shape[1]
+        Hs = int(np.ceil(np.sqrt(N)))
+        add = Hs * Hs - N
+        x = ops.WsiEmbedFn.apply(h.float(), self._fc1[0].weight, self._fc1[0].bias, self.cls_token)
+        x = self.layer1(x)
+        x = self.pos_layer(x)
+        x = self.layer2(x)
+        y, y16 = ops.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
+        return y, y16, add
+
+    def forward(self, h):
+        return self._tokens(h)[0][:, 0]
+
+
+# ===========================================
+#  TransFormer for Pre-training
+# ===========================================
+class TransFormerHybrid(TransFormer):
+    """models/mirror.py:386-569."""
+
+    def __init__(self, input_dim, embed_dim=768, depth=2, num_heads=12, mlp_ratio=4.0, qkv_bias=True, gene_embed="learn",
+                 pos_drop_rate=0.0, proj_drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0, norm_layer=None,
+                 act_layer=None, retention_decoder_depth=1, **kw):
+        super().__init__(input_dim=input_dim, embed_dim=embed_dim, depth=depth, num_heads=num_heads, mlp_ratio=mlp_ratio,
+                         qkv_bias=qkv_bias, gene_embed=gene_embed, pos_drop_rate=pos_drop_rate, proj_drop_rate=proj_drop_rate,
+                         attn_drop_rate=attn_drop_rate, drop_path_rate=drop_path_rate, norm_layer=norm_layer,
+                         act_layer=act_layer, **kw)
+        eps = _norm_eps(norm_layer)
+        self.alignment_head = nn.Linear(embed_dim, embed_dim)
+        self.retention_embed = nn.Linear(embed_dim, embed_dim)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1))
+        self.retention_gene_embed = nn.Parameter(torch.randn(1, embed_dim) * 0.02)
+        self.retention_blocks = nn.ModuleList([
+            Block(embed_dim, num_heads, mlp_ratio, qkv_bias, proj_drop_rate, eps) for _ in range(retention_decoder_depth)])
+        self.retention_norm = nn.LayerNorm(embed_dim, eps=eps)
+        self.retention_head = nn.Linear(embed_dim, embed_dim)
+        nn.init.normal_(self.mask_token, std=0.02)
+        nn.init.trunc_normal_(self.retention_gene_embed, std=0.02)
+        for layer_id, layer in enumerate(self.retention_blocks):
+            layer.attn.proj.weight.data.div_(math.sqrt(2.0 * (layer_id + 1)))
+            layer.mlp.fc2.weight.data.div_(math.sqrt(2.0 * (layer_id + 1)))
+
+    def random_masking(self, x, mask_ratio, noise=None):
+        """models/mirror.py:510-533; returns (masked x + retention_gene_embed, mask)."""
+        B, N = x.shape
+        keep = int(N * (1 - mask_ratio))
+        if noise is None:
+            noise = torch.rand(B, N, device=x.device)
+        mask = K.rank_mask(noise.float().contiguous(), keep)
+        r = ops.MaskPosFn.apply(x.view(B, N, 1), mask, self.mask_token, self.retention_gene_embed.view(N, 1), 0)
+        return r.view(B, N), mask
+
+    def forward_encoder(self, x):
+        return super().forward(x)
+
+    def forward_alignment_head(self, x):
+        eps = 1e-6 if x.dtype == torch.float16 else 1e-12
+        return ops.linear(ops.l2_normalize(x, eps), self.alignment_head.weight, self.alignment_head.bias)
+
+    def forward_retention_head(self, x, mask_ratio, noise=None):
+        r = ops.linear(x, self.retention_embed.weight, self.retention_embed.bias)
+        r, mask = self.random_masking(r, mask_ratio, noise)  # includes "+ retention_gene_embed" (:549)
+        for blk in self.retention_blocks:
+            r = blk(r)
+        r, r16 = ops.layer_norm(r, self.retention_norm.weight, self.retention_norm.bias, self.retention_norm.eps)
+        return ops.linear(r, self.retention_head.weight, self.retention_head.bias, x16=r16), mask
+
+    def forward_decoders(self, x, mask_ratio, noise=None):
+        a = self.forward_alignment_head(x)
+        r, mask = self.forward_retention_head(x, mask_ratio, noise)
+        return a, r, mask
+
+    def forward(self, x, mask_ratio=0.75):
+        x = self.forward_encoder(x)
+        a, r, mask = self.forward_decoders(x, mask_ratio)
+        return a, r, x, mask
+
+
+# ===========================================
+#  TransMIL for Pre-training
+# ===========================================
+class FeatureTransMILHybrid(FeatureTransMIL):
+    """models/mirror.py:575-714."""
+
+    def __init__(self, input_dim=1024, embed_dim=512, num_tokens=2048, retention_decoder_depth=1):
+        super().__init__(input_dim, embed_dim)
+        self.num_tokens = num_tokens
+        self.alignment_head = nn.Linear(embed_dim, embed_dim)
+        self.retention_embed = nn.Linear(embed_dim, embed_dim)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.retention_gene_embed = nn.Parameter(torch.randn(1, num_tokens + 1, embed_dim) * 0.02)
+        self.retention_blocks = nn.ModuleList([TransLayer(dim=embed_dim) for _ in range(retention_decoder_depth)])
+        self.retention_norm = nn.LayerNorm(embed_dim)
+        self.retention_head = nn.Linear(embed_dim, embed_dim)
+        self.init_weights()
+
+    def init_weights(self):
+        nn.init.normal_(self.mask_token, std=0.02)
+        nn.init.normal_(self.cls_token, std=0.02)
+        nn.init.trunc_normal_(self.retention_gene_embed, std=0.02)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_uniform_(m.weight)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def forward_encoder(self, h):
+        y, y16, add = self._tokens(h)
+        S = y.shape[1]
+        self._emb16 = y16[:, : S - add, :]  # bf16 copy for the decoders of THIS forward (not a parameter/buffer)
+        return y[:, : S - add, :]
+
+    def forward_alignment_head(self, h):
+        eps = 1e-6 if h.dtype == torch.float16 else 1e-12
+        return ops.linear(ops.l2_normalize(h[:, 0, :], eps), self.alignment_head.weight, self.alignment_head.bias)
+
+    def forward_retention_head(self, h, mask_ratio, noise=None):
+        B, T, E = h.shape  # T = N + 1
+        N = T - 1
+        keep = int(N * (1 - mask_ratio))
+        if noise is None:
+            noise = torch.rand(B, N, device=h.device)
+        mask = K.rank_mask(noise.float().contiguous(), keep)
+        x16 = getattr(self, "_emb16", None)
+        if x16 is not None and (x16.shape != h.shape or not h.is_contiguous() or not x16.is_contiguous()):
+            x16 = None
+        r = ops.linear(h, self.retention_embed.weight, self.retention_embed.bias, x16=x16)
+        r = ops.MaskPosFn.apply(r, mask, self.mask_token, self.retention_gene_embed, 1)
+        for blk in self.retention_blocks:
+            r = blk(r)
+        r, r16 = ops.layer_norm(r, self.retention_norm.weight, self.retention_norm.bias, self.retention_norm.eps)
+        r = ops.linear(r, self.retention_head.weight, self.retention_head.bias, x16=r16)
+        return r[:, 1:, :], mask
+
+    def forward_decoders(self, h, mask_ratio, noise=None):
+        a = self.forward_alignment_head(h)
+        r, mask = self.forward_retention_head(h, mask_ratio, noise)
+        self._emb16 = None
+        return a, r, mask
+
+    def forward(self, h, mask_ratio=0.75):
+        h = self.forward_encoder(h)
+        a, r, mask = self.forward_decoders(h, mask_ratio)
+        return a, r, h[:, 1:, :], mask
+
+
+# ===========================================
+#  MIRROR for Pre-training
+# ===========================================
+class MIRROR(nn.Module):
+    """models/mirror.py:720-915.  ``noise`` (optional, not in the reference signature) injects the four random draws of
+    the forward (``wsi_mask``, ``rna_mask``, ``wsi_eps``, ``rna_eps``) for parity tests; by default they are drawn with
+    ``torch.rand`` / ``torch.randn`` in the reference's call order."""
+
+    def __init__(self, wsi_embed_dim: int, rna_embed_dim: int, embed_dim: int, wsi_num_tokens: int = 2048,
+                 wsi_retention_decoder_depth: int = 1, rna_encoder_depth: int = 2, rna_gene_embed: str = "learn",
+                 rna_mlp_ratio: float = 2.572, rna_pos_drop_rate: float = 0.0, rna_proj_drop_rate: float = 0.1,
+                 rna_attn_drop_rate: float = 0.0, rna_drop_path_rate: float = 0.0, rna_norm_layer=None, rna_act_layer=None,
+                 rna_retention_decoder_depth: int = 1, init_logit_scale: float = np.log(1 / 0.07),
+                 style_mlp_hidden_dim: int = 512, style_mlp_out_dim: int = 256, style_norm_layer=None, style_act_layer=None,
+                 style_latent_dim: int = 128, num_prototypes: int = 3000) -> None:
+        super().__init__()
+        self.wsi_embed_dim, self.rna_embed_dim, self.embed_dim = wsi_embed_dim, rna_embed_dim, embed_dim
+        self.wsi_num_tokens = wsi_num_tokens
+        self.wsi_retention_decoder_depth = wsi_retention_decoder_depth
+        self.rna_encoder_depth, self.rna_gene_embed, self.rna_mlp_ratio = rna_encoder_depth, rna_gene_embed, rna_mlp_ratio
+        self.rna_pos_drop_rate, self.rna_proj_drop_rate = rna_pos_drop_rate, rna_proj_drop_rate
+        self.attn_drop_rate, self.drop_path_rate = rna_attn_drop_rate, rna_drop_path_rate
+        self.rna_norm_layer, self.rna_act_layer = rna_norm_layer, rna_act_layer
+        self.rna_retention_decoder_depth = rna_retention_decoder_depth
+        if embed_dim % 24:
+            raise ValueError("embed_dim must be a multiple of 24 (8 Nystrom heads and 12 RNA chunks, models/mirror.py:64,301)")
+        if style_norm_layer is not None:
+            raise NotImplementedError("style_norm_layer is not used by the reference configuration")
+        _check_gelu(style_act_layer)
+
+        self.logit_scale = nn.Parameter(torch.ones([]) * init_logit_scale)
+        self.wsi_encoder = FeatureTransMILHybrid(input_dim=wsi_embed_dim, embed_dim=embed_dim, num_tokens=wsi_num_tokens,
+                                                 retention_decoder_depth=wsi_retention_decoder_depth)
+        self.rna_encoder = TransFormerHybrid(input_dim=rna_embed_dim, embed_dim=embed_dim, depth=rna_encoder_depth,
+                                             gene_embed=rna_gene_embed, mlp_ratio=rna_mlp_ratio, pos_drop_rate=rna_pos_drop_rate,
+                                             proj_drop_rate=rna_proj_drop_rate, attn_drop_rate=rna_attn_drop_rate,
+                                             drop_path_rate=rna_drop_path_rate, norm_layer=rna_norm_layer,
+                                             act_layer=rna_act_layer, retention_decoder_depth=rna_retention_decoder_depth)
+        self.style_encoder_mlp = _Mlp(embed_dim, style_mlp_hidden_dim, style_mlp_out_dim, drop=0.0)
+        self.style_mu = nn.Linear(style_mlp_out_dim, style_latent_dim)
+        self.style_logstd = nn.Linear(style_mlp_out_dim, style_latent_dim)
+        self.style_decoder = nn.Linear(style_latent_dim, embed_dim)
+        self.prototypes = nn.Linear(embed_dim, num_prototypes, bias=False)
+        nn.init.orthogonal_(self.prototypes.weight)
+
+    def reparameterize(self, mu, logstd, eps=None):
+        if eps is None:
+            eps = torch.randn_like(mu)
+        return ops.ReparamFn.apply(mu, logstd, eps.float())
+
+    def forward_style_clustering(self, wsi_emb, rna_emb, wsi_eps=None, rna_eps=None):
+        """models/mirror.py:835-858; both modalities share the weights, so they run as ONE stacked batch of 2B rows."""
+        B = wsi_emb.shape[0]
+        x = ops.stack_rows(wsi_emb, rna_emb)  # [2B,E]
+        x = self.style_encoder_mlp(x)
+        mu = ops.linear(x, self.style_mu.weight, self.style_mu.bias)
+        logstd = ops.linear(x, self.style_logstd.weight, self.style_logstd.bias)
+        if wsi_eps is None:
+            wsi_eps = torch.randn(B, mu.shape[1], device=mu.device)
+        if rna_eps is None:
+            rna_eps = torch.randn(B, mu.shape[1], device=mu.device)
+        z = self.reparameterize(mu, logstd, torch.cat([wsi_eps.float(), rna_eps.float()], 0))
+        z = ops.linear(z, self.style_decoder.weight, self.style_decoder.bias)
+        score = ops.linear(z, self.prototypes.weight)
+        return score[:B], mu[:B], logstd[:B], score[B:], mu[B:], logstd[B:]
+
+    def forward(self, wsi_emb, rna_emb, wsi_mask_ratio: float = 0.75, rna_mask_ratio: float = 0.75, noise=None) -> Tuple[torch.Tensor, ...]:
+        noise = noise or {}
+        wsi_emb = self.wsi_encoder.forward_encoder(wsi_emb)
+        wa, wr, wm = self.wsi_encoder.forward_decoders(wsi_emb, wsi_mask_ratio, noise.get("wsi_mask"))
+        wsi_retention_target = wsi_emb[:, 1:, :]
+        rna_emb = self.rna_encoder.forward_encoder(rna_emb)
+        ra, rr, rm = self.rna_encoder.forward_decoders(rna_emb, rna_mask_ratio, noise.get("rna_mask"))
+        ws, wmu, wls, rs, rmu, rls = self.forward_style_clustering(wsi_emb[:, 0, :], rna_emb, noise.get("wsi_eps"),
+                                                                   noise.get("rna_eps"))
+        return (wa, wr, wsi_retention_target, wm, ws, wmu, wls, ra, rr, rna_emb, rm, rs, rmu, rls, self.logit_scale.exp())
+
+
+class MIRRORDualEncoder(nn.Module):
+    """The 2-output model ``train_pretrain.py:1119-1122`` unpacks (the reference registers none):
+    FeatureTransMIL cls embedding (models/mirror.py:352-380) and TransFormer embedding (:283-289)."""
+
+    def __init__(self, wsi_embed_dim, rna_embed_dim, embed_dim, rna_encoder_depth=2, rna_gene_embed="learn", rna_mlp_ratio=2.572,
+                 rna_proj_drop_rate=0.1, rna_norm_layer=None, rna_act_layer=None):
+        super().__init__()
+        self.wsi_encoder = FeatureTransMIL(input_dim=wsi_embed_dim, embed_dim=embed_dim)
+        self.rna_encoder = TransFormer(input_dim=rna_embed_dim, embed_dim=embed_dim, depth=rna_encoder_depth,
+                                       gene_embed=rna_gene_embed, mlp_ratio=rna_mlp_ratio, proj_drop_rate=rna_proj_drop_rate,
+                                       norm_layer=rna_norm_layer, act_layer=rna_act_layer)
+
+    def forward(self, wsi_emb, rna_emb):
+        return self.wsi_encoder(wsi_emb), self.rna_encoder(rna_emb)
+
+
+_MIRROR_ARGS = {
+    "wsi_embed_dim", "rna_embed_dim", "embed_dim", "wsi_num_tokens", "wsi_retention_decoder_depth", "rna_encoder_depth",
+    "rna_gene_embed", "rna_mlp_ratio", "rna_pos_drop_rate", "rna_proj_drop_rate", "rna_attn_drop_rate", "rna_drop_path_rate",
+    "rna_norm_layer", "rna_act_layer", "rna_retention_decoder_depth", "init_logit_scale", "style_mlp_hidden_dim",
+    "style_mlp_out_dim", "style_norm_layer", "style_act_layer", "style_latent_dim", "num_prototypes",
+}
+_DUAL_ARGS = {"wsi_embed_dim", "rna_embed_dim", "embed_dim", "rna_encoder_depth", "rna_gene_embed", "rna_mlp_ratio",
+              "rna_proj_drop_rate", "rna_norm_layer", "rna_act_layer"}
+
+
+def _filtered(kwargs, accepted):
+    dropped = [k for k in kwargs if k not in accepted]
+    if dropped:  # timm injects pretrained / pretrained_cfg / ...: filter with a warning like models/mirror.py:1045-1053
+        _logger.warning("Filtered model kwargs: %s", ", ".join(dropped))
+    return {k: v for k, v in kwargs.items() if k in accepted}
+
+
+@register_model
+def mirror(**kwargs):
+    return MIRROR(**_filtered(kwargs, _MIRROR_ARGS))
+
+
+@register_model
+def mirror_dual_encoder(**kwargs):
+    return MIRRORDualEncoder(**_filtered(kwargs, _DUAL_ARGS))

@@ -1,0 +1,690 @@
+"""Autograd functions of the MIRROR hot path, written on top of the C-ABI kernels.
+
+Forward AND backward of every function are explicit sequences of kernel
+launches (``mirror_b200.kernels``); PyTorch autograd only chains them.
+Precision plan (SURVEY.md §7 "Precision"): bf16 tensor-core operands, fp32
+accumulation, fp32 residual stream / LayerNorm / softmax statistics / head
+outputs / losses.
+"""
+import math
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import kernels as K
+
+F32, BF16 = torch.float32, torch.bfloat16
+WSI_HEADS = 8  # models/mirror.py:302
+PINV_ITERS = 6  # models/mirror.py:304
+
+_seed_state = {"base": None, "n": 0}
+
+
+def next_seed() -> int:
+    """Host-side counter-based seed for the hashed dropout masks (no device sync)."""
+    if _seed_state["base"] is None:
+        _seed_state["base"] = torch.initial_seed() & 0xFFFFFFFF
+    _seed_state["n"] += 1
+    return ((_seed_state["base"] * 0x9E3779B1) ^ (_seed_state["n"] * 0x85EBCA77)) & 0x7FFFFFFFFFFFFFFF
+
+
+def _r8(x):
+    return (x + 7) // 8 * 8
+
+
+def _cfwd(fn):
+    return torch.amp.custom_fwd(fn, device_type="cuda", cast_inputs=torch.float32)
+
+
+def _cbwd(fn):
+    return torch.amp.custom_bwd(fn, device_type="cuda")
+
+
+def _T(x):
+    return x.transpose(-1, -2)
+
+
+def _split_k(M, N, Kdim):
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if (N % 256 == 0 or N >= 1024) else (N + 127) // 128)
+    kb = (Kdim + 63) // 64
+    return max(1, min(148 // max(tiles, 1), kb // 4 if kb >= 8 else 1, 32))
+
+
+def wgrad(dy16, x16, out_rows, out_cols):
+    """dW[out_rows,out_cols] (f32) = dy16^T @ x16 with the contraction over rows, split-K over the SMs.
+    dy16: [rows, >=out_rows] bf16 view, x16: [rows, >=out_cols] bf16 view (row strides multiples of 8)."""
+    rows = dy16.shape[0]
+    dw = torch.zeros(out_rows, out_cols, device=dy16.device, dtype=F32)
+    K.gemm(_T(dy16[:, :out_rows]), _T(x16[:, :out_cols]), out_f32=dw, split_k=_split_k(out_rows, out_cols, rows))
+    return dw
+
+
+def colsum(x, cols):
+    out = torch.zeros(cols, device=x.device, dtype=F32)
+    K.colsum_(x[:, :cols], out)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+class LinearFn(Function):
+    """y = [res +] dropout(x @ W^T + b) [+ row_res broadcast over rows].  nn.Linear of the heads, the RNA encoder and the
+    style MLPs (models/mirror.py:70,74,470-495,594-605,823-827; timm Mlp fc1/fc2) with the following Dropout and residual
+    add of Block.forward (:149-152) fused into the GEMM epilogue.  x16: optional bf16 copy of x."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, x, weight, bias, row_res, x16, res, drop_p, seed):
+        N, Kd = weight.shape
+        lead = x.shape[:-1]
+        rows = x.numel() // Kd
+        Kp = _r8(Kd)
+        if x16 is None or Kp != Kd:
+            x2 = x.reshape(rows, Kd) if x.is_contiguous() or x.dim() == 2 else x.contiguous().view(rows, Kd)
+            x16 = K.cast_bf16(x2, Kp)
+        else:
+            x16 = x16.reshape(rows, Kd)
+        w16 = K.cast_bf16(weight, Kp)
+        y = torch.empty(*lead, N, device=x.device, dtype=F32)  # returned as-is (no view) so callers may update it in place
+        assert row_res is None or res is None
+        r = None
+        if row_res is not None:
+            r = row_res.reshape(1, N).expand(rows, N)
+        elif res is not None:
+            r = res.contiguous().view(rows, N)
+        K.gemm(x16[:, :Kd], w16[:, :Kd], out_f32=y.view(rows, N), bias=bias, res=r, drop_p=drop_p, drop_seed=seed)
+        ctx.save_for_backward(x16, w16)
+        ctx.meta = (rows, N, Kd, bias is not None, tuple(row_res.shape) if row_res is not None else None, res is not None,
+                    tuple(x.shape), drop_p, seed)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, dy):
+        x16, w16 = ctx.saved_tensors
+        rows, N, Kd, has_b, has_rr, has_res, xshape, drop_p, seed = ctx.meta
+        Np = _r8(N)
+        dy2 = dy.reshape(rows, N)
+        if dy2.stride(1) != 1 or (dy2.stride(0) != N and rows > 1):
+            dy2 = dy2.contiguous()
+        if drop_p > 0:
+            dy16 = torch.empty(rows, Np, device=dy.device, dtype=BF16)
+            K.act_bwd(dy2.view(1, rows, N), None, K.ACT_NONE, drop_p, seed, out16=dy16[:, :N].unsqueeze(0))
+        else:
+            dy16 = K.cast_bf16(dy2, Np)
+        dx = dw = db = drr = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(rows, Kd, device=dy.device, dtype=F32)
+            K.gemm(dy16[:, :N], _T(w16[:, :Kd]), out_f32=dx)
+            dx = dx.view(xshape)
+        if ctx.needs_input_grad[1]:
+            dw = wgrad(dy16, x16, N, Kd)
+        if has_b and ctx.needs_input_grad[2]:
+            db = colsum(dy16, N)
+        if has_rr is not None and ctx.needs_input_grad[3]:
+            drr = colsum(dy2, N).view(has_rr)  # row_res is added after the dropout
+        if has_res and ctx.needs_input_grad[5]:
+            dres = dy
+        return dx, dw, db, drr, None, dres, None, None
+
+
+def linear(x, weight, bias=None, row_res=None, x16=None, res=None, drop_p=0.0):
+    return LinearFn.apply(x, weight, bias, row_res, x16, res, drop_p, next_seed() if drop_p > 0 else 0)
+
+
+class StackRowsFn(Function):
+    """[a; b] for two [B,E] f32 row blocks (a may be a strided view such as the cls rows)."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, a, b):
+        B, E = a.shape
+        out = torch.empty(2 * B, E, device=a.device, dtype=F32)
+        K.copy_rows_(a, out[:B])
+        K.copy_rows_(b, out[B:])
+        ctx.B = B
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        return dy[:ctx.B], dy[ctx.B:]
+
+
+def stack_rows(a, b):
+    return StackRowsFn.apply(a, b)
+
+
+# ----------------------------------------------------------------------------------------------
+class LayerNormFn(Function):
+    """nn.LayerNorm over the last dim; returns (y f32, y bf16 copy [non-differentiable])."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, x, weight, bias, eps):
+        E = x.shape[-1]
+        x3 = x.contiguous().view(1, -1, E)
+        y16, y32, mean, rstd = K.layernorm_fwd(x3, weight, bias, eps, want_bf16=True, want_f32=True)
+        ctx.save_for_backward(x3, weight, mean, rstd)
+        ctx.shape = tuple(x.shape)
+        y16 = y16.view(ctx.shape)
+        ctx.mark_non_differentiable(y16)
+        return y32.view(ctx.shape), y16
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, dy, _unused):
+        x3, weight, mean, rstd = ctx.saved_tensors
+        E = x3.shape[-1]
+        dx = torch.empty_like(x3)
+        dg = torch.zeros(E, device=dy.device, dtype=F32)
+        db = torch.zeros(E, device=dy.device, dtype=F32)
+        K.layernorm_bwd(dy.contiguous().view(1, -1, E), x3, weight, mean, rstd, 0, dx, None, dg, db)
+        return dx.view(ctx.shape), dg, db, None
+
+
+def layer_norm(x, weight, bias, eps):
+    return LayerNormFn.apply(x, weight, bias, eps)
+
+
+# ----------------------------------------------------------------------------------------------
+class ActFn(Function):
+    """dropout(act(x)) for the small RNA / style MLP activations (exact-erf GELU)."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, pre, act, drop_p, seed):
+        pre = pre.contiguous()
+        _, y = K.act_fwd(pre, act, drop_p, seed, want_bf16=False, want_f32=True)
+        ctx.save_for_backward(pre)
+        ctx.cfg = (act, drop_p, seed)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, dy):
+        (pre,) = ctx.saved_tensors
+        act, drop_p, seed = ctx.cfg
+        dx = torch.empty_like(pre)
+        C = pre.shape[-1]
+        K.act_bwd(dy.contiguous().view(1, -1, C), pre.view(1, -1, C), act, drop_p, seed, out32=dx.view(1, -1, C))
+        return dx, None, None, None
+
+
+def activation(pre, act, drop_p=0.0):
+    return ActFn.apply(pre, act, drop_p, next_seed() if drop_p > 0 else 0)
+
+
+# ----------------------------------------------------------------------------------------------
+class L2NormFn(Function):
+    """F.normalize(x, dim=-1, eps) on a [rows, E] view (rows may be strided, e.g. the cls rows)."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, x, eps):
+        y, norm = K.l2norm_fwd(x, eps)
+        ctx.save_for_backward(x, norm)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, dy):
+        x, norm = ctx.saved_tensors
+        return K.l2norm_bwd(dy.contiguous(), x, norm), None
+
+
+def l2_normalize(x, eps):
+    return L2NormFn.apply(x, eps)
+
+
+# ----------------------------------------------------------------------------------------------
+class WsiEmbedFn(Function):
+    """_fc1 (Linear+ReLU) + wrap-around square padding + cls token (models/mirror.py:652-665) -> h [B,S,E] f32."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, wsi, w, b, cls):
+        B, N, Dw = wsi.shape
+        E = w.shape[0]
+        H = int(math.ceil(math.sqrt(N)))
+        add = H * H - N
+        S = H * H + 1
+        Dp = _r8(Dw)
+        x16 = K.cast_bf16(wsi.contiguous().view(B * N, Dw), Dp).view(B, N, Dp)
+        w16 = K.cast_bf16(w, Dp)
+        h = torch.empty(B, S, E, device=wsi.device, dtype=F32)
+        K.gemm(x16[:, :, :Dw], w16[:, :Dw].unsqueeze(0).expand(B, E, Dw), out_f32=h[:, 1:1 + N, :], bias=b, act=K.ACT_RELU)
+        K.wsi_assemble_fwd(h, cls.reshape(E), N, add)
+        ctx.save_for_backward(x16, h)
+        ctx.meta = (B, N, Dw, E, add)
+        return h
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, dh):
+        x16, h = ctx.saved_tensors
+        B, N, Dw, E, add = ctx.meta
+        dcls = torch.zeros(E, device=dh.device, dtype=F32)
+        dpre = K.wsi_embed_bwd(dh.contiguous(), h, N, add, dcls)
+        dw = wgrad(dpre.view(B * N, E), x16.view(B * N, -1), E, Dw)
+        db = colsum(dpre.view(B * N, E), E)
+        return None, dw, db, dcls.view(1, 1, E)
+
+
+# ----------------------------------------------------------------------------------------------
+def _heads(t, col0, E, h=WSI_HEADS):
+    """[B, rows, W] -> view [B, h, rows, d] of columns col0 .. col0+E."""
+    B, rows, _ = t.shape
+    return t[:, :, col0:col0 + E].unflatten(-1, (h, E // h)).permute(0, 2, 1, 3)
+
+
+class NystromLayerFn(Function):
+    """TransLayer: x + NystromAttention(LayerNorm(x)) (models/mirror.py:295-314; nystrom_attention forward).
+
+    Differences from the reference evaluation order, all exact in real arithmetic: q's 1/sqrt(d) is folded into the three
+    similarity GEMMs; (attn1 z)(attn3 v) is evaluated as attn1 (z (attn3 v)); each Moore-Penrose step is evaluated as
+    xz = a2 z, u1 = 7xz - xz xz, u2 = 15xz - xz u1, z' = 3.25 z - 0.25 z u2 (no explicit identity matrices).
+    """
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, h, ln_w, ln_b, qkv_w, out_w, out_b, conv_w, drop_p, seed):
+        B, S, E = h.shape
+        hd = WSI_HEADS
+        d, m = E // hd, E // 2
+        pad = (m - S % m) % m
+        n = S + pad
+        seg = math.ceil(S / m)
+        scale = d ** -0.5
+        dev = h.device
+        h = h.contiguous()
+        xn16, _, mean, rstd = K.layernorm_fwd(h, ln_w, ln_b, 1e-5, n_out=n, pad=pad)
+        wqkv16 = K.cast_bf16(qkv_w)
+        qkv = torch.empty(B, n, 3 * E, device=dev, dtype=BF16)
+        K.gemm(xn16.view(B * n, E), wqkv16, out_bf16=qkv.view(B * n, 3 * E))
+        lm = K.landmark_fwd(qkv, m, seg)
+        q, k, v = _heads(qkv, 0, E), _heads(qkv, E, E), _heads(qkv, 2 * E, E)
+        ql, kl = _heads(lm, 0, E), _heads(lm, E, E)
+        s1 = torch.empty(B, hd, n, m, device=dev, dtype=F32)
+        K.gemm(q, kl, out_f32=s1, alpha=scale)
+        a1, _ = K.softmax_fwd(s1)
+        del s1
+        s2 = torch.empty(B, hd, m, m, device=dev, dtype=F32)
+        K.gemm(ql, kl, out_f32=s2, alpha=scale)
+        a2_16, a2_32 = K.softmax_fwd(s2, want_f32=True)
+        del s2
+        s3 = torch.empty(B, hd, m, n, device=dev, dtype=F32)
+        K.gemm(ql, k, out_f32=s3, alpha=scale)
+        a3, _ = K.softmax_fwd(s3)
+        del s3
+        z32, z16, scratch = K.pinv_init(a2_32)
+        z0_32 = z32
+        iters = []
+        mm = (B, hd, m, m)
+        for _ in range(PINV_ITERS):
+            xz = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(a2_16, _T(z16), out_bf16=xz)
+            u1 = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(xz, _T(xz), out_bf16=u1, alpha=-1.0, res=xz, gamma=7.0)
+            u2 = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(xz, _T(u1), out_bf16=u2, alpha=-1.0, res=xz, gamma=15.0)
+            zn32 = torch.empty(mm, device=dev, dtype=F32)
+            zn16 = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(z16, _T(u2), out_f32=zn32, out_bf16=zn16, alpha=-0.25, res=z32, gamma=3.25)
+            iters += [z16, xz, u1, u2]
+            z32, z16 = zn32, zn16
+        kv = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
+        K.gemm(a3, _T(v), out_bf16=kv)
+        w_ = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
+        K.gemm(z16, _T(kv), out_bf16=w_)
+        rc = K.res_conv_fwd(qkv, conv_w.reshape(hd, -1))
+        o16 = torch.empty(B, n, E, device=dev, dtype=BF16)
+        K.gemm(a1, _T(w_), out_bf16=_heads(o16, 0, E), res=_heads(rc, 0, E))
+        del rc
+        wout16 = K.cast_bf16(out_w)
+        y = torch.empty(B, S, E, device=dev, dtype=F32)
+        K.gemm(o16[:, pad:, :], wout16.unsqueeze(0).expand(B, E, E), out_f32=y, bias=out_b, drop_p=drop_p, drop_seed=seed, res=h)
+        ctx.save_for_backward(h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, a1, a2_16, a3, z0_32, scratch, z16, kv, w_, o16,
+                              wout16, conv_w, *iters)
+        ctx.meta = (B, S, E, pad, n, seg, scale, drop_p, seed)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, dy):
+        (h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, a1, a2_16, a3, z0_32, scratch, zf16, kv, w_, o16, wout16,
+         conv_w, *iters) = ctx.saved_tensors
+        B, S, E, pad, n, seg, scale, drop_p, seed = ctx.meta
+        hd = WSI_HEADS
+        d, m = E // hd, E // 2
+        dev = dy.device
+        dy = dy.contiguous()
+        q, k, v = _heads(qkv, 0, E), _heads(qkv, E, E), _heads(qkv, 2 * E, E)
+        ql, kl = _heads(lm, 0, E), _heads(lm, E, E)
+        mm = (B, hd, m, m)
+
+        # ---- to_out: y = h + drop(o16[pad:] @ Wout^T + b)
+        dyd = torch.zeros(B, n, E, device=dev, dtype=BF16) if pad else torch.empty(B, n, E, device=dev, dtype=BF16)
+        K.act_bwd(dy, None, K.ACT_NONE, drop_p, seed, out16=dyd[:, pad:, :])
+        do16 = torch.empty(B, n, E, device=dev, dtype=BF16)
+        K.gemm(dyd.view(B * n, E), _T(wout16), out_bf16=do16.view(B * n, E))
+        d_out_w = wgrad(dyd.view(B * n, E), o16.view(B * n, E), E, E)
+        d_out_b = colsum(dyd.view(B * n, E), E)
+        del dyd
+        do_h = _heads(do16, 0, E)
+
+        # ---- out = a1 @ w + res_conv(v)
+        da1 = torch.empty(B, hd, n, m, device=dev, dtype=F32)
+        K.gemm(do_h, w_, out_f32=da1)
+        dw16 = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
+        K.gemm(_T(a1), _T(do_h), out_bf16=dw16)
+        ds1, _ = K.softmax_bwd(a1, da1, scale)
+        del da1
+
+        # ---- w = z @ kv ; kv = a3 @ v
+        gz32 = torch.empty(mm, device=dev, dtype=F32)
+        gz16 = torch.empty(mm, device=dev, dtype=BF16)
+        K.gemm(dw16, kv, out_f32=gz32, out_bf16=gz16)
+        dkv16 = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
+        K.gemm(_T(zf16), _T(dw16), out_bf16=dkv16)
+        da3 = torch.empty(B, hd, m, n, device=dev, dtype=F32)
+        K.gemm(dkv16, v, out_f32=da3)
+        dqkv32 = torch.empty(B, n, 3 * E, device=dev, dtype=F32)
+        K.gemm(_T(a3), _T(dkv16), out_f32=_heads(dqkv32, 2 * E, E))
+        d_conv = torch.zeros(hd, conv_w.numel() // hd, device=dev, dtype=F32)
+        K.res_conv_bwd_(do16, qkv, conv_w.reshape(hd, -1), dqkv32, d_conv)
+        del do16
+        ds3, _ = K.softmax_bwd(a3, da3, scale)
+        del da3
+
+        # ---- Moore-Penrose iterations, reversed
+        ga2 = torch.empty(mm, device=dev, dtype=F32)
+        for it in reversed(range(PINV_ITERS)):
+            z16, xz, u1, u2 = iters[4 * it:4 * it + 4]
+            gu2 = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(_T(z16), _T(gz16), out_bf16=gu2, alpha=-0.25)                       # -0.25 z^T g
+            gzn32 = torch.empty(mm, device=dev, dtype=F32)
+            K.gemm(gz16, u2, out_f32=gzn32, alpha=-0.25, res=gz32, gamma=3.25)          # 3.25 g - 0.25 g u2^T
+            gxz32 = torch.empty(mm, device=dev, dtype=F32)
+            K.gemm(gu2, u1, out_f32=gxz32, alpha=-1.0, res=gu2, gamma=15.0)             # 15 gu2 - gu2 u1^T
+            gu1 = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(_T(xz), _T(gu2), out_bf16=gu1, alpha=-1.0)                           # -xz^T gu2
+            K.gemm(gu1, xz, out_f32=gxz32, alpha=-1.0, res=gu1, gamma=7.0, beta=1.0)    # += 7 gu1 - gu1 xz^T
+            gxz16 = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(_T(xz), _T(gu1), out_f32=gxz32, out_bf16=gxz16, alpha=-1.0, beta=1.0)  # += -xz^T gu1
+            K.gemm(gxz16, z16, out_f32=ga2, beta=0.0 if it == PINV_ITERS - 1 else 1.0)  # ga2 += gxz z^T
+            gzn16 = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(_T(a2_16), _T(gxz16), out_f32=gzn32, out_bf16=gzn16, beta=1.0)       # gz += a2^T gxz
+            gz32, gz16 = gzn32, gzn16
+        K.pinv_init_bwd(gz32, z0_32, scratch, ga2, True)
+        ds2, _ = K.softmax_bwd(a2_16, ga2, scale)
+        del ga2, gz32, gz16
+
+        # ---- similarities (1/sqrt(d) already folded into ds*)
+        dlm32 = torch.empty(B, m, 2 * E, device=dev, dtype=F32)
+        K.gemm(ds1, _T(kl), out_f32=_heads(dqkv32, 0, E))            # dq  = ds1 kl
+        K.gemm(_T(ds1), _T(q), out_f32=_heads(dlm32, E, E))          # dkl = ds1^T q
+        K.gemm(ds2, _T(kl), out_f32=_heads(dlm32, 0, E))             # dql = ds2 kl
+        K.gemm(_T(ds2), _T(ql), out_f32=_heads(dlm32, E, E), beta=1.0)  # dkl += ds2^T ql
+        K.gemm(ds3, _T(k), out_f32=_heads(dlm32, 0, E), beta=1.0)    # dql += ds3 k
+        K.gemm(_T(ds3), _T(ql), out_f32=_heads(dqkv32, E, E))        # dk  = ds3^T ql
+        del ds1, ds2, ds3
+        dqkv16 = K.dqkv_finish(dqkv32, dlm32, seg)
+        del dqkv32, dlm32
+
+        # ---- to_qkv and LayerNorm
+        dxn = torch.empty(B, n, E, device=dev, dtype=F32)
+        K.gemm(dqkv16.view(B * n, 3 * E), _T(wqkv16), out_f32=dxn.view(B * n, E))
+        d_qkv_w = wgrad(dqkv16.view(B * n, 3 * E), xn16.view(B * n, E), 3 * E, E)
+        dg = torch.zeros(E, device=dev, dtype=F32)
+        db = torch.zeros(E, device=dev, dtype=F32)
+        dh = torch.empty_like(h)
+        K.layernorm_bwd(dxn, h, ln_w, mean, rstd, pad, dh, dy, dg, db)
+        return dh, dg, db, d_qkv_w, d_out_w, d_out_b, d_conv.view(conv_w.shape), None, None
+
+
+def nystrom_layer(h, norm_w, norm_b, qkv_w, out_w, out_b, conv_w, drop_p):
+    return NystromLayerFn.apply(h, norm_w, norm_b, qkv_w, out_w, out_b, conv_w, drop_p, next_seed() if drop_p > 0 else 0)
+
+
+# ----------------------------------------------------------------------------------------------
+class PpegFn(Function):
+    """PPEG (models/mirror.py:317-331) as one merged 7x7 depthwise stencil over token-major activations."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, x, w7, b7, w5, b5, w3, b3):
+        B, S, E = x.shape
+        H = int(round(math.sqrt(S - 1)))
+        x = x.contiguous()
+        y, wm = K.ppeg_fwd(x, w7.reshape(E, 49), w5.reshape(E, 25), w3.reshape(E, 9), b7, b5, b3, H)
+        ctx.save_for_backward(x, wm)
+        ctx.H = H
+        return y
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, dy):
+        x, wm = ctx.saved_tensors
+        E = x.shape[-1]
+        z = lambda *s: torch.zeros(*s, device=dy.device, dtype=F32)
+        dw7, dw5, dw3, db7, db5, db3 = z(E, 49), z(E, 25), z(E, 9), z(E), z(E), z(E)
+        dx = K.ppeg_bwd(dy.contiguous(), x, wm, ctx.H, dw7, dw5, dw3, db7, db5, db3)
+        return dx, dw7.view(E, 1, 7, 7), db7, dw5.view(E, 1, 5, 5), db5, dw3.view(E, 1, 3, 3), db3
+
+
+# ----------------------------------------------------------------------------------------------
+class MaskPosFn(Function):
+    """random_masking's token replacement + learned position table (models/mirror.py:521-527,549,636-643,692-693).
+    r: [B,T,E]; mask: [B,T-first] (1 = masked); tok: [E] or scalar; pos: [T,E].  r is overwritten."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, r, mask, tok, pos, first):
+        B, T, E = r.shape
+        tok_stride = 1 if tok.numel() == E and E > 1 else (1 if tok.numel() > 1 else 0)
+        K.mask_pos_fwd_(r, mask, tok.reshape(-1), tok_stride, pos.reshape(T, E).contiguous(), first)
+        ctx.mark_dirty(r)
+        ctx.save_for_backward(mask)
+        ctx.meta = (tok_stride, first, tuple(tok.shape), tuple(pos.shape))
+        return r
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        tok_stride, first, tshape, pshape = ctx.meta
+        B, T, E = dy.shape
+        dy = dy.contiguous().clone() if not dy.is_contiguous() else dy.clone()
+        dtok = torch.zeros(tshape, device=dy.device, dtype=F32)
+        dpos = torch.zeros(T, E, device=dy.device, dtype=F32)
+        K.mask_pos_bwd_(dy, mask, dtok.view(-1), tok_stride, dpos, first)
+        return dy, None, dtok, dpos.view(pshape), None
+
+
+# ----------------------------------------------------------------------------------------------
+class RnaAttnFn(Function):
+    """SDPA over the 12 chunks of one embedding + dim-major interleave (models/mirror.py:77-99)."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, qkv):
+        qkv = qkv.contiguous()
+        ctx.save_for_backward(qkv)
+        return K.rna_attn_fwd(qkv)
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        return K.rna_attn_bwd(qkv, dout.contiguous())
+
+
+# ----------------------------------------------------------------------------------------------
+class ReparamFn(Function):
+    """z = mu + exp(0.5*logvar)*eps (models/mirror.py:830-833 with the N(0,1) draw made explicit)."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, mu, logvar, eps):
+        mu, logvar, eps = mu.contiguous(), logvar.contiguous(), eps.contiguous()
+        ctx.save_for_backward(logvar, eps)
+        return K.reparam_fwd(mu, logvar, eps)
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, dz):
+        logvar, eps = ctx.saved_tensors
+        dmu = torch.zeros_like(logvar)
+        dlv = torch.zeros_like(logvar)
+        K.reparam_bwd_(dz.contiguous(), logvar, eps, dmu, dlv)
+        return dmu, dlv, None
+
+
+# ----------------------------------------------------------------------------------------------
+class ClipLossFn(Function):
+    """Contrastive loss over logits = scale * W R^T: ClipLoss (losses/mirror_loss.py:37-52, w_row=w_col=0.5) and
+    InfoNCE's implicit-negative branch (losses/info_nce.py:144-164).  `scale` is a 0-d device tensor."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, w, r, scale, w_row, w_col):
+        B, E = w.shape
+        Ep = _r8(E)
+        w16, r16 = K.cast_bf16(w.contiguous(), Ep), K.cast_bf16(r.contiguous(), Ep)
+        raw = torch.empty(B, B, device=w.device, dtype=F32)
+        K.gemm(w16[:, :E], r16[:, :E], out_f32=raw)
+        scale = scale.reshape(()).contiguous()
+        loss, row, col = K.clip_loss_fwd(raw, scale, w_row, w_col)
+        ctx.save_for_backward(w16, r16, raw, scale, row, col)
+        ctx.meta = (B, E, w_row, w_col)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, gout):
+        w16, r16, raw, scale, row, col = ctx.saved_tensors
+        B, E, w_row, w_col = ctx.meta
+        dscale = torch.zeros((), device=gout.device, dtype=F32)
+        G = K.clip_loss_bwd(raw, scale, w_row, w_col, row, col, gout.contiguous(), dscale)
+        Bp = _r8(B)
+        if Bp != B:  # keep the TMA row stride a multiple of 16 B
+            Gp = torch.zeros(B, Bp, device=G.device, dtype=BF16)
+            Gp[:, :B] = G
+            G = Gp
+        dw = torch.empty(B, E, device=gout.device, dtype=F32)
+        dr = torch.empty(B, E, device=gout.device, dtype=F32)
+        K.gemm(G[:, :B], _T(r16[:, :E]), out_f32=dw)          # dW = G R
+        K.gemm(_T(G[:, :B]), _T(w16[:, :E]), out_f32=dr)      # dR = G^T W
+        return dw, dr, dscale, None, None
+
+
+def clip_loss(w, r, scale, w_row=0.5, w_col=0.5):
+    return ClipLossFn.apply(w, r, scale, w_row, w_col)
+
+
+# ----------------------------------------------------------------------------------------------
+class MaskedMseFn(Function):
+    """sum_rows mask * mean_e (a-b)^2 / sum mask (losses/mirror_loss.py:98-103); a, b: [B,T,E] views."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, a, b, mask):
+        out, scratch = K.masked_mse_fwd(a, b, mask.contiguous())
+        ctx.save_for_backward(a, b, mask, scratch)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, g):
+        a, b, mask, scratch = ctx.saved_tensors
+        da = torch.empty(a.shape, device=a.device, dtype=F32) if ctx.needs_input_grad[0] else None
+        db = torch.empty(b.shape, device=a.device, dtype=F32) if ctx.needs_input_grad[1] else None
+        K.masked_mse_bwd(a, b, mask, scratch, g.contiguous(), 1.0, da, False, db, False)
+        return da, db, None
+
+
+class GaussKlFn(Function):
+    """0.5/B * sum (exp(lv) + mu^2 - 1 - lv) over stacked modalities (losses/mirror_loss.py:105-112)."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, mu, lv, B):
+        mu, lv = mu.contiguous(), lv.contiguous()
+        ctx.save_for_backward(mu, lv)
+        ctx.B = B
+        return K.gauss_kl_fwd(mu, lv, B)
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, g):
+        mu, lv = ctx.saved_tensors
+        dmu, dlv = torch.zeros_like(mu), torch.zeros_like(lv)
+        K.gauss_kl_bwd_(mu, lv, ctx.B, g.contiguous(), 1.0, dmu, dlv)
+        return dmu, dlv, None
+
+
+class SymKlFn(Function):
+    """0.5*(KL(r||w)+KL(w||r)) batchmean over softmaxed prototype scores (losses/mirror_loss.py:114-119).
+    scores: [2B,P], WSI rows first."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, scores, B):
+        scores = scores.contiguous()
+        ctx.save_for_backward(scores)
+        ctx.B = B
+        return K.sym_kl_fwd(scores, B)
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, g):
+        (scores,) = ctx.saved_tensors
+        return K.sym_kl_bwd(scores, ctx.B, g.contiguous(), 1.0), None
+
+
+class CombineFn(Function):
+    """total = sum_i w_i * term_i (losses/mirror_loss.py:121-127)."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, terms, weights):
+        ctx.weights = weights
+        return K.loss_combine(terms.contiguous(), weights)
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, g):
+        # five scalars: host-side list -> one tiny tensor op (bookkeeping, not arithmetic of the hot path)
+        return g.reshape(1) * torch.tensor(ctx.weights, device=g.device, dtype=F32), None
+
+
+class StackScalarsFn(Function):
+    """Pack five 0-d device scalars into one [5] tensor (pure pointer bookkeeping: five 4-byte copies)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        out = torch.empty(len(xs), device=xs[0].device, dtype=F32)
+        for i, x in enumerate(xs):
+            K.copy_rows_(x.reshape(1, 1), out[i:i + 1].view(1, 1))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return tuple(g[i] for i in range(g.shape[0]))

@@ -1,0 +1,373 @@
+"""TEST INFRASTRUCTURE: a torch (CPU) re-statement of every entry point of ``mirror_b200.kernels``.
+
+Installed with ``use()`` by the CPU tests so that the host logic — shapes, strides, views, the hand-written
+backward passes in ``mirror_b200/ops.py``, the module wiring in ``mirror_b200/models`` and ``losses`` — can be
+checked against the oracle without a GPU.  It mimics the kernels' precision plan (bf16 operand storage, fp32
+accumulation) so CPU runs also predict the numerical error of the device path.  Never imported by product code.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from mirror_b200 import kernels as K
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+def use():
+    K._TEST_BACKEND = Emu()
+
+
+def release():
+    K._TEST_BACKEND = None
+
+
+def hash_u01(seed, idx):
+    """mb::hash_u01 (csrc/common.cuh) on numpy uint64."""
+    with np.errstate(over="ignore"):
+        z = idx.astype(np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x632BE59BD9B4E019)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def keep_mask(seed, shape, p):
+    """inverted-dropout multiplier over a dense index space of `shape`."""
+    n = int(np.prod(shape))
+    u = hash_u01(seed, np.arange(n, dtype=np.uint64))
+    return torch.from_numpy(np.where(u >= np.float32(p), np.float32(1.0 / (1.0 - p)), np.float32(0.0))).view(*shape)
+
+
+def _act(v, act):
+    if act == K.ACT_RELU:
+        return torch.relu(v)
+    if act == K.ACT_GELU:
+        return F.gelu(v)
+    return v
+
+
+class Emu:
+    launches = 0
+
+    # ------------------------------------------------------------------ GEMM
+    def gemm(self, a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=0, drop_p=0.0, drop_seed=0, res=None,
+             gamma=1.0, beta=0.0, split_k=1):
+        assert a.dtype == BF16 and b.dtype == BF16
+        assert a.stride(-1) == 1 or a.stride(-2) == 1
+        assert b.stride(-1) == 1 or b.stride(-2) == 1
+        for t in (a, b):  # TMA alignment rules of the real kernel
+            ld = t.stride(-2) if t.stride(-1) == 1 else t.stride(-1)
+            assert ld % 8 == 0, f"operand ld {ld} not a multiple of 8"
+            assert (t.storage_offset() * 2) % 16 == 0, "operand base not 16-byte aligned"
+            for s, n in zip(t.stride()[:-2], t.shape[:-2]):
+                assert n == 1 or s % 8 == 0, f"batch stride {s}"
+        acc = torch.matmul(a.float(), b.float().transpose(-1, -2))
+        if split_k > 1:
+            assert out_f32 is not None and out_bf16 is None and bias is None and res is None and act == 0 and drop_p == 0
+            out_f32 += alpha * acc.view(out_f32.shape)
+            return
+        v = alpha * acc
+        if bias is not None:
+            v = v + bias
+        v = _act(v, act)
+        if drop_p > 0:
+            v = v * keep_mask(drop_seed, tuple(v.shape), drop_p)
+        if res is not None:
+            assert res.shape == v.shape and res.stride(-1) == 1
+            v = v + gamma * res.float()
+        if out_f32 is not None:
+            assert out_f32.shape == v.shape and out_f32.stride(-1) == 1
+            if beta != 0.0:
+                v = v + beta * out_f32
+            out_f32.copy_(v)
+        if out_bf16 is not None:
+            assert out_bf16.shape == v.shape and out_bf16.stride(-1) == 1
+            out_bf16.copy_(v.to(BF16))
+
+    # ------------------------------------------------------------ elementwise
+    def cast_bf16(self, src, cols_out=None):
+        cols = src.shape[-1]
+        cols_out = cols_out or cols
+        dst = torch.zeros(*src.shape[:-1], cols_out, dtype=BF16)
+        dst[..., :cols] = src.to(BF16)
+        return dst
+
+    def copy_rows_(self, src, dst):
+        dst.copy_(src)
+        return dst
+
+    def axpy_(self, dst, src, alpha=1.0):
+        dst += alpha * src
+        return dst
+
+    def act_fwd(self, pre, act, drop_p=0.0, seed=0, want_bf16=True, want_f32=False):
+        v = _act(pre, act)
+        if drop_p > 0:
+            v = v * keep_mask(seed, tuple(v.shape), drop_p)
+        return (v.to(BF16) if want_bf16 else None), (v if want_f32 else None)
+
+    def act_bwd(self, dy, pre, act, drop_p=0.0, seed=0, out16=None, out32=None):
+        g = dy.clone()
+        if drop_p > 0:
+            g = g * keep_mask(seed, tuple(g.shape), drop_p)
+        if act == K.ACT_RELU:
+            g = g * (pre > 0)
+        elif act == K.ACT_GELU:
+            x = pre
+            cdf = 0.5 * (1 + torch.erf(x / math.sqrt(2)))
+            pdf = torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+            g = g * (cdf + x * pdf)
+        if out16 is not None:
+            out16.copy_(g.to(BF16))
+        if out32 is not None:
+            out32.copy_(g)
+
+    def wsi_assemble_fwd(self, h, cls, N, add):
+        h[:, 0, :] = cls
+        if add:
+            h[:, 1 + N:, :] = h[:, 1:1 + add, :]
+
+    def wsi_embed_bwd(self, dh, h, N, add, dcls):
+        g = dh[:, 1:1 + N, :].clone()
+        if add:
+            g[:, :add, :] += dh[:, 1 + N:, :]
+        dcls += dh[:, 0, :].sum(0)
+        return (g * (h[:, 1:1 + N, :] > 0)).to(BF16)
+
+    def rank_mask(self, noise, keep):
+        rank = torch.argsort(torch.argsort(noise, dim=1, stable=True), dim=1)
+        return (rank >= keep).float()
+
+    def mask_pos_fwd_(self, r, mask, tok, tok_stride, pos, first):
+        B, T, E = r.shape
+        m = torch.zeros(B, T, 1, dtype=torch.bool)
+        m[:, first:, 0] = mask != 0
+        tokv = tok.reshape(-1)[:E] if tok_stride else tok.reshape(-1)[:1].expand(E)
+        r.copy_(torch.where(m, tokv.view(1, 1, E).expand(B, T, E), r) + pos.view(1, T, E))
+        return r
+
+    def mask_pos_bwd_(self, dy, mask, dtok, tok_stride, dpos, first):
+        B, T, E = dy.shape
+        dpos += dy.sum(0)
+        m = torch.zeros(B, T, 1, dtype=torch.bool)
+        m[:, first:, 0] = mask != 0
+        g = (dy * m).sum((0, 1))
+        if tok_stride:
+            dtok[:E] += g
+        else:
+            dtok[:1] += g.sum()
+        dy.mul_(~m)
+        return dy
+
+    def landmark_fwd(self, qkv, m, seg):
+        B, n, E3 = qkv.shape
+        E = E3 // 3
+        return qkv[:, :, :2 * E].float().view(B, m, seg, 2 * E).sum(2).div(seg).to(BF16)
+
+    def dqkv_finish(self, dqkv32, dlm32, seg):
+        B, n, E3 = dqkv32.shape
+        E = E3 // 3
+        out = dqkv32.clone()
+        out[:, :, :2 * E] += dlm32.repeat_interleave(seg, dim=1) / seg
+        return out.to(BF16)
+
+    def colsum_(self, x, out):
+        out += x.float().sum(0)
+        return out
+
+    def reparam_fwd(self, mu, logvar, eps):
+        return mu + torch.exp(0.5 * logvar) * eps
+
+    def reparam_bwd_(self, dz, logvar, eps, dmu, dlogvar):
+        dmu += dz
+        dlogvar += dz * eps * 0.5 * torch.exp(0.5 * logvar)
+
+    # ------------------------------------------------------- norms / softmax
+    def layernorm_fwd(self, x, gamma, beta, eps, n_out=None, pad=0, want_bf16=True, want_f32=False):
+        B, S, E = x.shape
+        n_out = n_out or S
+        mean = x.mean(-1)
+        var = x.var(-1, unbiased=False)
+        rstd = torch.rsqrt(var + eps)
+        y = (x - mean[..., None]) * rstd[..., None] * gamma + beta
+        full = torch.zeros(B, n_out, E)
+        full[:, pad:pad + S] = y
+        return (full.to(BF16) if want_bf16 else None), (full if want_f32 else None), mean, rstd
+
+    def layernorm_bwd(self, dy, x, gamma, mean, rstd, pad, dx, add, dgamma, dbeta):
+        B, S, E = x.shape
+        g = dy[:, pad:pad + S]
+        xh = (x - mean[..., None]) * rstd[..., None]
+        gg = g * gamma
+        d = rstd[..., None] * (gg - gg.mean(-1, keepdim=True) - xh * (gg * xh).mean(-1, keepdim=True))
+        dgamma += (g * xh).sum((0, 1))
+        dbeta += g.sum((0, 1))
+        dx.copy_(d + add if add is not None else d)
+
+    def softmax_fwd(self, x, want_bf16=True, want_f32=False):
+        p = torch.softmax(x, -1)
+        return (p.to(BF16) if want_bf16 else None), (p if want_f32 else None)
+
+    def softmax_bwd(self, y16, dy, scale=1.0, want_bf16=True, want_f32=False):
+        y = y16.float()
+        d = scale * y * (dy - (dy * y).sum(-1, keepdim=True))
+        return (d.to(BF16) if want_bf16 else None), (d if want_f32 else None)
+
+    def l2norm_fwd(self, x, eps):
+        norm = x.norm(dim=-1).clamp_min(eps)
+        return x / norm[:, None], norm
+
+    def l2norm_bwd(self, dy, x, norm):
+        y = x / norm[:, None]
+        return (dy - y * (y * dy).sum(-1, keepdim=True)) / norm[:, None]
+
+    # --------------------------------------------------------------- nystrom
+    def res_conv_fwd(self, qkv, w):
+        B, n, E3 = qkv.shape
+        E = E3 // 3
+        h = w.shape[0]
+        v = qkv[:, :, 2 * E:].float().view(B, n, h, E // h).permute(0, 2, 1, 3)
+        o = F.conv2d(v, w.view(h, 1, -1, 1), padding=(w.shape[1] // 2, 0), groups=h)
+        return o.permute(0, 2, 1, 3).reshape(B, n, E).to(BF16)
+
+    @torch.enable_grad()
+    def res_conv_bwd_(self, dout16, qkv, w, dqkv32, dw):
+        B, n, E3 = qkv.shape
+        E = E3 // 3
+        h = w.shape[0]
+        v = qkv[:, :, 2 * E:].float().view(B, n, h, E // h).permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+        ww = w.view(h, 1, -1, 1).clone().requires_grad_(True)
+        o = F.conv2d(v, ww, padding=(w.shape[1] // 2, 0), groups=h)
+        go = dout16.float().view(B, n, h, E // h).permute(0, 2, 1, 3)
+        gv, gw = torch.autograd.grad(o, (v, ww), go)
+        dqkv32[:, :, 2 * E:] += gv.permute(0, 2, 1, 3).reshape(B, n, E)
+        dw += gw.view(h, -1)
+
+    def pinv_init(self, a2):
+        ax = a2.abs()
+        rs, cs = ax.sum(-1), ax.sum(-2)
+        scratch = torch.zeros(8)
+        scratch[0], scratch[1] = rs.max(), cs.max()
+        scratch[3], scratch[4] = float(rs.flatten().argmax()), float(cs.flatten().argmax())
+        z = a2.transpose(-1, -2) / (scratch[0] * scratch[1])
+        z = z.contiguous()
+        return z, z.to(BF16), scratch
+
+    def pinv_init_bwd(self, gz0, z0_32, scratch, gx, accumulate):
+        c, r = scratch[0], scratch[1]
+        D = c * r
+        dD = -(gz0 * z0_32).sum() / D
+        m = gz0.shape[-1]
+        v = gz0.transpose(-1, -2) / D
+        v = v.contiguous()
+        vf = v.view(-1, m, m)
+        ir, ic = int(scratch[3]), int(scratch[4])
+        vf[ir // m, ir % m, :] += dD * r
+        vf[ic // m, :, ic % m] += dD * c
+        if accumulate:
+            gx += v
+        else:
+            gx.copy_(v)
+
+    # ------------------------------------------------------------------ ppeg
+    def ppeg_fwd(self, x, w7, w5, w3, b7, b5, b3, H):
+        B, S, E = x.shape
+        wm = w7.view(E, 7, 7).clone()
+        wm[:, 1:6, 1:6] += w5.view(E, 5, 5)
+        wm[:, 2:5, 2:5] += w3.view(E, 3, 3)
+        wm[:, 3, 3] += 1.0
+        f = x[:, 1:].transpose(1, 2).reshape(B, E, H, H)
+        y = F.conv2d(f, wm.view(E, 1, 7, 7), b7 + b5 + b3, padding=3, groups=E)
+        return torch.cat([x[:, :1], y.flatten(2).transpose(1, 2)], 1), wm.view(E, 49).t().contiguous()
+
+    @torch.enable_grad()
+    def ppeg_bwd(self, dy, x, wm, H, dw7, dw5, dw3, db7, db5, db3):
+        B, S, E = x.shape
+        w = wm.t().reshape(E, 1, 7, 7).clone().requires_grad_(True)
+        f = x[:, 1:].transpose(1, 2).reshape(B, E, H, H).clone().requires_grad_(True)
+        y = F.conv2d(f, w, None, padding=3, groups=E)
+        g = dy[:, 1:].transpose(1, 2).reshape(B, E, H, H)
+        gf, gw = torch.autograd.grad(y, (f, w), g)
+        gw = gw.view(E, 7, 7)
+        dw7 += gw.reshape(E, 49)
+        dw5 += gw[:, 1:6, 1:6].reshape(E, 25)
+        dw3 += gw[:, 2:5, 2:5].reshape(E, 9)
+        gb = g.sum((0, 2, 3))
+        db7 += gb
+        db5 += gb
+        db3 += gb
+        return torch.cat([dy[:, :1], gf.flatten(2).transpose(1, 2)], 1)
+
+    # -------------------------------------------------------------- rna attn
+    def _rna(self, qkv):
+        B, E3 = qkv.shape
+        E = E3 // 3
+        t = qkv.view(B, 3, 12, E // 12)
+        q, k, v = t[:, 0], t[:, 1], t[:, 2]
+        a = torch.softmax(q @ k.transpose(-1, -2) * (E // 12) ** -0.5, -1)
+        return (a @ v).transpose(1, 2).reshape(B, E)
+
+    def rna_attn_fwd(self, qkv):
+        return self._rna(qkv)
+
+    @torch.enable_grad()
+    def rna_attn_bwd(self, qkv, dout):
+        q = qkv.clone().requires_grad_(True)
+        (g,) = torch.autograd.grad(self._rna(q), q, dout)
+        return g
+
+    # ---------------------------------------------------------------- losses
+    def clip_loss_fwd(self, raw, scale, w_row, w_col):
+        l = scale * raw
+        row, col = torch.logsumexp(l, 1), torch.logsumexp(l, 0)
+        d = l.diagonal()
+        return (w_row * (row - d) + w_col * (col - d)).mean(), row, col
+
+    def clip_loss_bwd(self, raw, scale, w_row, w_col, row, col, gout, dscale):
+        B = raw.shape[0]
+        l = scale * raw
+        p = w_row * torch.exp(l - row[:, None]) + w_col * torch.exp(l - col[None, :]) - (w_row + w_col) * torch.eye(B)
+        p = p * gout / B
+        dscale += (p * raw).sum()
+        return (p * scale).to(BF16)
+
+    def masked_mse_fwd(self, a, b, mask):
+        E = a.shape[-1]
+        num = (((a - b) ** 2).sum(-1) / E * mask).sum()
+        den = mask.sum()
+        return num / den, torch.stack([num, den])
+
+    def masked_mse_bwd(self, a, b, mask, scratch, gout, gw, da, acc_a, db, acc_b):
+        E = a.shape[-1]
+        v = gout * gw * 2.0 / (E * scratch[1]) * mask[..., None] * (a - b)
+        if da is not None:
+            da.copy_(da + v if acc_a else v)
+        if db is not None:
+            db.copy_(db - v if acc_b else -v)
+
+    def gauss_kl_fwd(self, mu, logvar, B):
+        return 0.5 / B * (logvar.exp() + mu ** 2 - 1 - logvar).sum()
+
+    def gauss_kl_bwd_(self, mu, logvar, B, gout, gw, dmu, dlogvar):
+        k = gout * gw / B
+        dmu += k * mu
+        dlogvar += k * 0.5 * (logvar.exp() - 1)
+
+    def _symkl(self, scores, B):
+        lw, lr = F.log_softmax(scores[:B], -1), F.log_softmax(scores[B:], -1)
+        return 0.5 / B * ((lr.exp() - lw.exp()) * (lr - lw)).sum()
+
+    def sym_kl_fwd(self, scores, B):
+        return self._symkl(scores, B)
+
+    @torch.enable_grad()
+    def sym_kl_bwd(self, scores, B, gout, gw):
+        s = scores.clone().requires_grad_(True)
+        (g,) = torch.autograd.grad(self._symkl(s, B), s)
+        return g * gout * gw
+
+    def loss_combine(self, terms5, weights):
+        return (terms5 * torch.tensor(weights, dtype=F32)).sum()
