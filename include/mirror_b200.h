@@ -38,7 +38,7 @@ int mirror_device_supported(void);
  * Batched GEMM on 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed, persistent).
  *
  *   for every (b2,b1):  acc[M,N] = sum_k A[m,k] * B[n,k]            (bf16 x bf16 -> fp32)
- *   v = alpha*acc + bias[n];  v = act(v);  v = dropout(v);
+ *   v = alpha*acc + diag*[m==n] + bias[n];  v = act(v);  v = dropout(v);
  *   v += gamma * R[m,n] + beta * out_f32_old[m,n];   out_f32 = v;  out_bf16 = bf16(v)
  *
  * Replaces every nn.Linear / einsum / `@` of the hot path:
@@ -77,6 +77,7 @@ typedef struct {
   int64_t ldc16, c16_bs1, c16_bs2;
   int32_t split_k; /* >1: K is split over CTAs and fp32 partials are atomically added into out_f32
                       (caller pre-zeroes it); only alpha is applied */
+  float diag;      /* added to alpha*acc where m == n (e.g. E = I - a2.z of the Moore-Penrose step) */
 } mirror_gemm_args;
 
 int mirror_gemm_bf16(const mirror_gemm_args* args, mirror_stream_t stream);
@@ -91,6 +92,14 @@ int mirror_gemm_bf16_simt(const mirror_gemm_args* args, mirror_stream_t stream);
  * (train_mirror.py:1145) and `h.float()` (models/mirror.py:652). */
 int mirror_cast_f32_bf16(const float* src, int64_t rows, int32_t cols, int64_t lds, void* dst, int32_t cols_out, int64_t ldd,
                          mirror_stream_t stream);
+/* bf16 split-3 operand: hi = bf16(x), lo = bf16(x-hi); blocks (hi,lo,hi) (order 0) or (hi,hi,lo) (order 1), side by side
+ * (stack_rows 0: dst [rows_out, 3*cols_out]) or stacked (stack_rows 1: dst [3*rows_out, cols_out]), zero padded.  One tensor-core
+ * GEMM over the tripled contraction then gives hi.hi + lo.hi + hi.lo, i.e. an (almost) fp32 product.  Used where bf16 operand
+ * rounding is visible in the result at negligible cost: _fc1 (models/mirror.py:654; its ReLU mask must match the fp32 reference,
+ * every flipped mask bit is a 100 % error in that element's weight gradient — SURVEY.md §8c(v)), and every M = batch-sized Linear
+ * (RNA encoder, heads, style/prototype heads, contrastive logits), which are weight-bandwidth-bound anyway. */
+int mirror_cast_split3(const float* src, int64_t rows, int32_t cols, int64_t lds, void* dst, int64_t rows_out, int32_t cols_out,
+                       int32_t stack_rows, int32_t order, mirror_stream_t stream);
 /* dst[r,0:cols] = src[r,0:cols] with row strides: gathers `wsi_emb[:, 0, :]` (models/mirror.py:896) into a dense block */
 int mirror_copy_rows_f32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd, mirror_stream_t stream);
 /* dst += alpha*src  (gradient accumulation of the autograd graph) */
@@ -188,9 +197,9 @@ int mirror_rna_attn_bwd(const float* qkv, const float* dout, int32_t B, int32_t 
  * on raw = W.R^T (unscaled, from mirror_gemm_bf16); logits = (*scale) * raw. */
 int mirror_clip_loss_fwd(const float* raw, int32_t B, const float* scale, float w_row, float w_col, float* row_lse, float* col_lse,
                          float* loss, mirror_stream_t stream);
-/* G = d loss / d raw (bf16, operand of dW = G.R and dR = G^T.W); dscale += d loss / d scale */
+/* G = d loss / d raw (bf16 and/or f32; operand of dW = G.R and dR = G^T.W); dscale += d loss / d scale */
 int mirror_clip_loss_bwd(const float* raw, int32_t B, const float* scale, float w_row, float w_col, const float* row_lse,
-                         const float* col_lse, const float* gout, void* G_bf16, float* dscale, mirror_stream_t stream);
+                         const float* col_lse, const float* gout, void* G_bf16, float* G_f32, float* dscale, mirror_stream_t stream);
 /* retention terms, losses/mirror_loss.py:98-103: out = sum_rows mask*mean_e (a-b)^2 / sum mask; batches strided by a_bs / b_bs */
 int mirror_masked_mse_fwd(const float* a, int64_t a_bs, const float* b, int64_t b_bs, const float* mask, int32_t B, int32_t T,
                           int32_t E, float* scratch2, float* out, mirror_stream_t stream);

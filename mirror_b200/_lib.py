@@ -34,6 +34,7 @@ class GemmArgs(ctypes.Structure):
         ("out_bf16", ctypes.c_void_p),
         ("ldc16", ctypes.c_int64), ("c16_bs1", ctypes.c_int64), ("c16_bs2", ctypes.c_int64),
         ("split_k", ctypes.c_int32),
+        ("diag", ctypes.c_float),
     ]
 
 
@@ -59,6 +60,7 @@ SIGNATURES = {
     "mirror_gemm_bf16": [_P, _P],
     "mirror_gemm_bf16_simt": [_P, _P],
     "mirror_cast_f32_bf16": [_P, _I64, _I32, _I64, _P, _I32, _I64, _P],
+    "mirror_cast_split3": [_P, _I64, _I32, _I64, _P, _I64, _I32, _I32, _I32, _P],
     "mirror_copy_rows_f32": [_P, _I64, _I64, _I32, _P, _I64, _P],
     "mirror_axpy_f32": [_P, _P, _I64, _F, _P],
     "mirror_act_fwd": [_P, _I64, _I32, _F, _U64, _P, _P, _P],
@@ -88,7 +90,7 @@ SIGNATURES = {
     "mirror_rna_attn_fwd": [_P, _I32, _I32, _P, _P, _P],
     "mirror_rna_attn_bwd": [_P, _P, _I32, _I32, _P, _P, _P],
     "mirror_clip_loss_fwd": [_P, _I32, _P, _F, _F, _P, _P, _P, _P],
-    "mirror_clip_loss_bwd": [_P, _I32, _P, _F, _F, _P, _P, _P, _P, _P, _P],
+    "mirror_clip_loss_bwd": [_P, _I32, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "mirror_masked_mse_fwd": [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P],
     "mirror_masked_mse_bwd": [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _F, _P, _I64, _I32, _P, _I64, _I32, _P],
     "mirror_gauss_kl_fwd": [_P, _P, _I64, _I32, _P, _P],

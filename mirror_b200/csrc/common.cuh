@@ -101,7 +101,7 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
 // ---- GEMM epilogue shared by the tcgen05 kernel and the SIMT cross-check kernel ----
 struct Epi {
   int M, N, batch1;
-  float alpha;
+  float alpha, diag;
   const float* bias;
   int act;
   float drop_p, drop_scale;
@@ -124,6 +124,7 @@ __device__ __forceinline__ void epi_store_scalar(const Epi& e, float acc, int b1
     return;
   }
   float v = e.alpha * acc;
+  if (row == col) v += e.diag;
   if (e.bias) v += e.bias[col];
   if (e.act == MIRROR_ACT_RELU) v = fmaxf(v, 0.f);
   else if (e.act == MIRROR_ACT_GELU) v = gelu_erf(v);

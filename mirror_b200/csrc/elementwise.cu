@@ -39,6 +39,28 @@ __global__ void cast_vec_kernel(const float4* __restrict__ src, uint4* __restric
   }
 }
 
+// bf16 "split-3" operand for near-fp32 products on bf16 tensor cores: x = hi + lo (+ O(2^-17)).
+// order 0: (hi, lo, hi)   order 1: (hi, hi, lo)   so that  <A0, A1> over the tripled contraction = hi.hi + lo.hi + hi.lo
+// The three blocks are laid side by side (stack_rows = 0: dst is [rows_out, 3*cols_out]) or on top of each other
+// (stack_rows = 1: dst is [3*rows_out, cols_out]); rows/cols beyond the source extent are zero.
+__global__ void cast_split3_kernel(const float* __restrict__ src, long long rows, int cols, long long lds,
+                                   bf16* __restrict__ dst, long long rows_out, int cols_out, int stack_rows, int order) {
+  const long long total = rows_out * cols_out;
+  const long long ldd = stack_rows ? cols_out : 3LL * cols_out;
+  const long long blk = stack_rows ? rows_out * (long long)cols_out : cols_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols_out;
+    const int c = (int)(i - r * cols_out);
+    const float x = (r < rows && c < cols) ? src[r * lds + c] : 0.f;
+    const bf16 hi = __float2bfloat16(x);
+    const bf16 lo = __float2bfloat16(x - __bfloat162float(hi));
+    bf16* d = dst + r * ldd + c;
+    d[0] = hi;
+    d[blk] = order == 0 ? lo : hi;
+    d[2 * blk] = order == 0 ? hi : lo;
+  }
+}
+
 // strided 2-D copy (gathers e.g. the cls rows of [B,N+1,E] into a dense [B,E] block)
 __global__ void copy_rows_kernel(const float* __restrict__ src, long long lds, long long rows, int cols, float* __restrict__ dst,
                                  long long ldd) {
@@ -282,6 +304,16 @@ extern "C" int mirror_cast_f32_bf16(const float* src, int64_t rows, int32_t cols
     cast_pad_kernel<<<grid_for(rows * (long long)cols_out, 256), 256, 0, STREAM>>>(src, rows, cols, lds,
                                                                                  reinterpret_cast<bf16*>(dst), cols_out, ldd);
   }
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_cast_split3(const float* src, int64_t rows, int32_t cols, int64_t lds, void* dst, int64_t rows_out,
+                                  int32_t cols_out, int32_t stack_rows, int32_t order, mirror_stream_t stream) {
+  MB_CHECK_ARG(src && dst && rows > 0 && cols > 0 && cols_out >= cols && rows_out >= rows && lds >= cols && (order == 0 || order == 1),
+               "cast_split3: bad args");
+  cast_split3_kernel<<<grid_for(rows_out * (long long)cols_out, 256), 256, 0, STREAM>>>(
+      src, rows, cols, lds, reinterpret_cast<bf16*>(dst), rows_out, cols_out, stack_rows, order);
   MB_LAUNCH_CHECK();
   return 0;
 }

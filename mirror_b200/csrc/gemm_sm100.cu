@@ -48,6 +48,10 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, const uint32_t (&ac
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = e.alpha * __uint_as_float(acc[j]);
+  if (e.diag != 0.f && row >= col0 && row < col0 + 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += (col0 + j == row) ? e.diag : 0.f;
+  }
   if (e.bias) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -351,10 +355,10 @@ int fill_epi(const mirror_gemm_args* g, Epi* e) {
   MB_CHECK_ARG(g->out_f32 || g->out_bf16, "gemm: no output");
   MB_CHECK_ARG(g->beta == 0.f || g->out_f32, "gemm: beta needs out_f32");
   MB_CHECK_ARG(g->drop_p >= 0.f && g->drop_p < 1.f, "gemm: drop_p out of range");
-  MB_CHECK_ARG(g->split_k <= 1 || (g->out_f32 && !g->out_bf16 && !g->bias && !g->res && g->act == 0 && g->drop_p == 0.f),
+  MB_CHECK_ARG(g->split_k <= 1 || (g->out_f32 && !g->out_bf16 && !g->bias && !g->res && g->act == 0 && g->drop_p == 0.f && g->diag == 0.f),
                "gemm: split_k supports only alpha and an fp32 accumulate target");
   e->M = g->M; e->N = g->N; e->batch1 = g->batch1;
-  e->alpha = g->alpha; e->bias = g->bias; e->act = g->act;
+  e->alpha = g->alpha; e->diag = g->diag; e->bias = g->bias; e->act = g->act;
   e->drop_p = g->drop_p; e->drop_scale = 1.f / (1.f - g->drop_p); e->drop_seed = g->drop_seed;
   e->res = g->res; e->res_is_bf16 = g->res_is_bf16; e->gamma = g->gamma;
   e->ldr = g->ldr; e->r_bs1 = g->r_bs1; e->r_bs2 = g->r_bs2;

@@ -57,7 +57,8 @@ __global__ void clip_loss_kernel(const float* __restrict__ raw, int B, const flo
 // dscale += sum_ij (G/s) * raw
 __global__ void clip_grad_kernel(const float* __restrict__ raw, int B, const float* __restrict__ scale,
                                  const float* __restrict__ row_lse, const float* __restrict__ col_lse, float wr, float wc,
-                                 const float* __restrict__ gout, bf16* __restrict__ G, float* __restrict__ dscale) {
+                                 const float* __restrict__ gout, bf16* __restrict__ G, float* __restrict__ G32,
+                                 float* __restrict__ dscale) {
   __shared__ float sh[32];
   const float s = *scale, g = *gout / B;
   float acc = 0.f;
@@ -70,7 +71,8 @@ __global__ void clip_grad_kernel(const float* __restrict__ raw, int B, const flo
     if (i == j) p -= wr + wc;
     p *= g;
     acc += p * r;
-    G[idx] = __float2bfloat16(p * s);
+    if (G) G[idx] = __float2bfloat16(p * s);
+    if (G32) G32[idx] = p * s;
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0 && dscale) atomicAdd(dscale, acc);
@@ -231,11 +233,11 @@ extern "C" int mirror_clip_loss_fwd(const float* raw, int32_t B, const float* sc
   return 0;
 }
 extern "C" int mirror_clip_loss_bwd(const float* raw, int32_t B, const float* scale, float w_row, float w_col,
-                                    const float* row_lse, const float* col_lse, const float* gout, void* G_bf16, float* dscale,
-                                    mirror_stream_t stream) {
-  MB_CHECK_ARG(raw && scale && row_lse && col_lse && gout && G_bf16 && B > 0, "clip_loss_bwd: bad args");
+                                    const float* row_lse, const float* col_lse, const float* gout, void* G_bf16, float* G_f32,
+                                    float* dscale, mirror_stream_t stream) {
+  MB_CHECK_ARG(raw && scale && row_lse && col_lse && gout && (G_bf16 || G_f32) && B > 0, "clip_loss_bwd: bad args");
   clip_grad_kernel<<<ew_grid((long long)B * B, 256), 256, 0, STREAM>>>(raw, B, scale, row_lse, col_lse, w_row, w_col, gout,
-                                                                       reinterpret_cast<bf16*>(G_bf16), dscale);
+                                                                       reinterpret_cast<bf16*>(G_bf16), G_f32, dscale);
   MB_LAUNCH_CHECK();
   return 0;
 }

@@ -53,7 +53,7 @@ def _major(t):
 
 
 def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NONE, drop_p=0.0, drop_seed=0,
-         res=None, gamma=1.0, beta=0.0, split_k=1, simt=False):
+         res=None, gamma=1.0, beta=0.0, split_k=1, diag=0.0, simt=False):
     """C[..,M,N] = epilogue(A[..,M,K] @ B[..,N,K]^T); see mirror_gemm_args.
 
     ``a`` / ``b`` are bf16 views whose last two dims are (M,K) / (N,K); either
@@ -62,7 +62,8 @@ def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NON
     """
     if _TEST_BACKEND is not None:
         return _TEST_BACKEND.gemm(a, b, out_f32=out_f32, out_bf16=out_bf16, alpha=alpha, bias=bias, act=act,
-                                  drop_p=drop_p, drop_seed=drop_seed, res=res, gamma=gamma, beta=beta, split_k=split_k)
+                                  drop_p=drop_p, drop_seed=drop_seed, res=res, gamma=gamma, beta=beta, split_k=split_k,
+                                  diag=diag)
     a4, b4 = _as4(_cuda(a, torch.bfloat16)), _as4(_cuda(b, torch.bfloat16))
     B2, B1, M, K = a4.shape
     N = b4.shape[2]
@@ -85,7 +86,7 @@ def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NON
         if r4.dtype not in (torch.bfloat16, torch.float32):
             raise TypeError("residual must be bf16 or f32")
         g.ldr, g.r_bs1, g.r_bs2 = r4.stride(2), r4.stride(1), r4.stride(0)
-    g.gamma, g.beta, g.split_k = gamma, beta, split_k
+    g.gamma, g.beta, g.split_k, g.diag = gamma, beta, split_k, diag
     for o, dt, name in ((out_f32, torch.float32, "32"), (out_bf16, torch.bfloat16, "16")):
         if o is None:
             continue
@@ -151,6 +152,18 @@ def cast_bf16(src, cols_out=None):
     rows = src.numel() // cols
     dst = torch.empty(*src.shape[:-1], cols_out, device=src.device, dtype=BF16)
     _call("mirror_cast_f32_bf16", _p(src, F32), rows, cols, lds, _p(dst), cols_out, cols_out)
+    return dst
+
+
+@_op
+def cast_split3(src, rows_out, cols_out, stack_rows, order):
+    """2-D f32 view (unit column stride) -> bf16 split-3 operand: [rows_out, 3*cols_out] (stack_rows=0) or
+    [3*rows_out, cols_out] (stack_rows=1); blocks (hi,lo,hi) for order 0, (hi,hi,lo) for order 1."""
+    rows, cols = src.shape
+    assert src.stride(1) == 1 or cols == 1
+    shape = (3 * rows_out, cols_out) if stack_rows else (rows_out, 3 * cols_out)
+    dst = torch.empty(shape, device=src.device, dtype=BF16)
+    _call("mirror_cast_split3", _p(src, F32), rows, cols, src.stride(0), _p(dst), rows_out, cols_out, int(stack_rows), order)
     return dst
 
 
@@ -423,11 +436,12 @@ def clip_loss_fwd(raw, scale, w_row, w_col):
 
 
 @_op
-def clip_loss_bwd(raw, scale, w_row, w_col, row, col, gout, dscale):
-    """returns G (bf16 [B,B]) = d loss / d raw; dscale (0-d f32) is accumulated."""
+def clip_loss_bwd(raw, scale, w_row, w_col, row, col, gout, dscale, want_f32=False):
+    """returns G = d loss / d raw as bf16 [B,B] (or f32 when want_f32); dscale (0-d f32) is accumulated."""
     B = raw.shape[0]
-    G = torch.empty(B, B, device=raw.device, dtype=BF16)
-    _call("mirror_clip_loss_bwd", _p(raw, F32), B, _p(scale, F32), w_row, w_col, _p(row), _p(col), _p(gout, F32), _p(G), _p(dscale))
+    G = torch.empty(B, B, device=raw.device, dtype=F32 if want_f32 else BF16)
+    _call("mirror_clip_loss_bwd", _p(raw, F32), B, _p(scale, F32), w_row, w_col, _p(row), _p(col), _p(gout, F32),
+          None if want_f32 else _p(G), _p(G) if want_f32 else None, _p(dscale))
     return G
 
 

@@ -67,10 +67,17 @@ def colsum(x, cols):
 
 
 # ----------------------------------------------------------------------------------------------
+PRECISE_ROWS = 1024  # Linears with at most this many rows are weight-bandwidth-bound: run them fp32-grade (split-3 bf16)
+
+
 class LinearFn(Function):
     """y = [res +] dropout(x @ W^T + b) [+ row_res broadcast over rows].  nn.Linear of the heads, the RNA encoder and the
     style MLPs (models/mirror.py:70,74,470-495,594-605,823-827; timm Mlp fc1/fc2) with the following Dropout and residual
-    add of Block.forward (:149-152) fused into the GEMM epilogue.  x16: optional bf16 copy of x."""
+    add of Block.forward (:149-152) fused into the GEMM epilogue.  x16: optional bf16 copy of x.
+
+    rows <= PRECISE_ROWS (everything whose M is the batch size): operands are split into bf16 hi/lo parts and the three
+    cross products run as ONE tensor-core GEMM over a tripled contraction, forward and backward, so these layers are
+    fp32-accurate; their cost is the weight stream, not the FLOPs.  Larger inputs use plain bf16 operands."""
 
     @staticmethod
     @_cfwd
@@ -79,12 +86,7 @@ class LinearFn(Function):
         lead = x.shape[:-1]
         rows = x.numel() // Kd
         Kp = _r8(Kd)
-        if x16 is None or Kp != Kd:
-            x2 = x.reshape(rows, Kd) if x.is_contiguous() or x.dim() == 2 else x.contiguous().view(rows, Kd)
-            x16 = K.cast_bf16(x2, Kp)
-        else:
-            x16 = x16.reshape(rows, Kd)
-        w16 = K.cast_bf16(weight, Kp)
+        precise = rows <= PRECISE_ROWS
         y = torch.empty(*lead, N, device=x.device, dtype=F32)  # returned as-is (no view) so callers may update it in place
         assert row_res is None or res is None
         r = None
@@ -92,36 +94,67 @@ class LinearFn(Function):
             r = row_res.reshape(1, N).expand(rows, N)
         elif res is not None:
             r = res.contiguous().view(rows, N)
-        K.gemm(x16[:, :Kd], w16[:, :Kd], out_f32=y.view(rows, N), bias=bias, res=r, drop_p=drop_p, drop_seed=seed)
-        ctx.save_for_backward(x16, w16)
+        if precise:
+            x2 = x if x.dim() == 2 and x.stride(1) == 1 else x.contiguous().view(rows, Kd)
+            K.gemm(K.cast_split3(x2, rows, Kp, False, 0), K.cast_split3(weight, N, Kp, False, 1), out_f32=y.view(rows, N),
+                   bias=bias, res=r, drop_p=drop_p, drop_seed=seed)
+            ctx.save_for_backward(x2, weight)
+        else:
+            if x16 is None or Kp != Kd:
+                x2 = x.reshape(rows, Kd) if x.is_contiguous() or x.dim() == 2 else x.contiguous().view(rows, Kd)
+                x16 = K.cast_bf16(x2, Kp)
+            else:
+                x16 = x16.reshape(rows, Kd)
+            w16 = K.cast_bf16(weight, Kp)
+            K.gemm(x16[:, :Kd], w16[:, :Kd], out_f32=y.view(rows, N), bias=bias, res=r, drop_p=drop_p, drop_seed=seed)
+            ctx.save_for_backward(x16, w16)
         ctx.meta = (rows, N, Kd, bias is not None, tuple(row_res.shape) if row_res is not None else None, res is not None,
-                    tuple(x.shape), drop_p, seed)
+                    tuple(x.shape), drop_p, seed, precise)
         return y
 
     @staticmethod
     @once_differentiable
     @_cbwd
     def backward(ctx, dy):
-        x16, w16 = ctx.saved_tensors
-        rows, N, Kd, has_b, has_rr, has_res, xshape, drop_p, seed = ctx.meta
-        Np = _r8(N)
+        xs, ws = ctx.saved_tensors
+        rows, N, Kd, has_b, has_rr, has_res, xshape, drop_p, seed, precise = ctx.meta
+        Np, Kp = _r8(N), _r8(Kd)
         dy2 = dy.reshape(rows, N)
         if dy2.stride(1) != 1 or (dy2.stride(0) != N and rows > 1):
             dy2 = dy2.contiguous()
-        if drop_p > 0:
-            dy16 = torch.empty(rows, Np, device=dy.device, dtype=BF16)
-            K.act_bwd(dy2.view(1, rows, N), None, K.ACT_NONE, drop_p, seed, out16=dy16[:, :N].unsqueeze(0))
-        else:
-            dy16 = K.cast_bf16(dy2, Np)
         dx = dw = db = drr = dres = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty(rows, Kd, device=dy.device, dtype=F32)
-            K.gemm(dy16[:, :N], _T(w16[:, :Kd]), out_f32=dx)
-            dx = dx.view(xshape)
-        if ctx.needs_input_grad[1]:
-            dw = wgrad(dy16, x16, N, Kd)
-        if has_b and ctx.needs_input_grad[2]:
-            db = colsum(dy16, N)
+        if precise:
+            g = dy2
+            if drop_p > 0:
+                g = torch.empty(rows, N, device=dy.device, dtype=F32)
+                K.act_bwd(dy2.view(1, rows, N), None, K.ACT_NONE, drop_p, seed, out32=g.view(1, rows, N))
+            Rp = _r8(rows)
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(rows, Kd, device=dy.device, dtype=F32)
+                wst = K.cast_split3(ws, Np, Kp, True, 1)                                  # [3Np, Kp] = (hi; hi; lo)
+                K.gemm(K.cast_split3(g, rows, Np, False, 0), _T(wst[:, :Kd]), out_f32=dx)  # dX = dY W
+                dx = dx.view(xshape)
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty(N, Kd, device=dy.device, dtype=F32)
+                gst = K.cast_split3(g, Rp, Np, True, 0)                                    # [3Rp, Np]
+                xst = K.cast_split3(xs, Rp, Kp, True, 1)                                   # [3Rp, Kp]
+                K.gemm(_T(gst[:, :N]), _T(xst[:, :Kd]), out_f32=dw)                        # dW = dY^T X
+            if has_b and ctx.needs_input_grad[2]:
+                db = colsum(g, N)
+        else:
+            if drop_p > 0:
+                dy16 = torch.empty(rows, Np, device=dy.device, dtype=BF16)
+                K.act_bwd(dy2.view(1, rows, N), None, K.ACT_NONE, drop_p, seed, out16=dy16[:, :N].unsqueeze(0))
+            else:
+                dy16 = K.cast_bf16(dy2, Np)
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(rows, Kd, device=dy.device, dtype=F32)
+                K.gemm(dy16[:, :N], _T(ws[:, :Kd]), out_f32=dx)
+                dx = dx.view(xshape)
+            if ctx.needs_input_grad[1]:
+                dw = wgrad(dy16, xs, N, Kd)
+            if has_b and ctx.needs_input_grad[2]:
+                db = colsum(dy16, N)
         if has_rr is not None and ctx.needs_input_grad[3]:
             drr = colsum(dy2, N).view(has_rr)  # row_res is added after the dropout
         if has_res and ctx.needs_input_grad[5]:
@@ -254,10 +287,11 @@ class WsiEmbedFn(Function):
         add = H * H - N
         S = H * H + 1
         Dp = _r8(Dw)
-        x16 = K.cast_bf16(wsi.contiguous().view(B * N, Dw), Dp).view(B, N, Dp)
-        w16 = K.cast_bf16(w, Dp)
+        # split-3 bf16 operands ([hi|lo|hi] x [hi|hi|lo]): an fp32-grade product, so the ReLU mask matches the reference
+        x16 = K.cast_split3(wsi.contiguous().view(B * N, Dw), B * N, Dp, False, 0).view(B, N, 3 * Dp)
+        w16 = K.cast_split3(w.contiguous(), E, Dp, False, 1)
         h = torch.empty(B, S, E, device=wsi.device, dtype=F32)
-        K.gemm(x16[:, :, :Dw], w16[:, :Dw].unsqueeze(0).expand(B, E, Dw), out_f32=h[:, 1:1 + N, :], bias=b, act=K.ACT_RELU)
+        K.gemm(x16, w16.unsqueeze(0).expand(B, E, 3 * Dp), out_f32=h[:, 1:1 + N, :], bias=b, act=K.ACT_RELU)
         K.wsi_assemble_fwd(h, cls.reshape(E), N, add)
         ctx.save_for_backward(x16, h)
         ctx.meta = (B, N, Dw, E, add)
@@ -271,7 +305,7 @@ class WsiEmbedFn(Function):
         B, N, Dw, E, add = ctx.meta
         dcls = torch.zeros(E, device=dh.device, dtype=F32)
         dpre = K.wsi_embed_bwd(dh.contiguous(), h, N, add, dcls)
-        dw = wgrad(dpre.view(B * N, E), x16.view(B * N, -1), E, Dw)
+        dw = wgrad(dpre.view(B * N, E), x16.view(B * N, -1), E, Dw)  # the "hi" block of x16 is its first Dw columns
         db = colsum(dpre.view(B * N, E), E)
         return None, dw, db, dcls.view(1, 1, E)
 
@@ -287,8 +321,9 @@ class NystromLayerFn(Function):
     """TransLayer: x + NystromAttention(LayerNorm(x)) (models/mirror.py:295-314; nystrom_attention forward).
 
     Differences from the reference evaluation order, all exact in real arithmetic: q's 1/sqrt(d) is folded into the three
-    similarity GEMMs; (attn1 z)(attn3 v) is evaluated as attn1 (z (attn3 v)); each Moore-Penrose step is evaluated as
-    xz = a2 z, u1 = 7xz - xz xz, u2 = 15xz - xz u1, z' = 3.25 z - 0.25 z u2 (no explicit identity matrices).
+    similarity GEMMs; (attn1 z)(attn3 v) is evaluated as attn1 (z (attn3 v)); each Moore-Penrose step
+    z' = 0.25 z (13I - xz(15I - xz(7I - xz))) is evaluated in the residual E = I - a2 z as z' = z + z(E + E^2 + 0.25 E^3),
+    the same cubic without the cancellation between O(10)-sized terms that costs bf16 operands their accuracy.
     """
 
     @staticmethod
@@ -327,16 +362,18 @@ class NystromLayerFn(Function):
         iters = []
         mm = (B, hd, m, m)
         for _ in range(PINV_ITERS):
-            xz = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(a2_16, _T(z16), out_bf16=xz)
-            u1 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(xz, _T(xz), out_bf16=u1, alpha=-1.0, res=xz, gamma=7.0)
-            u2 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(xz, _T(u1), out_bf16=u2, alpha=-1.0, res=xz, gamma=15.0)
+            # z' = 0.25 z (13 I - xz (15 I - xz (7 I - xz))) written in the residual E = I - xz:
+            #   z' = z + z (E + E^2 + 0.25 E^3)  --  same polynomial, but no cancellation between O(10) terms
+            Em = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(a2_16, _T(z16), out_bf16=Em, alpha=-1.0, diag=1.0)              # E  = I - a2 z
+            G1 = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(Em, _T(Em), out_bf16=G1, alpha=0.25, res=Em)                    # G1 = E + 0.25 E E
+            Fm = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(Em, _T(G1), out_bf16=Fm, res=Em)                                # F  = E + E G1
             zn32 = torch.empty(mm, device=dev, dtype=F32)
             zn16 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(z16, _T(u2), out_f32=zn32, out_bf16=zn16, alpha=-0.25, res=z32, gamma=3.25)
-            iters += [z16, xz, u1, u2]
+            K.gemm(z16, _T(Fm), out_f32=zn32, out_bf16=zn16, res=z32)              # z' = z + z F
+            iters += [z16, Em, G1, Fm]
             z32, z16 = zn32, zn16
         kv = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
         K.gemm(a3, _T(v), out_bf16=kv)
@@ -406,21 +443,21 @@ class NystromLayerFn(Function):
         # ---- Moore-Penrose iterations, reversed
         ga2 = torch.empty(mm, device=dev, dtype=F32)
         for it in reversed(range(PINV_ITERS)):
-            z16, xz, u1, u2 = iters[4 * it:4 * it + 4]
-            gu2 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(_T(z16), _T(gz16), out_bf16=gu2, alpha=-0.25)                       # -0.25 z^T g
+            z16, Em, G1, Fm = iters[4 * it:4 * it + 4]
+            gF = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(_T(z16), _T(gz16), out_bf16=gF)                                        # gF  = z^T g
             gzn32 = torch.empty(mm, device=dev, dtype=F32)
-            K.gemm(gz16, u2, out_f32=gzn32, alpha=-0.25, res=gz32, gamma=3.25)          # 3.25 g - 0.25 g u2^T
-            gxz32 = torch.empty(mm, device=dev, dtype=F32)
-            K.gemm(gu2, u1, out_f32=gxz32, alpha=-1.0, res=gu2, gamma=15.0)             # 15 gu2 - gu2 u1^T
-            gu1 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(_T(xz), _T(gu2), out_bf16=gu1, alpha=-1.0)                           # -xz^T gu2
-            K.gemm(gu1, xz, out_f32=gxz32, alpha=-1.0, res=gu1, gamma=7.0, beta=1.0)    # += 7 gu1 - gu1 xz^T
-            gxz16 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(_T(xz), _T(gu1), out_f32=gxz32, out_bf16=gxz16, alpha=-1.0, beta=1.0)  # += -xz^T gu1
-            K.gemm(gxz16, z16, out_f32=ga2, beta=0.0 if it == PINV_ITERS - 1 else 1.0)  # ga2 += gxz z^T
+            K.gemm(gz16, Fm, out_f32=gzn32, res=gz32)                                     # gz  = g + g F^T
+            gE32 = torch.empty(mm, device=dev, dtype=F32)
+            K.gemm(gF, G1, out_f32=gE32, res=gF)                                          # gE  = gF + gF G1^T
+            gG1 = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(_T(Em), _T(gF), out_bf16=gG1)                                          # gG1 = E^T gF
+            K.gemm(gG1, Em, out_f32=gE32, alpha=0.25, res=gG1, beta=1.0)                  # gE += gG1 + 0.25 gG1 E^T
+            gE16 = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(_T(Em), _T(gG1), out_f32=gE32, out_bf16=gE16, alpha=0.25, beta=1.0)    # gE += 0.25 E^T gG1
+            K.gemm(gE16, z16, out_f32=ga2, alpha=-1.0, beta=0.0 if it == PINV_ITERS - 1 else 1.0)  # ga2 -= gE z^T
             gzn16 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(_T(a2_16), _T(gxz16), out_f32=gzn32, out_bf16=gzn16, beta=1.0)       # gz += a2^T gxz
+            K.gemm(_T(a2_16), _T(gE16), out_f32=gzn32, out_bf16=gzn16, alpha=-1.0, beta=1.0)       # gz  -= a2^T gE
             gz32, gz16 = gzn32, gzn16
         K.pinv_init_bwd(gz32, z0_32, scratch, ga2, True)
         ds2, _ = K.softmax_bwd(a2_16, ga2, scale)
@@ -554,39 +591,50 @@ class ReparamFn(Function):
 # ----------------------------------------------------------------------------------------------
 class ClipLossFn(Function):
     """Contrastive loss over logits = scale * W R^T: ClipLoss (losses/mirror_loss.py:37-52, w_row=w_col=0.5) and
-    InfoNCE's implicit-negative branch (losses/info_nce.py:144-164).  `scale` is a 0-d device tensor."""
+    InfoNCE's implicit-negative branch (losses/info_nce.py:144-164).  `scale` is a 0-d device tensor.
+    Up to PRECISE_ROWS samples the three small GEMMs (logits, dW, dR) run fp32-grade (split-3 bf16 operands): the
+    temperature multiplies every rounding error of the similarities by ~14-100."""
 
     @staticmethod
     @_cfwd
     def forward(ctx, w, r, scale, w_row, w_col):
         B, E = w.shape
         Ep = _r8(E)
-        w16, r16 = K.cast_bf16(w.contiguous(), Ep), K.cast_bf16(r.contiguous(), Ep)
+        w, r = w.contiguous(), r.contiguous()
+        precise = B <= PRECISE_ROWS
         raw = torch.empty(B, B, device=w.device, dtype=F32)
-        K.gemm(w16[:, :E], r16[:, :E], out_f32=raw)
+        if precise:
+            K.gemm(K.cast_split3(w, B, Ep, False, 0), K.cast_split3(r, B, Ep, False, 1), out_f32=raw)
+            ctx.save_for_backward(w, r)
+        else:
+            w16, r16 = K.cast_bf16(w, Ep), K.cast_bf16(r, Ep)
+            K.gemm(w16[:, :E], r16[:, :E], out_f32=raw)
+            ctx.save_for_backward(w16, r16)
         scale = scale.reshape(()).contiguous()
         loss, row, col = K.clip_loss_fwd(raw, scale, w_row, w_col)
-        ctx.save_for_backward(w16, r16, raw, scale, row, col)
-        ctx.meta = (B, E, w_row, w_col)
+        ctx.aux = (raw, scale, row, col)
+        ctx.meta = (B, E, w_row, w_col, precise)
         return loss
 
     @staticmethod
     @once_differentiable
     @_cbwd
     def backward(ctx, gout):
-        w16, r16, raw, scale, row, col = ctx.saved_tensors
-        B, E, w_row, w_col = ctx.meta
+        ws, rs = ctx.saved_tensors
+        raw, scale, row, col = ctx.aux
+        B, E, w_row, w_col, precise = ctx.meta
+        Bp, Ep = _r8(B), _r8(E)
         dscale = torch.zeros((), device=gout.device, dtype=F32)
-        G = K.clip_loss_bwd(raw, scale, w_row, w_col, row, col, gout.contiguous(), dscale)
-        Bp = _r8(B)
-        if Bp != B:  # keep the TMA row stride a multiple of 16 B
-            Gp = torch.zeros(B, Bp, device=G.device, dtype=BF16)
-            Gp[:, :B] = G
-            G = Gp
+        G = K.clip_loss_bwd(raw, scale, w_row, w_col, row, col, gout.contiguous(), dscale, want_f32=precise)
         dw = torch.empty(B, E, device=gout.device, dtype=F32)
         dr = torch.empty(B, E, device=gout.device, dtype=F32)
-        K.gemm(G[:, :B], _T(r16[:, :E]), out_f32=dw)          # dW = G R
-        K.gemm(_T(G[:, :B]), _T(w16[:, :E]), out_f32=dr)      # dR = G^T W
+        if precise:
+            K.gemm(K.cast_split3(G, B, Bp, False, 0), _T(K.cast_split3(rs, Bp, Ep, True, 1)[:, :E]), out_f32=dw)       # dW = G R
+            K.gemm(_T(K.cast_split3(G, Bp, Bp, True, 0)[:, :B]), _T(K.cast_split3(ws, Bp, Ep, True, 1)[:, :E]), out_f32=dr)  # dR = G^T W
+        else:
+            assert B % 8 == 0, "batch must be a multiple of 8 beyond PRECISE_ROWS (TMA row stride)"
+            K.gemm(G, _T(rs[:, :E]), out_f32=dw)
+            K.gemm(_T(G), _T(ws[:, :E]), out_f32=dr)
         return dw, dr, dscale, None, None
 
 

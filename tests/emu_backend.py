@@ -54,7 +54,7 @@ class Emu:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=0, drop_p=0.0, drop_seed=0, res=None,
-             gamma=1.0, beta=0.0, split_k=1):
+             gamma=1.0, beta=0.0, split_k=1, diag=0.0):
         assert a.dtype == BF16 and b.dtype == BF16
         assert a.stride(-1) == 1 or a.stride(-2) == 1
         assert b.stride(-1) == 1 or b.stride(-2) == 1
@@ -70,6 +70,8 @@ class Emu:
             out_f32 += alpha * acc.view(out_f32.shape)
             return
         v = alpha * acc
+        if diag != 0.0:
+            v = v + diag * torch.eye(v.shape[-2], v.shape[-1])
         if bias is not None:
             v = v + bias
         v = _act(v, act)
@@ -94,6 +96,14 @@ class Emu:
         dst = torch.zeros(*src.shape[:-1], cols_out, dtype=BF16)
         dst[..., :cols] = src.to(BF16)
         return dst
+
+    def cast_split3(self, src, rows_out, cols_out, stack_rows, order):
+        rows, cols = src.shape
+        hi = torch.zeros(rows_out, cols_out, dtype=BF16)
+        lo = torch.zeros(rows_out, cols_out, dtype=BF16)
+        hi[:rows, :cols] = src.to(BF16)
+        lo[:rows, :cols] = (src - hi[:rows, :cols].float()).to(BF16)
+        return torch.cat([hi, lo, hi] if order == 0 else [hi, hi, lo], 0 if stack_rows else 1)
 
     def copy_rows_(self, src, dst):
         dst.copy_(src)
@@ -326,13 +336,13 @@ class Emu:
         d = l.diagonal()
         return (w_row * (row - d) + w_col * (col - d)).mean(), row, col
 
-    def clip_loss_bwd(self, raw, scale, w_row, w_col, row, col, gout, dscale):
+    def clip_loss_bwd(self, raw, scale, w_row, w_col, row, col, gout, dscale, want_f32=False):
         B = raw.shape[0]
         l = scale * raw
         p = w_row * torch.exp(l - row[:, None]) + w_col * torch.exp(l - col[None, :]) - (w_row + w_col) * torch.eye(B)
         p = p * gout / B
         dscale += (p * raw).sum()
-        return (p * scale).to(BF16)
+        return (p * scale) if want_f32 else (p * scale).to(BF16)
 
     def masked_mse_fwd(self, a, b, mask):
         E = a.shape[-1]
