@@ -397,6 +397,14 @@ class MIRROR(nn.Module):
         self.prototypes = nn.Linear(embed_dim, num_prototypes, bias=False)
         nn.init.orthogonal_(self.prototypes.weight)
 
+    @torch.no_grad()
+    def normalize_prototypes(self):
+        """The trainer's per-step `prototypes.weight.data = F.normalize(w, dim=1, p=2)` (train_mirror.py:1133-1136) as one
+        kernel launch, in place."""
+        w = self.prototypes.weight
+        y, _ = K.l2norm_fwd(w.data, 1e-12)
+        K.copy_rows_(y, w.data)
+
     def reparameterize(self, mu, logstd, eps=None):
         if eps is None:
             eps = torch.randn_like(mu)

@@ -1,0 +1,287 @@
+"""GPU: every C-ABI kernel against its CPU re-statement (tests/emu_backend.py) on the same seeded inputs,
+including ragged sizes, padded layouts and strided views.  All calls go through the C ABI (ctypes)."""
+import copy
+
+import pytest
+import torch
+
+import emu_backend
+from mirror_b200 import kernels as K
+
+pytestmark = pytest.mark.gpu
+EMU = emu_backend.Emu()
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def rn(*s, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(s))
+    return torch.randn(*s, generator=g) * scale
+
+
+def to_dev(x):
+    if torch.is_tensor(x):
+        if x._base is not None or not x.is_contiguous():  # rebuild views on the device copy of the base storage
+            base = x._base if x._base is not None else x
+            db = base.detach().clone().cuda()
+            return torch.as_strided(db, x.shape, x.stride(), x.storage_offset())
+        return x.detach().clone().cuda()
+    if isinstance(x, (list, tuple)):
+        return type(x)(to_dev(v) for v in x)
+    return x
+
+
+def close(a, b, tol, name=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    scale = float(b.abs().max()) + 1e-6
+    err = float((a - b).abs().max())
+    assert err <= tol * scale, f"{name}: max err {err:.3e} vs scale {scale:.3e} (tol {tol})"
+
+
+def both(op, args, kwargs=None, tol=1e-5, check_args=()):
+    """run `op` on the emulation (CPU) and on the device; compare return values and the listed in-place args."""
+    kwargs = kwargs or {}
+    a_cpu = copy.deepcopy(args)
+    a_gpu = to_dev(args)
+    r_cpu = getattr(EMU, op)(*a_cpu, **kwargs)
+    r_gpu = getattr(K, op)(*a_gpu, **kwargs)
+    torch.cuda.synchronize()
+    rc = r_cpu if isinstance(r_cpu, (tuple, list)) else (r_cpu,)
+    rg = r_gpu if isinstance(r_gpu, (tuple, list)) else (r_gpu,)
+    for i, (c, g) in enumerate(zip(rc, rg)):
+        if torch.is_tensor(c) and c.numel() > 0 and op not in ("pinv_init",) or (op == "pinv_init" and i < 2):
+            close(g, c, tol if c.dtype != BF16 else max(tol, 8e-3), f"{op} ret{i}")
+    for i in check_args:
+        close(a_gpu[i], a_cpu[i], tol if a_cpu[i].dtype != BF16 else max(tol, 8e-3), f"{op} arg{i}")
+    return r_gpu, a_gpu
+
+
+def test_device_supported():
+    from mirror_b200 import _lib
+    assert _lib.lib().mirror_device_supported() == 1
+
+
+@pytest.mark.parametrize("rows,cols,cols_out", [(37, 100, 104), (64, 768, 768), (5, 10234, 10240)])
+def test_cast(rows, cols, cols_out):
+    both("cast_bf16", (rn(rows, cols),), {"cols_out": cols_out}, tol=1e-6)
+
+
+def test_cast_strided_rows():
+    base = rn(6, 11, 96)
+    both("cast_bf16", (base[:, 0, :],), {"cols_out": 96}, tol=1e-6)
+
+
+@pytest.mark.parametrize("stack,order", [(False, 0), (False, 1), (True, 0), (True, 1)])
+def test_cast_split3(stack, order):
+    both("cast_split3", (rn(13, 77), 16, 80, stack, order), tol=1e-6)
+
+
+def test_split3_product_is_fp32_grade():
+    a, b = rn(64, 300).cuda(), rn(48, 300, seed=1).cuda()
+    out = torch.empty(64, 48, device="cuda")
+    K.gemm(K.cast_split3(a, 64, 304, False, 0), K.cast_split3(b, 48, 304, False, 1), out_f32=out)
+    ref = a.double() @ b.double().t()
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 2e-5
+    plain = torch.empty(64, 48, device="cuda")
+    K.gemm(K.cast_bf16(a, 304)[:, :300], K.cast_bf16(b, 304)[:, :300], out_f32=plain)
+    assert float((plain.double() - ref).abs().max()) > 20 * float((out.double() - ref).abs().max())
+
+
+def test_copy_rows_axpy():
+    base = rn(5, 9, 64)
+    both("copy_rows_", (base[:, 0, :], torch.zeros(5, 64)), check_args=(1,))
+    both("axpy_", (rn(1000), rn(1000, seed=3)), {"alpha": 0.3}, check_args=(0,))
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_act_fwd_bwd(act, p):
+    pre = rn(7, 33, 40)
+    both("act_fwd", (pre, act, p, 99), {"want_bf16": True, "want_f32": True}, tol=2e-6)
+    dy = rn(7, 33, 40, seed=5)
+    out32 = torch.zeros(7, 40, 40)[:, :33, :]  # padded destination view
+    out16 = torch.zeros(7, 33, 40, dtype=BF16)
+    a_gpu = to_dev((dy, pre, out16, out32))
+    K.act_bwd(a_gpu[0], a_gpu[1], act, p, 99, out16=a_gpu[2], out32=a_gpu[3])
+    c16, c32 = out16.clone(), out32.clone()
+    EMU.act_bwd(dy, pre, act, p, 99, out16=c16, out32=c32)
+    close(a_gpu[3], c32, 3e-6, "act_bwd f32")
+    close(a_gpu[2], c16, 8e-3, "act_bwd bf16")
+
+
+@pytest.mark.parametrize("N,add", [(97, 3), (100, 0), (2048, 68)])
+def test_wsi_assemble_and_embed_bwd(N, add):
+    B, E = 3, 64
+    S = 1 + N + add
+    h = rn(B, S, E)
+    both("wsi_assemble_fwd", (h, rn(E, seed=2), N, add), check_args=(0,))
+    both("wsi_embed_bwd", (rn(B, S, E, seed=4), h, N, add, torch.zeros(E)), tol=1e-5, check_args=(4,))
+
+
+@pytest.mark.parametrize("N,keep", [(50, 12), (2048, 512), (768, 192), (1, 0)])
+def test_rank_mask(N, keep):
+    noise = torch.rand(4, N, generator=torch.Generator().manual_seed(N))
+    (m, _) = both("rank_mask", (noise, keep), tol=0)
+    assert int(m.sum()) == 4 * (N - keep)
+
+
+def test_rank_mask_ties_are_stable():
+    noise = torch.zeros(2, 64)
+    m, _ = both("rank_mask", (noise, 16), tol=0)
+    assert torch.equal(m.cpu()[0], (torch.arange(64) >= 16).float())
+
+
+@pytest.mark.parametrize("first,E,tok_stride", [(1, 48, 1), (0, 1, 0)])
+def test_mask_pos(first, E, tok_stride):
+    B, T = 3, 41
+    mask = (torch.rand(B, T - first, generator=torch.Generator().manual_seed(1)) > 0.3).float()
+    tok = rn(E if tok_stride else 1, seed=7)
+    both("mask_pos_fwd_", (rn(B, T, E), mask, tok, tok_stride, rn(T, E, seed=8), first), check_args=(0,))
+    both("mask_pos_bwd_", (rn(B, T, E, seed=9), mask, torch.zeros_like(tok), tok_stride, torch.zeros(T, E), first), tol=1e-5,
+         check_args=(0, 2, 4))
+
+
+def test_landmark_and_dqkv_finish():
+    B, m, seg, E = 2, 24, 3, 48
+    qkv = rn(B, m * seg, 3 * E).to(BF16)
+    both("landmark_fwd", (qkv, m, seg), tol=8e-3)
+    both("dqkv_finish", (rn(B, m * seg, 3 * E, seed=1), rn(B, m, 2 * E, seed=2), seg), tol=8e-3)
+
+
+def test_colsum():
+    x = rn(1000, 200)
+    both("colsum_", (x[:, :197], torch.zeros(197)), tol=1e-5, check_args=(1,))
+    both("colsum_", (x.to(BF16), torch.ones(200)), tol=1e-5, check_args=(1,))
+
+
+def test_reparam():
+    mu, lv, eps = rn(6, 16), rn(6, 16, seed=1), rn(6, 16, seed=2)
+    both("reparam_fwd", (mu, lv, eps), tol=2e-6)
+    both("reparam_bwd_", (rn(6, 16, seed=3), lv, eps, torch.zeros(6, 16), torch.ones(6, 16)), tol=2e-6, check_args=(3, 4))
+
+
+@pytest.mark.parametrize("B,S,E,pad", [(2, 65, 192, 31), (1, 300, 768, 0), (3, 17, 1536, 5)])
+def test_layernorm(B, S, E, pad):
+    x, g, b = rn(B, S, E, scale=2.0) + 0.5, 1 + 0.1 * rn(E, seed=1), 0.1 * rn(E, seed=2)
+    both("layernorm_fwd", (x, g, b, 1e-5), {"n_out": S + pad, "pad": pad, "want_bf16": True, "want_f32": True}, tol=3e-6)
+    mean, var = x.mean(-1), x.var(-1, unbiased=False)
+    rstd = torch.rsqrt(var + 1e-5)
+    dy = rn(B, S + pad, E, seed=3)
+    for add in (None, rn(B, S, E, seed=4)):
+        both("layernorm_bwd", (dy, x, g, mean, rstd, pad, torch.zeros(B, S, E), add, torch.zeros(E), torch.zeros(E)), tol=2e-5,
+             check_args=(6, 8, 9))
+
+
+@pytest.mark.parametrize("rows,cols", [(100, 384), (7, 2304), (33, 3000), (5, 16512), (64, 96)])
+def test_softmax(rows, cols):
+    x = rn(rows, cols, scale=3.0)
+    (y16, y32), _ = both("softmax_fwd", (x,), {"want_bf16": True, "want_f32": True}, tol=2e-6)
+    y = torch.softmax(x, -1).to(BF16)
+    both("softmax_bwd", (y, rn(rows, cols, seed=1)), {"scale": 0.3, "want_bf16": True, "want_f32": True}, tol=3e-6)
+
+
+def test_l2norm_strided_rows():
+    base = rn(5, 9, 96)
+    x = base[:, 0, :]
+    both("l2norm_fwd", (x, 1e-12), tol=2e-6)
+    norm = x.norm(dim=-1).clamp_min(1e-12)
+    both("l2norm_bwd", (rn(5, 96, seed=1), x, norm), tol=3e-6)
+
+
+@pytest.mark.parametrize("B,n,E", [(2, 72, 48), (1, 300, 192)])
+def test_res_conv(B, n, E):
+    qkv = rn(B, n, 3 * E).to(BF16)
+    w = rn(8, 33, scale=0.2)
+    both("res_conv_fwd", (qkv, w), tol=8e-3)
+    dout = rn(B, n, E, seed=1).to(BF16)
+    both("res_conv_bwd_", (dout, qkv, w, rn(B, n, 3 * E, seed=2), torch.zeros(8, 33)), tol=2e-4, check_args=(3, 4))
+
+
+def test_pinv_init_and_bwd():
+    # rows of a real attn2 all sum to 1 (the arg-max row is then decided by round-off); scale the rows apart so that
+    # the arg-max row / column are well defined and CPU and GPU must agree on them
+    a2 = torch.softmax(rn(2, 8, 24, 24, scale=2.0), -1) * (1 + 0.2 * torch.rand(2, 8, 24, 1, generator=torch.Generator().manual_seed(3)))
+    (z32, z16, scratch), _ = both("pinv_init", (a2,), tol=2e-6)
+    z_cpu, _, s_cpu = EMU.pinv_init(a2)
+    g = rn(2, 8, 24, 24, seed=1)
+    gx_cpu = torch.ones(2, 8, 24, 24)
+    EMU.pinv_init_bwd(g, z_cpu, s_cpu, gx_cpu, True)
+    gx = torch.ones(2, 8, 24, 24, device="cuda")
+    K.pinv_init_bwd(g.cuda(), z32, scratch, gx, True)
+    close(gx, gx_cpu, 1e-5, "pinv_init_bwd")
+
+
+@pytest.mark.parametrize("B,H,E", [(2, 7, 48), (1, 13, 192)])
+def test_ppeg(B, H, E):
+    x = rn(B, H * H + 1, E)
+    w7, w5, w3 = rn(E, 49, scale=0.1), rn(E, 25, scale=0.1), rn(E, 9, scale=0.1)
+    b7, b5, b3 = rn(E, seed=1, scale=0.1), rn(E, seed=2, scale=0.1), rn(E, seed=3, scale=0.1)
+    (y, wm), _ = both("ppeg_fwd", (x, w7, w5, w3, b7, b5, b3, H), tol=5e-6)
+    wm_cpu = EMU.ppeg_fwd(x, w7, w5, w3, b7, b5, b3, H)[1]
+    z = lambda *s: torch.zeros(*s)
+    both("ppeg_bwd", (rn(B, H * H + 1, E, seed=5), x, wm_cpu, H, z(E, 49), z(E, 25), z(E, 9), z(E), z(E), z(E)), tol=2e-5,
+         check_args=(4, 5, 6, 7, 8, 9))
+
+
+@pytest.mark.parametrize("B,E", [(3, 192), (2, 768)])
+def test_rna_attn(B, E):
+    qkv = rn(B, 3 * E)
+    both("rna_attn_fwd", (qkv,), tol=3e-6)
+    both("rna_attn_bwd", (qkv, rn(B, E, seed=1)), tol=1e-5)
+
+
+@pytest.mark.parametrize("B", [5, 64])
+@pytest.mark.parametrize("wr,wc", [(0.5, 0.5), (1.0, 0.0)])
+def test_clip_loss_kernels(B, wr, wc):
+    raw = rn(B, B, scale=0.3)
+    scale = torch.tensor(14.2857)
+    (loss, row, col), _ = both("clip_loss_fwd", (raw, scale, wr, wc), tol=3e-6)
+    l_cpu, r_cpu, c_cpu = EMU.clip_loss_fwd(raw, scale, wr, wc)
+    for f32 in (False, True):
+        both("clip_loss_bwd", (raw, scale, wr, wc, r_cpu, c_cpu, torch.tensor(0.7), torch.zeros(())), {"want_f32": f32}, tol=3e-6,
+             check_args=(7,))
+
+
+def test_masked_mse_strided():
+    B, T, E = 3, 20, 32
+    big = rn(B, T + 1, E)
+    a, b = rn(B, T + 1, E, seed=1)[:, 1:, :], big[:, 1:, :]
+    mask = (torch.rand(B, T, generator=torch.Generator().manual_seed(2)) > 0.25).float()
+    (out, scratch), _ = both("masked_mse_fwd", (a, b, mask), tol=3e-6)
+    s_cpu = EMU.masked_mse_fwd(a, b, mask)[1]
+    both("masked_mse_bwd", (a, b, mask, s_cpu, torch.tensor(1.3), 0.5, torch.zeros(B, T, E), False, torch.ones(B, T, E), True), tol=3e-6,
+         check_args=(6, 8))
+
+
+def test_gauss_and_sym_kl():
+    B, L, P = 4, 16, 3000
+    mu, lv = rn(2 * B, L), rn(2 * B, L, seed=1, scale=0.5)
+    both("gauss_kl_fwd", (mu, lv, B), tol=3e-6)
+    both("gauss_kl_bwd_", (mu, lv, B, torch.tensor(0.9), 0.1, torch.zeros(2 * B, L), torch.zeros(2 * B, L)), tol=3e-6, check_args=(5, 6))
+    scores = rn(2 * B, P)
+    both("sym_kl_fwd", (scores, B), tol=5e-6)
+    both("sym_kl_bwd", (scores, B, torch.tensor(1.1), 0.2), tol=2e-5)
+    both("loss_combine", (rn(5), (0.5, 0.1, 0.1, 0.1, 0.2)), tol=1e-6)
+
+
+def test_gemm_matches_emulation_with_epilogues():
+    a, b = rn(200, 72).to(BF16), rn(136, 72, seed=1).to(BF16)
+    for kw in (dict(alpha=0.5, bias=rn(136, seed=2), act=1), dict(diag=1.0, alpha=-1.0), dict(res=rn(200, 136, seed=3), gamma=3.25, alpha=-0.25),
+               dict(drop_p=0.1, drop_seed=77, bias=rn(136, seed=2)), dict(res=rn(200, 136, seed=3).to(BF16), gamma=7.0, alpha=-1.0)):
+        o_cpu, o16_cpu = torch.zeros(200, 136), torch.zeros(200, 136, dtype=BF16)
+        EMU.gemm(a, b, out_f32=o_cpu, out_bf16=o16_cpu, **kw)
+        kw_g = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}
+        o, o16 = torch.zeros(200, 136, device="cuda"), torch.zeros(200, 136, device="cuda", dtype=BF16)
+        K.gemm(a.cuda(), b.cuda(), out_f32=o, out_bf16=o16, **kw_g)
+        close(o, o_cpu, 1e-5, f"gemm {list(kw)}")
+        close(o16, o16_cpu, 8e-3, f"gemm bf16 {list(kw)}")
+
+
+def test_gemm_broadcast_weight_over_batch():
+    B, S, E = 3, 70, 64
+    x = rn(B, S + 5, E).to(BF16)
+    w = rn(E, E, seed=1).to(BF16)
+    out_cpu, out = torch.zeros(B, S, E), torch.zeros(B, S, E, device="cuda")
+    EMU.gemm(x[:, 5:, :], w.unsqueeze(0).expand(B, E, E), out_f32=out_cpu)
+    xd = x.cuda()
+    K.gemm(xd[:, 5:, :], w.cuda().unsqueeze(0).expand(B, E, E), out_f32=out)
+    close(out, out_cpu, 1e-5, "broadcast gemm")
