@@ -268,7 +268,9 @@ def main():
         bt = 1
         for d in a.shape[:-2]:
             bt *= d
-        rec.append((s_, e_, 2.0 * bt * a.shape[-2] * a.shape[-1] * b.shape[-2]))
+        sig = (bt, a.shape[-2], b.shape[-2], a.shape[-1], "T" if a.stride(-1) != 1 else "N", "N" if b.stride(-1) != 1 else "T",
+               "f32" if kw.get("out_f32") is not None else "", "b16" if kw.get("out_bf16") is not None else "", kw.get("split_k", 1))
+        rec.append((s_, e_, 2.0 * bt * a.shape[-2] * a.shape[-1] * b.shape[-2], sig))
 
     K.gemm = timed_gemm
     import mirror_b200.ops as _ops
@@ -279,8 +281,20 @@ def main():
     ei1.record()
     torch.cuda.synchronize()
     K.gemm = real_gemm
-    gemm_ms = sum(s_.elapsed_time(e_) for s_, e_, _ in rec)
-    gemm_flop = sum(f for _, _, f in rec)
+    gemm_ms = sum(s_.elapsed_time(e_) for s_, e_, _, _ in rec)
+    gemm_flop = sum(f for _, _, f, _ in rec)
+    if os.environ.get("MIRROR_BENCH_VERBOSE") and rank == 0:
+        agg = {}
+        for s_, e_, f, sig in rec:
+            t_ = agg.setdefault(sig, [0, 0.0, 0.0])
+            t_[0] += 1
+            t_[1] += s_.elapsed_time(e_)
+            t_[2] += f
+        print(f"GEMM launches of one step: {len(rec)}, {gemm_ms:.2f} ms of {ei0.elapsed_time(ei1):.2f} ms", file=sys.stderr)
+        print("batch      M      N      K  AB  outs      sk  count       ms   TFLOP/s", file=sys.stderr)
+        for sig, (c, ms_, f) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+            print(f"{sig[0]:5d} {sig[1]:6d} {sig[2]:6d} {sig[3]:6d}  {sig[4]}{sig[5]}  {sig[6]:3s} {sig[7]:3s} {sig[8]:3d} {c:6d} {ms_:8.3f} {f / ms_ / 1e9:9.0f}",
+                  file=sys.stderr)
     inst_ms = ei0.elapsed_time(ei1)
     achieved = gemm_flop / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     f_slide = algorithmic_gflop_per_slide(N, Dw)

@@ -2,7 +2,8 @@
 // accumulators, double buffered) -> fused epilogue.  Persistent, warp specialised:
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..5  epilogue: tcgen05.ld -> alpha/bias/act/dropout/residual/beta -> global stores
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, each owning half of the tile's columns):
+//               residual prefetch -> tcgen05.ld -> alpha/diag/bias/act/dropout/residual/beta -> 128-bit global stores
 // See include/mirror_b200.h (mirror_gemm_bf16) for the contract and the reference call sites.
 #include <cudaTypedefs.h>
 
@@ -15,7 +16,8 @@ namespace {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // one 128-byte swizzle row of bf16
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kAccStages = 2;
 
 struct KParams {
@@ -35,16 +37,40 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
 };
 
-template <int BN, bool FULL>
-__device__ __forceinline__ void epilogue_chunk(const Epi& e, const uint32_t (&acc)[32], int b1, int b2, int row,
-                                               int col0, bool vec_ok) {
-  if (!FULL || !vec_ok || e.atomic) {
+// 32 columns of one output row of the residual (or of the accumulate target), fetched BEFORE the accumulator is ready so
+// that the global-load latency hides behind the tile's MMAs.  fp32: 8 x 16 B, bf16: 4 x 16 B.
+struct ResBuf {
+  uint4 v[8];
+};
+
+__device__ __forceinline__ void res_prefetch(const Epi& e, ResBuf& rb, int b1, int b2, int row, int col0) {
+  if (e.res) {
+    const long long off = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)row * e.ldr + col0;
+    if (e.res_is_bf16) {
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res) + off);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j < e.N) epi_store_scalar(e, __uint_as_float(acc[j]), b1, b2, row, col0 + j);
-    return;
+      for (int j = 0; j < 4; ++j) rb.v[j] = rp[j];
+    } else {
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(e.res) + off);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rb.v[j] = rp[j];
+    }
+  } else if (e.beta != 0.f) {
+    const uint4* rp = reinterpret_cast<const uint4*>(e.o32 + b2 * e.c32_bs2 + b1 * e.c32_bs1 + (long long)row * e.ldc32 + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rb.v[j] = rp[j];
   }
-  if constexpr (FULL) {
+}
+
+__device__ __forceinline__ void epilogue_chunk_scalar(const Epi& e, const uint32_t (&acc)[32], int b1, int b2, int row, int col0) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (col0 + j < e.N) epi_store_scalar(e, __uint_as_float(acc[j]), b1, b2, row, col0 + j);
+}
+
+// full, 16-byte aligned 32-column chunk
+__device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, const uint32_t (&acc)[32], const ResBuf& rb, int b1, int b2,
+                                                   int row, int col0) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = e.alpha * __uint_as_float(acc[j]);
@@ -72,13 +98,10 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, const uint32_t (&ac
     for (int j = 0; j < 32; ++j) v[j] = hash_u01(e.drop_seed, base + j) >= e.drop_p ? v[j] * e.drop_scale : 0.f;
   }
   if (e.res) {
-    const long long off = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)row * e.ldr + col0;
     if (e.res_is_bf16) {
-      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res) + off);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 u = rp[j];
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rb.v[j]);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 f = __bfloat1622float2(h[t]);
@@ -87,10 +110,9 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, const uint32_t (&ac
         }
       }
     } else {
-      const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.res) + off);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 f = rp[j];
+        const float4 f = *reinterpret_cast<const float4*>(&rb.v[j]);
         v[4 * j] += e.gamma * f.x; v[4 * j + 1] += e.gamma * f.y;
         v[4 * j + 2] += e.gamma * f.z; v[4 * j + 3] += e.gamma * f.w;
       }
@@ -101,7 +123,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, const uint32_t (&ac
     if (e.beta != 0.f) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 f = op[j];
+        const float4 f = e.res ? op[j] : *reinterpret_cast<const float4*>(&rb.v[j]);  // prefetched unless res took the buffer
         v[4 * j] += e.beta * f.x; v[4 * j + 1] += e.beta * f.y;
         v[4 * j + 2] += e.beta * f.z; v[4 * j + 3] += e.beta * f.w;
       }
@@ -119,7 +141,6 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, const uint32_t (&ac
       for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j * 8 + 2 * t], v[j * 8 + 2 * t + 1]);
       op[j] = u;
     }
-  }
   }
 }
 
@@ -152,7 +173,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       for (int s = 0; s < kAccStages; ++s) {
         mbar_init(&tfull[s], 1);
-        mbar_init(&tempty[s], 4);  // one arrive per epilogue warp
+        mbar_init(&tempty[s], kEpiWarps);  // one arrive per epilogue warp
       }
       fence_mbar_init();
     }
@@ -243,7 +264,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;            // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
+    constexpr int NCH = BN / 64;       // 32-column chunks per thread
+    const bool fast = vec_ok != 0 && !p.e.atomic;
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int tile = w / p.split_k, ks = w - tile * p.split_k;
@@ -254,23 +278,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int mb_ = t % p.tiles_m;
       t /= p.tiles_m;
       const int b1 = t % p.batch1, b2 = t / p.batch1;
-      const int n0 = nb * BN;
+      const int cbase = nb * BN + half * (BN / 2);
       const int row = mb_ * BM + q * 32 + lane;
+      const bool row_ok = row < p.e.M;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      ResBuf rb[2];
+      if (fast && row_ok) {  // start the residual loads of the first two chunks while the MMAs of this tile still run
+        if (cbase + 32 <= p.e.N) res_prefetch(p.e, rb[0], b1, b2, row, cbase);
+        if (NCH > 1 && cbase + 64 <= p.e.N) res_prefetch(p.e, rb[1], b1, b2, row, cbase + 32);
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.e.N) break;  // warp-uniform
-        uint32_t acc[32];
-        tmem_ld_32x32(taddr + c * 32, acc);
-        tmem_ld_wait();
-        if (row < p.e.M) {
-          if (col0 + 32 <= p.e.N) epilogue_chunk<BN, true>(p.e, acc, b1, b2, row, col0, vec_ok != 0);
-          else epilogue_chunk<BN, false>(p.e, acc, b1, b2, row, col0, false);
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col0 = cbase + c * 32;
+        if (col0 < p.e.N) {  // warp-uniform
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + c * 32, acc);
+          tmem_ld_wait();
+          if (row_ok) {
+            if (fast && col0 + 32 <= p.e.N) epilogue_chunk_vec(p.e, acc, rb[c & 1], b1, b2, row, col0);
+            else epilogue_chunk_scalar(p.e, acc, b1, b2, row, col0);
+          }
+          if (c + 2 < NCH && fast && row_ok && col0 + 96 <= p.e.N) res_prefetch(p.e, rb[c & 1], b1, b2, row, col0 + 64);
         }
       }
       tc_fence_before();

@@ -10,75 +10,107 @@ namespace {
 
 constexpr int TAPS = 33;
 
-// out16[b,t,c] = sum_j w[h(c), j] * v[b, t + j*dir - 16*dir, c]  over the v slot of qkv ([B,n,3E], column 2E+c).
-// dir=+1: forward cross-correlation.  dir=-1 (on a [B,n,E] gradient): data gradient, accumulated into dst32.
+// Depthwise 33-tap FIR along the token axis.  Each thread owns one bf16 channel pair and a strip of TT consecutive
+// tokens: the TT+32 inputs of the strip are loaded once into registers and reused by all 33 taps (3 loads per
+// output pair instead of 33), threads of a warp cover 64 consecutive channels (128-byte coalesced rows).
+//   FWD: out16[b,t,c] = sum_j w[h(c),j] * v[b,t+j-16,c]      (v = value slot of qkv [B,n,3E], column 2E+c)
+//   BWD: dst32[b,t,2E+c] += sum_j w[h(c),j] * dout[b,t-j+16,c]   (data gradient, accumulated into dqkv32)
+constexpr int TT = 16;
+
 template <bool BWD>
-__global__ void res_conv_kernel(const bf16* __restrict__ src, long long src_ld, int src_col0, const float* __restrict__ w,
-                                int B, int n, int E, int d, bf16* __restrict__ dst16, float* __restrict__ dst32,
-                                long long dst_ld, int dst_col0) {
+__global__ void __launch_bounds__(128)
+res_conv_kernel(const bf16* __restrict__ src, long long src_ld, int src_col0, const float* __restrict__ w, int n, int E, int d,
+                bf16* __restrict__ dst16, float* __restrict__ dst32, long long dst_ld, int dst_col0) {
   __shared__ float sw[8 * TAPS];
   for (int i = threadIdx.x; i < 8 * TAPS; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
-  const int E2 = E / 2;
-  const long long total = (long long)B * n * E2;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = 2 * (int)(i % E2);
-    const long long bt = i / E2;
-    const int t = (int)(bt % n);
-    const long long b = bt / n;
-    const float* wh = sw + (c / d) * TAPS;
-    float ax = 0.f, ay = 0.f;
+  const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (c >= E) return;
+  const int t0 = blockIdx.y * TT;
+  const long long b = blockIdx.z;
+  const float* wh = sw + (c / d) * TAPS;
+  float2 in[TT + TAPS - 1];
 #pragma unroll
-    for (int j = 0; j < TAPS; ++j) {
-      const int tt = BWD ? t - j + 16 : t + j - 16;
-      if (tt >= 0 && tt < n) {
-        const float2 f = __bfloat1622float2(
-            *reinterpret_cast<const __nv_bfloat162*>(src + (b * n + tt) * src_ld + src_col0 + c));
-        ax += wh[j] * f.x;
-        ay += wh[j] * f.y;
-      }
+  for (int i = 0; i < TT + TAPS - 1; ++i) {
+    const int tt = t0 + i - 16;
+    in[i] = (tt >= 0 && tt < n)
+                ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + (b * n + tt) * src_ld + src_col0 + c))
+                : make_float2(0.f, 0.f);
+  }
+  float2 acc[TT];
+#pragma unroll
+  for (int i = 0; i < TT; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < TAPS; ++j) {
+    const float wj = BWD ? wh[TAPS - 1 - j] : wh[j];  // BWD: out[t] = sum_j w[j] in[t-j+16] = sum_j' w[32-j'] in[t+j'-16]
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+      acc[i].x += wj * in[i + j].x;
+      acc[i].y += wj * in[i + j].y;
     }
+  }
+#pragma unroll
+  for (int i = 0; i < TT; ++i) {
+    const int t = t0 + i;
+    if (t >= n) break;
     if (BWD) {
-      float2* p = reinterpret_cast<float2*>(dst32 + bt * dst_ld + dst_col0 + c);
+      float2* p = reinterpret_cast<float2*>(dst32 + (b * n + t) * dst_ld + dst_col0 + c);
       float2 o = *p;
-      o.x += ax;
-      o.y += ay;
+      o.x += acc[i].x;
+      o.y += acc[i].y;
       *p = o;
     } else {
-      *reinterpret_cast<__nv_bfloat162*>(dst16 + bt * dst_ld + dst_col0 + c) = __floats2bfloat162_rn(ax, ay);
+      *reinterpret_cast<__nv_bfloat162*>(dst16 + (b * n + t) * dst_ld + dst_col0 + c) = __floats2bfloat162_rn(acc[i].x, acc[i].y);
     }
   }
 }
 
-// dw[h,j] += sum_{b,t,c in head h} dout[b,t,c] * v[b,t+j-16,c].   grid = (chunks, 8 heads); block 256.
-__global__ void res_conv_wgrad_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ qkv, int B, int n, int E, int d,
-                                      float* __restrict__ dw, int rows_per_block) {
-  __shared__ float sh[32];
-  const int h = blockIdx.y;
-  const long long rows = (long long)B * n;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  float acc[TAPS];
+// dw[h,j] += sum_{b,t,c in head h} dout[b,t,c] * v[b,t+j-16,c].  Same strip decomposition; the 33 partial sums of a
+// thread are reduced over the CTA through shared-memory atomics, then one global atomic per (head, tap) and CTA.
+__global__ void __launch_bounds__(128)
+res_conv_wgrad_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ qkv, int n, int E, int d, float* __restrict__ dw) {
+  __shared__ float sacc[8 * TAPS];
+  for (int i = threadIdx.x; i < 8 * TAPS; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int t0 = blockIdx.y * TT;
+  const long long b = blockIdx.z;
+  // warp-uniform fast path: all 32 lanes active and inside one head -> shuffle-reduce, one shared atomic per tap
+  const int c_first = 2 * (blockIdx.x * blockDim.x + (threadIdx.x & ~31));
+  const bool warp_one_head = (c_first + 62 < E) && (c_first / d == (c_first + 62) / d);
+  if (c < E) {
+    float2 vin[TT + TAPS - 1];
 #pragma unroll
-  for (int j = 0; j < TAPS; ++j) acc[j] = 0.f;
-  const long long work = (r1 - r0) * d;
-  for (long long i = threadIdx.x; i < work; i += blockDim.x) {
-    const int c = h * d + (int)(i % d);
-    const long long bt = r0 + i / d;
-    const int t = (int)(bt % n);
-    const long long b = bt / n;
-    const float g = __bfloat162float(dout[bt * E + c]);
+    for (int i = 0; i < TT + TAPS - 1; ++i) {
+      const int tt = t0 + i - 16;
+      vin[i] = (tt >= 0 && tt < n)
+                   ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qkv + (b * n + tt) * 3LL * E + 2 * E + c))
+                   : make_float2(0.f, 0.f);
+    }
+    float2 g[TT];
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+      const int t = t0 + i;
+      g[i] = t < n ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + (b * n + t) * (long long)E + c))
+                   : make_float2(0.f, 0.f);
+    }
+    const int h = c / d;
 #pragma unroll
     for (int j = 0; j < TAPS; ++j) {
-      const int tt = t + j - 16;
-      if (tt >= 0 && tt < n) acc[j] += g * __bfloat162float(qkv[(b * n + tt) * 3 * E + 2 * E + c]);
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < TT; ++i) a += g[i].x * vin[i + j].x + g[i].y * vin[i + j].y;
+      if (warp_one_head) {
+        a = warp_sum(a);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[h * TAPS + j], a);
+      } else {
+        atomicAdd(&sacc[h * TAPS + j], a);
+      }
     }
   }
-#pragma unroll
-  for (int j = 0; j < TAPS; ++j) {
-    const float s = block_sum(acc[j], sh);
-    if (threadIdx.x == 0) atomicAdd(dw + h * TAPS + j, s);
-  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * TAPS; i += blockDim.x)
+    if (sacc[i] != 0.f) atomicAdd(dw + i, sacc[i]);
 }
 
 // ---- pinv set-up.  a2: [BH, m, m] f32 (row softmax).  scal: [0]=max row abs-sum, [1]=max col abs-sum (as ordered
@@ -181,25 +213,21 @@ static int ew_grid(long long n, int block) {
 extern "C" int mirror_res_conv_fwd(const void* qkv, const float* w, int32_t B, int32_t n, int32_t E, void* out_bf16,
                                    mirror_stream_t stream) {
   MB_CHECK_ARG(qkv && w && out_bf16 && B > 0 && n > 0 && E % 16 == 0, "res_conv_fwd: bad args");
-  res_conv_kernel<false><<<ew_grid((long long)B * n * E / 2, 256), 256, 0, STREAM>>>(
-      reinterpret_cast<const bf16*>(qkv), 3LL * E, 2 * E, w, B, n, E, E / 8, reinterpret_cast<bf16*>(out_bf16), nullptr, E, 0);
+  dim3 grid((E / 2 + 127) / 128, (n + TT - 1) / TT, B);
+  res_conv_kernel<false><<<grid, 128, 0, STREAM>>>(reinterpret_cast<const bf16*>(qkv), 3LL * E, 2 * E, w, n, E, E / 8,
+                                                  reinterpret_cast<bf16*>(out_bf16), nullptr, E, 0);
   MB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int mirror_res_conv_bwd(const void* dout_bf16, const void* qkv, const float* w, int32_t B, int32_t n, int32_t E,
                                    float* dqkv32, float* dw, mirror_stream_t stream) {
   MB_CHECK_ARG(dout_bf16 && qkv && w && dqkv32 && dw && B > 0 && n > 0 && E % 16 == 0, "res_conv_bwd: bad args");
-  res_conv_kernel<true><<<ew_grid((long long)B * n * E / 2, 256), 256, 0, STREAM>>>(
-      reinterpret_cast<const bf16*>(dout_bf16), E, 0, w, B, n, E, E / 8, nullptr, dqkv32, 3LL * E, 2 * E);
+  dim3 grid((E / 2 + 127) / 128, (n + TT - 1) / TT, B);
+  res_conv_kernel<true><<<grid, 128, 0, STREAM>>>(reinterpret_cast<const bf16*>(dout_bf16), E, 0, w, n, E, E / 8, nullptr, dqkv32,
+                                                 3LL * E, 2 * E);
   MB_LAUNCH_CHECK();
-  const long long rows = (long long)B * n;
-  int chunks = num_sms() * 2 / 8;
-  if (chunks < 1) chunks = 1;
-  long long rpb = (rows + chunks - 1) / chunks;
-  if (rpb < 16) rpb = 16;
-  chunks = (int)((rows + rpb - 1) / rpb);
-  res_conv_wgrad_kernel<<<dim3(chunks, 8), 256, 0, STREAM>>>(reinterpret_cast<const bf16*>(dout_bf16),
-                                                             reinterpret_cast<const bf16*>(qkv), B, n, E, E / 8, dw, (int)rpb);
+  res_conv_wgrad_kernel<<<grid, 128, 0, STREAM>>>(reinterpret_cast<const bf16*>(dout_bf16), reinterpret_cast<const bf16*>(qkv), n, E,
+                                                  E / 8, dw);
   MB_LAUNCH_CHECK();
   return 0;
 }

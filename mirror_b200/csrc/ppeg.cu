@@ -24,93 +24,109 @@ __global__ void ppeg_merge_kernel(const float* __restrict__ w7, const float* __r
   if (tap == 0) bm[c] = b7[c] + b5[c] + b3[c];
 }
 
-// y[b,1+t,c] = bm[c]*use_bias + sum_tap wm[tap or flipped][c] * x[b,1+nbr(t,tap),c];  y[b,0,:] = x[b,0,:]
+// y[b,1+t,c] = bm[c] + sum_tap wm[tap][c] * x[b,1+nbr(t,tap),c];  y[b,0,:] = x[b,0,:].  FLIP: transposed stencil (data grad).
+// One thread = one channel (a warp reads 128 contiguous bytes per token) and a strip of TX outputs of one grid row:
+// per input row the TX+6 inputs and 7 weights are loaded once and reused by 7*TX FMAs.
+constexpr int TX = 16;
+
 template <bool FLIP>
-__global__ void ppeg_stencil_kernel(const float* __restrict__ x, const float* __restrict__ wm, const float* __restrict__ bm,
-                                    int B, int H, int E, float* __restrict__ y, int accumulate) {
+__global__ void __launch_bounds__(128)
+ppeg_stencil_kernel(const float* __restrict__ x, const float* __restrict__ wm, const float* __restrict__ bm, int H, int E,
+                    float* __restrict__ y, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= E) return;
   const int S = H * H + 1;
-  const int E4 = E / 4;
-  const long long total = (long long)B * S * E4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = 4 * (int)(i % E4);
-    const long long bs = i / E4;
-    const int s = (int)(bs % S);
-    const long long b = bs / S;
-    float4 acc;
-    if (s == 0) {
-      acc = *reinterpret_cast<const float4*>(x + bs * E + c);
-    } else {
-      const int t = s - 1, ty = t / H, tx = t % H;
-      acc = (FLIP || !bm) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(bm + c);
+  const long long b = blockIdx.z;
+  const int strips = (H + TX - 1) / TX;
+  if ((int)blockIdx.y == H * strips) {  // cls row bypasses the stencil
+    const long long o = b * S * E + c;
+    y[o] = accumulate ? y[o] + x[o] : x[o];
+    return;
+  }
+  const int ty = blockIdx.y / strips, tx0 = (blockIdx.y % strips) * TX;
+  float acc[TX];
+  const float bias = (FLIP || !bm) ? 0.f : bm[c];
 #pragma unroll
-      for (int dy = 0; dy < 7; ++dy) {
-        const int yy = ty + dy - 3;
-        if (yy < 0 || yy >= H) continue;
+  for (int i = 0; i < TX; ++i) acc[i] = bias;
 #pragma unroll
-        for (int dx = 0; dx < 7; ++dx) {
-          const int xx = tx + dx - 3;
-          if (xx < 0 || xx >= H) continue;
-          const int tap = FLIP ? (6 - dy) * 7 + (6 - dx) : dy * 7 + dx;
-          const float4 w = *reinterpret_cast<const float4*>(wm + (long long)tap * E + c);
-          const float4 v = *reinterpret_cast<const float4*>(x + ((b * S) + 1 + yy * H + xx) * E + c);
-          acc.x += w.x * v.x; acc.y += w.y * v.y; acc.z += w.z * v.z; acc.w += w.w * v.w;
-        }
-      }
+  for (int dy = 0; dy < 7; ++dy) {
+    const int yy = ty + dy - 3;
+    if (yy < 0 || yy >= H) continue;
+    float in[TX + 6], w[7];
+#pragma unroll
+    for (int i = 0; i < TX + 6; ++i) {
+      const int xx = tx0 + i - 3;
+      in[i] = (xx >= 0 && xx < H) ? x[(b * S + 1 + yy * H + xx) * E + c] : 0.f;
     }
-    float4* p = reinterpret_cast<float4*>(y + bs * E + c);
-    if (accumulate) {
-      const float4 o = *p;
-      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-    }
-    *p = acc;
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) w[dx] = wm[(long long)(FLIP ? (6 - dy) * 7 + (6 - dx) : dy * 7 + dx) * E + c];
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx)
+#pragma unroll
+      for (int i = 0; i < TX; ++i) acc[i] += w[dx] * in[i + dx];
+  }
+#pragma unroll
+  for (int i = 0; i < TX; ++i) {
+    const int tx = tx0 + i;
+    if (tx >= H) break;
+    const long long o = (b * S + 1 + ty * H + tx) * E + c;
+    y[o] = accumulate ? y[o] + acc[i] : acc[i];
   }
 }
 
-// dwm[tap][c] += sum_{b,t} dy[b,1+t,c] * x[b,1+nbr(t,tap),c]; dbm[c] += sum dy.  grid (E/32, chunks), block (32, 8)
-__global__ void ppeg_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, int B, int H, int E,
-                                  float* __restrict__ dwm, float* __restrict__ dbm, int toks_per_block) {
-  __shared__ float sh[8][33];
-  const int S = H * H + 1, T = H * H;
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  const long long toks = (long long)B * T;
-  const long long t0 = (long long)blockIdx.y * toks_per_block;
-  const long long t1 = t0 + toks_per_block < toks ? t0 + toks_per_block : toks;
+// dwm[tap][c] += sum_{b,t} dy[b,1+t,c] * x[b,1+nbr(t,tap),c]; dbm[c] += sum dy.
+// One thread = one channel; a CTA walks RY grid rows of one slide.  Along a row the 7x7 input window lives in registers:
+// column j sits in slot j mod 7, the row loop is unrolled by 7 so every slot index is a compile-time constant
+// (7 loads + 49 FMAs per token, no register shuffling).  49+1 coalesced global atomics per thread at the end.
+constexpr int RY = 8;
+
+__global__ void __launch_bounds__(128)
+ppeg_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, int H, int E, float* __restrict__ dwm,
+                  float* __restrict__ dbm) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= E) return;
+  const int S = H * H + 1;
+  const long long b = blockIdx.z;
+  const float* xb = x + (b * S + 1) * E + c;
+  const float* gb = dy + (b * S + 1) * E + c;
   float acc[49];
 #pragma unroll
   for (int k = 0; k < 49; ++k) acc[k] = 0.f;
   float accb = 0.f;
-  if (c < E) {
-    for (long long q = t0 + threadIdx.y; q < t1; q += 8) {
-      const long long b = q / T;
-      const int t = (int)(q % T), ty = t / H, tx = t % H;
-      const float g = dy[(b * S + 1 + t) * E + c];
-      accb += g;
+  const int y0 = blockIdx.y * RY, y1 = min(H, y0 + RY);
+  for (int ty = y0; ty < y1; ++ty) {
+    float win[7][7];  // win[dy][slot]
 #pragma unroll
-      for (int dyy = 0; dyy < 7; ++dyy) {
-        const int yy = ty + dyy - 3;
+    for (int dyy = 0; dyy < 7; ++dyy) {
+      const int yy = ty + dyy - 3;
+      const bool rv = yy >= 0 && yy < H;
 #pragma unroll
-        for (int dxx = 0; dxx < 7; ++dxx) {
-          const int xx = tx + dxx - 3;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < H) acc[dyy * 7 + dxx] += g * x[(b * S + 1 + yy * H + xx) * E + c];
+      for (int sl = 0; sl < 7; ++sl) win[dyy][sl] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) win[dyy][j] = (rv && j < H) ? xb[(long long)(yy * H + j) * E] : 0.f;
+    }
+    for (int tx0 = 0; tx0 < H; tx0 += 7) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const int tx = tx0 + k;
+        const int xn = tx + 3;  // new column enters slot (k+3)%7
+#pragma unroll
+        for (int dyy = 0; dyy < 7; ++dyy) {
+          const int yy = ty + dyy - 3;
+          win[dyy][(k + 3) % 7] = (yy >= 0 && yy < H && xn < H) ? xb[(long long)(yy * H + xn) * E] : 0.f;
         }
+        const float g = tx < H ? gb[(long long)(ty * H + tx) * E] : 0.f;
+        accb += g;
+#pragma unroll
+        for (int dyy = 0; dyy < 7; ++dyy)
+#pragma unroll
+          for (int dxx = 0; dxx < 7; ++dxx) acc[dyy * 7 + dxx] += g * win[dyy][(k + dxx + 4) % 7];
       }
     }
   }
-#pragma unroll 1
-  for (int k = 0; k < 50; ++k) {
-    float v = accb;
 #pragma unroll
-    for (int kk = 0; kk < 49; ++kk) v = (k == kk) ? acc[kk] : v;  // keeps acc[] in registers
-    sh[threadIdx.y][threadIdx.x] = v;
-    __syncthreads();
-    if (threadIdx.y == 0 && c < E) {
-      float s = 0.f;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) s += sh[r][threadIdx.x];
-      atomicAdd(k < 49 ? dwm + (long long)k * E + c : dbm + c, s);
-    }
-    __syncthreads();
-  }
+  for (int k = 0; k < 49; ++k) atomicAdd(dwm + (long long)k * E + c, acc[k]);
+  atomicAdd(dbm + c, accb);
 }
 
 // scatter the merged gradient back: dw7 += dwm, dw5 += centre 5x5, dw3 += centre 3x3, db7/5/3 += dbm
@@ -139,12 +155,6 @@ __global__ void ppeg_split_kernel(const float* __restrict__ dwm, const float* __
 using namespace mb;
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
 
-static int ew_grid(long long n, int block) {
-  long long g = (n + block - 1) / block;
-  const long long cap = (long long)num_sms() * 16;
-  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
-}
-
 /* wm: [49*E] f32 scratch, bm: [E] f32 scratch (both caller-owned, reused by the backward) */
 extern "C" int mirror_ppeg_fwd(const float* x, const float* w7, const float* w5, const float* w3, const float* b7,
                                const float* b5, const float* b3, int32_t B, int32_t H, int32_t E, float* wm, float* bm, float* y,
@@ -152,7 +162,8 @@ extern "C" int mirror_ppeg_fwd(const float* x, const float* w7, const float* w5,
   MB_CHECK_ARG(x && w7 && w5 && w3 && b7 && b5 && b3 && wm && bm && y && B > 0 && H > 0 && E % 4 == 0, "ppeg_fwd: bad args");
   ppeg_merge_kernel<<<(49 * E + 255) / 256, 256, 0, STREAM>>>(w7, w5, w3, b7, b5, b3, E, wm, bm);
   MB_LAUNCH_CHECK();
-  ppeg_stencil_kernel<false><<<ew_grid((long long)B * (H * H + 1) * E / 4, 256), 256, 0, STREAM>>>(x, wm, bm, B, H, E, y, 0);
+  const dim3 grid((E + 127) / 128, H * ((H + TX - 1) / TX) + 1, B);
+  ppeg_stencil_kernel<false><<<grid, 128, 0, STREAM>>>(x, wm, bm, H, E, y, 0);
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -163,19 +174,12 @@ extern "C" int mirror_ppeg_bwd(const float* dy, const float* x, const float* wm,
                                float* db5, float* db3, mirror_stream_t stream) {
   MB_CHECK_ARG(dy && x && wm && dx && dwm && dbm && dw7 && dw5 && dw3 && db7 && db5 && db3 && B > 0 && H > 0 && E % 4 == 0,
                "ppeg_bwd: bad args");
-  ppeg_stencil_kernel<true><<<ew_grid((long long)B * (H * H + 1) * E / 4, 256), 256, 0, STREAM>>>(dy, wm, nullptr, B, H, E, dx,
-                                                                                                accumulate);
+  const dim3 grid((E + 127) / 128, H * ((H + TX - 1) / TX) + 1, B);
+  ppeg_stencil_kernel<true><<<grid, 128, 0, STREAM>>>(dy, wm, nullptr, H, E, dx, accumulate);
   MB_LAUNCH_CHECK();
   MB_CUDA(cudaMemsetAsync(dwm, 0, sizeof(float) * 49 * E, STREAM));
   MB_CUDA(cudaMemsetAsync(dbm, 0, sizeof(float) * E, STREAM));
-  const long long toks = (long long)B * H * H;
-  const int gx = (E + 31) / 32;
-  long long gy = (long long)num_sms() * 4 / gx;
-  if (gy < 1) gy = 1;
-  long long tpb = (toks + gy - 1) / gy;
-  if (tpb < 64) tpb = 64;
-  gy = (toks + tpb - 1) / tpb;
-  ppeg_wgrad_kernel<<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, STREAM>>>(dy, x, B, H, E, dwm, dbm, (int)tpb);
+  ppeg_wgrad_kernel<<<dim3((E + 127) / 128, (H + RY - 1) / RY, B), 128, 0, STREAM>>>(dy, x, H, E, dwm, dbm);
   MB_LAUNCH_CHECK();
   ppeg_split_kernel<<<(49 * E + 255) / 256, 256, 0, STREAM>>>(dwm, dbm, E, dw7, dw5, dw3, db7, db5, db3);
   MB_LAUNCH_CHECK();
