@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmirror_b200.so")
+_VARIANT = os.environ.get("MIRROR_B200_VARIANT", "")  # A/B builds for kernel experiments (see build.py)
+LIB_PATH = os.path.join(_HERE, f"libmirror_b200{'_' + _VARIANT if _VARIANT else ''}.so")
 _lib = None
 
 

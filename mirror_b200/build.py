@@ -9,8 +9,9 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libmirror_b200.so")
-OBJ = os.path.join(HERE, "csrc", "_obj")
+VARIANT = os.environ.get("MIRROR_B200_VARIANT", "")  # e.g. "transpose": A/B builds of kernel options, never the default
+OUT = os.path.join(HERE, f"libmirror_b200{'_' + VARIANT if VARIANT else ''}.so")
+OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + VARIANT if VARIANT else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
@@ -30,6 +31,10 @@ def _digest(paths):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    vdir = os.path.join(HERE, "csrc_variants", VARIANT)
+    if VARIANT and os.path.isdir(vdir):  # experiment builds: same-named files override the product sources
+        over = {os.path.basename(f): f for f in glob.glob(os.path.join(vdir, "*.cu"))}
+        srcs = [over.get(os.path.basename(f), f) for f in srcs]
     hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "mirror_b200.h")]
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "stamp")
@@ -39,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def cc(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        r = subprocess.run([NVCC, *FLAGS, "-I", CSRC, "-c", src, "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         if verbose:

@@ -45,13 +45,17 @@ inline int num_sms() {
   return n;
 }
 
-// ---- stateless counter-based uniform in [0,1): keep-mask of the fused dropout ----
+// ---- stateless counter-based uniform in [0,1): keep-mask of the fused dropout.  32-bit "lowbias32" finaliser over the
+// element index mixed with the 64-bit seed: ~10 integer ops per element (the epilogues evaluate it for every output).
 __host__ __device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t idx) {
-  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ULL + 0x632BE59BD9B4E019ULL;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-  z ^= z >> 31;
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
+  uint32_t h = (uint32_t)idx + (uint32_t)seed * 0x9E3779B1u + (uint32_t)(idx >> 32) * 0x85EBCA77u;
+  h ^= (uint32_t)(seed >> 32);
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }

@@ -6,6 +6,7 @@
 //               residual prefetch -> tcgen05.ld -> alpha/diag/bias/act/dropout/residual/beta -> 128-bit global stores
 // See include/mirror_b200.h (mirror_gemm_bf16) for the contract and the reference call sites.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -31,19 +32,38 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int TMEM_COLS = kAccStages * BN;  // 256 or 512, power of two
+  static constexpr int EPI_BYTES = 0;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int TMEM_COLS = (kAccStages * BN <= 256) ? 256 : 512;  // power of two >= 2 accumulator stages
   static constexpr int BAR_BYTES = (2 * STAGES + 2 * kAccStages) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
 };
 
-// 32 columns of one output row of the residual (or of the accumulate target), fetched BEFORE the accumulator is ready so
-// that the global-load latency hides behind the tile's MMAs.  fp32: 8 x 16 B, bf16: 4 x 16 B.
+// ---------------------------------------------------------------------------------------------- epilogue
+// A 32-row x 32-column chunk (one epilogue warp, one tcgen05.ld.32x32b.x32): thread = row, 32 consecutive columns.
+// (A variant that transposed the chunk through swizzled shared memory for fully coalesced stores was measured
+// 20-45 % SLOWER on every epilogue-bound shape and was dropped; see DESIGN.md.)
+// ResBuf holds the residual (or the accumulate target) of one chunk; it is fetched BEFORE the accumulator is ready
+// so that the global-load latency hides behind the tile's MMAs.
 struct ResBuf {
   uint4 v[8];
 };
 
-__device__ __forceinline__ void res_prefetch(const Epi& e, ResBuf& rb, int b1, int b2, int row, int col0) {
+// slow path (ragged N tail, unaligned views, split-K atomics, GELU).  Out of line, and it re-reads TMEM itself so that
+// the hot path never has to keep the accumulator chunk addressable (= spilled to local memory).
+__device__ __noinline__ void epilogue_chunk_scalar(const Epi& e, uint32_t taddr, int b1, int b2, int row, int col0) {
+  uint32_t acc[32];
+  tmem_ld_32x32(taddr, acc);
+  tmem_ld_wait();
+  if (row >= e.M) return;
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j)
+    if (col0 + j < e.N) epi_store_scalar(e, __uint_as_float(acc[j]), b1, b2, row, col0 + j);
+}
+
+__device__ __forceinline__ void res_prefetch(const Epi& e, ResBuf& rb, int b1, int b2, int row0, int col0, int lane) {
+  const int row = row0 + lane;
+  if (row >= e.M) return;
   if (e.res) {
     const long long off = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)row * e.ldr + col0;
     if (e.res_is_bf16) {
@@ -62,15 +82,39 @@ __device__ __forceinline__ void res_prefetch(const Epi& e, ResBuf& rb, int b1, i
   }
 }
 
-__device__ __forceinline__ void epilogue_chunk_scalar(const Epi& e, const uint32_t (&acc)[32], int b1, int b2, int row, int col0) {
+// Store NP 16-byte pieces per row so that every warp-wide store instruction writes FULL 32-byte sectors: lanes 2i and
+// 2i+1 (rows A = row0+2i and B = A+1) swap half of their pieces, then both write into the same row -- instruction j
+// covers bytes [32j, 32j+32) of row A (first NP/2 instructions) or row B (last NP/2).  With one row per lane each
+// instruction would touch 32 half-filled sectors, and the L1 -> L2 write path (not DRAM) is what saturates.
+template <int NP>
+__device__ __forceinline__ void store_rows_paired(uint4 (&pc)[NP], char* rowA, long long row_bytes, bool okA, bool okB, int lane) {
+  const bool odd = lane & 1;
+  uint4 rc[NP / 2];
 #pragma unroll
-  for (int j = 0; j < 32; ++j)
-    if (col0 + j < e.N) epi_store_scalar(e, __uint_as_float(acc[j]), b1, b2, row, col0 + j);
+  for (int j = 0; j < NP / 2; ++j) {  // even lane sends its odd pieces, odd lane its even pieces
+    const uint4 snd = odd ? pc[2 * j] : pc[2 * j + 1];
+    rc[j].x = __shfl_xor_sync(0xffffffffu, snd.x, 1);
+    rc[j].y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
+    rc[j].z = __shfl_xor_sync(0xffffffffu, snd.z, 1);
+    rc[j].w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
+  }
+  char* a = rowA + (odd ? 16 : 0);
+  char* b = rowA + row_bytes + (odd ? 16 : 0);
+#pragma unroll
+  for (int j = 0; j < NP / 2; ++j)  // row A: even lane writes its own piece 2j, odd lane the received piece 2j+1
+    if (okA) *reinterpret_cast<uint4*>(a + 32 * j) = odd ? rc[j] : pc[2 * j];
+#pragma unroll
+  for (int j = 0; j < NP / 2; ++j)  // row B: even lane writes the received piece 2j, odd lane its own piece 2j+1
+    if (okB) *reinterpret_cast<uint4*>(b + 32 * j) = odd ? pc[2 * j + 1] : rc[j];
 }
 
-// full, 16-byte aligned 32-column chunk
-__device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, const uint32_t (&acc)[32], const ResBuf& rb, int b1, int b2,
-                                                   int row, int col0) {
+__device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, uint32_t taddr, const ResBuf& rb, uint32_t /*stage*/, int b1, int b2,
+                                                   int row0, int col0, int lane) {
+  uint32_t acc[32];
+  tmem_ld_32x32(taddr, acc);
+  tmem_ld_wait();
+  const int row = row0 + lane;
+  const bool row_ok = row < e.M;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = e.alpha * __uint_as_float(acc[j]);
@@ -85,19 +129,16 @@ __device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, const uint32_t 
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
-  if (e.act == MIRROR_ACT_RELU) {
+  if (e.act == MIRROR_ACT_RELU) {  // (GELU goes through the scalar path: only tiny GEMMs use it)
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-  } else if (e.act == MIRROR_ACT_GELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
   }
   if (e.drop_p > 0.f) {
     const uint64_t base = ((uint64_t)(b2 * e.batch1 + b1) * e.M + row) * e.N + col0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = hash_u01(e.drop_seed, base + j) >= e.drop_p ? v[j] * e.drop_scale : 0.f;
   }
-  if (e.res) {
+  if (e.res && row_ok) {
     if (e.res_is_bf16) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -118,9 +159,12 @@ __device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, const uint32_t 
       }
     }
   }
+  const int rowA = row0 + (lane & ~1);
+  const bool okA = rowA < e.M, okB = rowA + 1 < e.M;
   if (e.o32) {
-    float4* op = reinterpret_cast<float4*>(e.o32 + b2 * e.c32_bs2 + b1 * e.c32_bs1 + (long long)row * e.ldc32 + col0);
-    if (e.beta != 0.f) {
+    const long long off = b2 * e.c32_bs2 + b1 * e.c32_bs1 + col0;
+    if (e.beta != 0.f && row_ok) {
+      const float4* op = reinterpret_cast<const float4*>(e.o32 + off + (long long)row * e.ldc32);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 f = e.res ? op[j] : *reinterpret_cast<const float4*>(&rb.v[j]);  // prefetched unless res took the buffer
@@ -128,18 +172,51 @@ __device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, const uint32_t 
         v[4 * j + 2] += e.beta * f.z; v[4 * j + 3] += e.beta * f.w;
       }
     }
+    uint4 pc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < 8; ++j)
+      pc[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+    store_rows_paired<8>(pc, reinterpret_cast<char*>(e.o32 + off + (long long)rowA * e.ldc32), e.ldc32 * 4, okA, okB, lane);
   }
   if (e.o16) {
-    uint4* op = reinterpret_cast<uint4*>(e.o16 + b2 * e.c16_bs2 + b1 * e.c16_bs1 + (long long)row * e.ldc16 + col0);
+    uint4 pc[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint4 u;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pc[j]);
 #pragma unroll
       for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j * 8 + 2 * t], v[j * 8 + 2 * t + 1]);
-      op[j] = u;
+    }
+    store_rows_paired<4>(pc, reinterpret_cast<char*>(e.o16 + b2 * e.c16_bs2 + b1 * e.c16_bs1 + col0 + (long long)rowA * e.ldc16),
+                         e.ldc16 * 2, okA, okB, lane);
+  }
+}
+
+// One epilogue warp's share of a finished tile: the 32 rows of its TMEM lane quarter (first row row0) x BN/2 columns
+// starting at cbase.  `stage`: this warp's 4 KB shared transpose tile (transposed mapping only).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t taddr, uint32_t stage, int b1, int b2, int row0,
+                                              int cbase, int lane, uint64_t* tfull_bar, uint32_t aphase) {
+  constexpr int NCH = BN / 64;  // 32-column chunks per thread
+  const bool rows_ok = row0 < e.M;  // warp-uniform
+  ResBuf rb0, rb1;
+  if (fast && rows_ok) {  // start the residual loads of the first two chunks while the MMAs of this tile still run
+    if (cbase + 32 <= e.N) res_prefetch(e, rb0, b1, b2, row0, cbase, lane);
+    if (NCH > 1 && cbase + 64 <= e.N) res_prefetch(e, rb1, b1, b2, row0, cbase + 32, lane);
+  }
+  mbar_wait(tfull_bar, aphase);
+  tc_fence_after();
+  if (!rows_ok) return;
+  // chunks go in pairs (static register names for the two prefetch buffers); fully unrolled: NCH <= 4
+#pragma unroll
+  for (int c = 0; c < NCH; c += 2) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int col0 = cbase + (c + u) * 32;
+      if (c + u < NCH && col0 < e.N) {  // warp-uniform
+        if (fast && col0 + 32 <= e.N) epilogue_chunk_vec(e, taddr + (c + u) * 32, u ? rb1 : rb0, stage, b1, b2, row0, col0, lane);
+        else epilogue_chunk_scalar(e, taddr + (c + u) * 32, b1, b2, row0 + lane, col0);
+        if (c + u + 2 < NCH && fast && col0 + 96 <= e.N) res_prefetch(e, u ? rb1 : rb0, b1, b2, row0, col0 + 64, lane);
+      }
     }
   }
 }
@@ -153,7 +230,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  const uint32_t epi_stage = smem_u32(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + kAccStages;
@@ -266,8 +344,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     const int q = warp & 3;            // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
     const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
-    constexpr int NCH = BN / 64;       // 32-column chunks per thread
-    const bool fast = vec_ok != 0 && !p.e.atomic;
+    const bool fast = vec_ok != 0 && !p.e.atomic && p.e.act != MIRROR_ACT_GELU;
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int tile = w / p.split_k, ks = w - tile * p.split_k;
@@ -279,32 +356,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       t /= p.tiles_m;
       const int b1 = t % p.batch1, b2 = t / p.batch1;
       const int cbase = nb * BN + half * (BN / 2);
-      const int row = mb_ * BM + q * 32 + lane;
-      const bool row_ok = row < p.e.M;
+      const int row0 = mb_ * BM + q * 32;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      ResBuf rb[2];
-      if (fast && row_ok) {  // start the residual loads of the first two chunks while the MMAs of this tile still run
-        if (cbase + 32 <= p.e.N) res_prefetch(p.e, rb[0], b1, b2, row, cbase);
-        if (NCH > 1 && cbase + 64 <= p.e.N) res_prefetch(p.e, rb[1], b1, b2, row, cbase + 32);
-      }
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2);
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int col0 = cbase + c * 32;
-        if (col0 < p.e.N) {  // warp-uniform
-          uint32_t acc[32];
-          tmem_ld_32x32(taddr + c * 32, acc);
-          tmem_ld_wait();
-          if (row_ok) {
-            if (fast && col0 + 32 <= p.e.N) epilogue_chunk_vec(p.e, acc, rb[c & 1], b1, b2, row, col0);
-            else epilogue_chunk_scalar(p.e, acc, b1, b2, row, col0);
-          }
-          if (c + 2 < NCH && fast && row_ok && col0 + 96 <= p.e.N) res_prefetch(p.e, rb[c & 1], b1, b2, row, col0 + 64);
-        }
-      }
+      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), epi_stage + (warp - 2) * 4096, b1,
+                        b2, row0, cbase, lane, &tfull[as], aphase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -318,6 +374,181 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Cluster variant: CL CTAs of a thread-block cluster own CL consecutive 128-row tiles of the SAME N range.  Each CTA
+// loads its own A rows and 1/CL of the B tile, which TMA *multicasts* into the shared memory of all CL CTAs, so a
+// B byte is fetched from L2 once per cluster instead of once per CTA (the plain kernel is L2-bandwidth bound: a
+// 128x256x64 step moves 48 KB for 4.2 MFLOP).  CL = 3 covers the 384-row Moore-Penrose matrices with one cluster.
+// MMAs, TMEM and epilogue stay per CTA (cta_group::1).  Protocol differences to the plain kernel:
+//   full[s]   still 1 local arrival (expect_tx of the whole stage); the bytes now arrive from CL different TMA issuers
+//   empty[s]  CL arrivals: every CTA's tcgen05.commit is multicast to all CTAs, because a refill of stage s by ANY
+//             producer overwrites the B slice in EVERY CTA
+//   cluster barrier at start (barriers initialised before remote traffic) and at exit (no CTA leaves while peers may
+//   still multicast into it)
+template <int BN, int A_MN, int B_MN, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tcgen05_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            const __grid_constant__ KParams p, const int vec_ok) {
+  using C = Cfg<BN>;
+  static_assert((BN / CL) % 64 == 0 || !B_MN, "MN-major B is sliced in 64-column chunks");
+  static_assert(BN % CL == 0, "B tile must split evenly over the cluster");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  const uint32_t epi_stage = smem_u32(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cid = blockIdx.x / CL, nclusters = gridDim.x / CL;
+  constexpr uint16_t kMask = (1u << CL) - 1;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < C::STAGES; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], CL);
+      }
+      for (int s = 0; s < kAccStages; ++s) {
+        mbar_init(&tfull[s], 1);
+        mbar_init(&tempty[s], kEpiWarps);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item = (batch, group of CL consecutive m tiles, n tile [, k split]); p.tiles_m counts groups here
+  const int tiles = p.tiles_m * p.tiles_n * p.batch1 * p.batch2;
+  const int total = tiles * p.split_k;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_per = (kb_total + p.split_k - 1) / p.split_k;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cid; w < total; w += nclusters) {
+        const int tile = w / p.split_k, ks = w - tile * p.split_k;
+        const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+        if (kb0 >= kb1) continue;
+        const int nb = tile % p.tiles_n;
+        int t = tile / p.tiles_n;
+        const int mg = t % p.tiles_m;
+        t /= p.tiles_m;
+        const int b1 = t % p.batch1, b2 = t / p.batch1;
+        const int m0 = (mg * CL + rank) * BM, n0 = nb * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);  // all CL consumers released this slot
+          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          uint8_t* a = sA + stage * C::A_BYTES;
+          uint8_t* b = sB + stage * C::B_BYTES;
+          if (A_MN) {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_4d(&tmA, &full[stage], a + i * (BK * 128), m0 + i * 64, kb * BK, b1 * p.a_b1, b2 * p.a_b2);
+          } else {
+            tma_load_4d(&tmA, &full[stage], a, kb * BK, m0, b1 * p.a_b1, b2 * p.a_b2);
+          }
+          // this CTA's 1/CL slice of the B tile, delivered to every CTA of the cluster
+          if (B_MN) {
+            constexpr int kChunks = BN / 64 / CL;
+#pragma unroll
+            for (int i = 0; i < kChunks; ++i) {
+              const int ch = rank * kChunks + i;
+              tma_load_4d_mc(&tmB, &full[stage], b + ch * (BK * 128), n0 + ch * 64, kb * BK, b1 * p.b_b1, b2 * p.b_b2, kMask);
+            }
+          } else {
+            constexpr int kRows = BN / CL;
+            tma_load_4d_mc(&tmB, &full[stage], b + rank * (kRows * 128), kb * BK, n0 + rank * kRows, b1 * p.b_b1, b2 * p.b_b2, kMask);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t a_lbo = A_MN ? BK * 128 : 0, b_lbo = B_MN ? BK * 128 : 0;
+      constexpr uint32_t a_kstep = A_MN ? (UMMA_K / 8) * 1024 : UMMA_K * 2;
+      constexpr uint32_t b_kstep = B_MN ? (UMMA_K / 8) * 1024 : UMMA_K * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = cid; w < total; w += nclusters) {
+        const int tile = w / p.split_k, ks = w - tile * p.split_k;
+        const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+        if (kb0 >= kb1) continue;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+            const uint64_t bd = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+            umma_f16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_mc(&empty[stage], kMask);  // this CTA is done with the slot: tell every producer of the cluster
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+        ++it;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const bool fast = vec_ok != 0 && !p.e.atomic && p.e.act != MIRROR_ACT_GELU;
+    int it = 0;
+    for (int w = cid; w < total; w += nclusters) {
+      const int tile = w / p.split_k, ks = w - tile * p.split_k;
+      const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+      if (kb0 >= kb1) continue;
+      const int nb = tile % p.tiles_n;
+      int t = tile / p.tiles_n;
+      const int mg = t % p.tiles_m;
+      t /= p.tiles_m;
+      const int b1 = t % p.batch1, b2 = t / p.batch1;
+      const int cbase = nb * BN + half * (BN / 2);
+      const int row0 = (mg * CL + rank) * BM + q * 32;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), epi_stage + (warp - 2) * 4096, b1,
+                        b2, row0, cbase, lane, &tfull[as], aphase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      ++it;
+    }
+  }
+
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();  // peers may still multicast data / barrier arrivals into this CTA until they are all done
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ host side
@@ -376,6 +607,23 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int
   const long long total = (long long)p.tiles_m * p.tiles_n * p.batch1 * p.batch2 * p.split_k;
   const int grid = (int)(total < num_sms() ? total : num_sms());
   kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, p, vec_ok);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN, int A_MN, int B_MN, int CL>
+int launch_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int vec_ok, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  auto kern = gemm_tcgen05_cluster_kernel<BN, A_MN, B_MN, CL>;
+  static bool configured = false;
+  if (!configured) {
+    MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const long long total = (long long)p.tiles_m * p.tiles_n * p.batch1 * p.batch2 * p.split_k;
+  const int max_clusters = num_sms() / CL;
+  const int clusters = (int)(total < max_clusters ? total : max_clusters);
+  kern<<<CL * clusters, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, p, vec_ok);  // cluster dims (CL,1,1) are compiled in
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -447,8 +695,55 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
   KParams p;
   int rc = fill_epi(g, &p.e);
   if (rc) return rc;
-  // N tile: 256 when it divides N (or N is large), otherwise 128 (less padding waste for N = 96, 384, ...).
-  const int BN = (g->N % 256 == 0 || g->N >= 1024) ? 256 : 128;
+  // Clusters with TMA-multicast B whenever a batch item has several 128-row tiles: CL = 3 for the 384-row
+  // Moore-Penrose / landmark matrices (one cluster per matrix and N tile), CL = 2 otherwise.
+  // Opt-in (MIRROR_B200_CLUSTER=1): measured on B200 it does not pay -- with clusters of 2..3 CTAs the multicast did not
+  // reduce L2 traffic (B300_MICROARCH: "MC ~ UC at cluster size <= 4"), CL=2 gave +1..4 %, CL=3 halved the throughput of
+  // the 384^3 GEMMs (lock-step of three CTAs); the limiter of these kernels is the L1->L2 write path of the epilogue.
+  static const bool cluster_enabled = [] {
+    const char* v = getenv("MIRROR_B200_CLUSTER");
+    return v && v[0] && v[0] != '0';
+  }();
+  const int mt = (g->M + BM - 1) / BM;
+  if (mt >= 2 && cluster_enabled) {
+    const int CL = (mt == 3) ? 3 : 2;
+    const int BNc = (CL == 3) ? ((g->N % 192 == 0 || g->N > 128) ? 192 : 0)
+                              : ((g->N % 256 == 0 || g->N >= 1024) ? 256 : 128);
+    if (BNc) {
+      p.K = g->K;
+      p.batch1 = g->batch1;
+      p.batch2 = g->batch2;
+      p.tiles_m = (mt + CL - 1) / CL;  // groups of CL row tiles
+      p.tiles_n = (g->N + BNc - 1) / BNc;
+      p.split_k = g->split_k > 1 ? g->split_k : 1;
+      p.a_b1 = (g->batch1 > 1 && g->a_bs1 == 0) ? 0 : 1;
+      p.a_b2 = (g->batch2 > 1 && g->a_bs2 == 0) ? 0 : 1;
+      p.b_b1 = (g->batch1 > 1 && g->b_bs1 == 0) ? 0 : 1;
+      p.b_b2 = (g->batch2 > 1 && g->b_bs2 == 0) ? 0 : 1;
+      CUtensorMap tmA, tmB;
+      rc = make_operand_map(&tmA, g->a, g->a_mn_major, g->M, g->K, g->lda, g->a_bs1, p.a_b1 ? g->batch1 : 1, g->a_bs2,
+                            p.a_b2 ? g->batch2 : 1, BM);
+      if (rc) return rc;
+      rc = make_operand_map(&tmB, g->b, g->b_mn_major, g->N, g->K, g->ldb, g->b_bs1, p.b_b1 ? g->batch1 : 1, g->b_bs2,
+                            p.b_b2 ? g->batch2 : 1, BNc / CL);
+      if (rc) return rc;
+      const int vec = epi_vec_ok(g) ? 1 : 0;
+      const int key = (g->a_mn_major ? 2 : 0) | (g->b_mn_major ? 1 : 0);
+#define MB_DISPATCHC(BNV, CLV)                                                 \
+  switch (key) {                                                               \
+    case 0: return launch_cluster<BNV, 0, 0, CLV>(tmA, tmB, p, vec, stream);   \
+    case 1: return launch_cluster<BNV, 0, 1, CLV>(tmA, tmB, p, vec, stream);   \
+    case 2: return launch_cluster<BNV, 1, 0, CLV>(tmA, tmB, p, vec, stream);   \
+    default: return launch_cluster<BNV, 1, 1, CLV>(tmA, tmB, p, vec, stream);  \
+  }
+      if (CL == 3) { MB_DISPATCHC(192, 3) }
+      if (BNc == 256) { MB_DISPATCHC(256, 2) }
+      MB_DISPATCHC(128, 2)
+#undef MB_DISPATCHC
+    }
+  }
+  // N tile: 256 when it divides N (or N is large), 192 for N = 384-like sizes (the Nystrom landmark matrices), else 128.
+  const int BN = (g->N % 256 == 0 || g->N >= 1024) ? 256 : (g->N % 192 == 0 ? 192 : 128);
   p.K = g->K;
   p.batch1 = g->batch1;
   p.batch2 = g->batch2;
@@ -468,17 +763,18 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
                         p.b_b2 ? g->batch2 : 1, BN);
   if (rc) return rc;
   const int vec = epi_vec_ok(g) ? 1 : 0;
-  const int key = (BN == 256 ? 4 : 0) | (g->a_mn_major ? 2 : 0) | (g->b_mn_major ? 1 : 0);
-  switch (key) {
-    case 0: return launch<128, 0, 0>(tmA, tmB, p, vec, stream);
-    case 1: return launch<128, 0, 1>(tmA, tmB, p, vec, stream);
-    case 2: return launch<128, 1, 0>(tmA, tmB, p, vec, stream);
-    case 3: return launch<128, 1, 1>(tmA, tmB, p, vec, stream);
-    case 4: return launch<256, 0, 0>(tmA, tmB, p, vec, stream);
-    case 5: return launch<256, 0, 1>(tmA, tmB, p, vec, stream);
-    case 6: return launch<256, 1, 0>(tmA, tmB, p, vec, stream);
-    default: return launch<256, 1, 1>(tmA, tmB, p, vec, stream);
+  const int key = (g->a_mn_major ? 2 : 0) | (g->b_mn_major ? 1 : 0);
+#define MB_DISPATCH(BNV)                                          \
+  switch (key) {                                                  \
+    case 0: return launch<BNV, 0, 0>(tmA, tmB, p, vec, stream);   \
+    case 1: return launch<BNV, 0, 1>(tmA, tmB, p, vec, stream);   \
+    case 2: return launch<BNV, 1, 0>(tmA, tmB, p, vec, stream);   \
+    default: return launch<BNV, 1, 1>(tmA, tmB, p, vec, stream);  \
   }
+  if (BN == 256) { MB_DISPATCH(256) }
+  if (BN == 192) { MB_DISPATCH(192) }
+  MB_DISPATCH(128)
+#undef MB_DISPATCH
 }
 
 extern "C" int mirror_gemm_bf16_simt(const mirror_gemm_args* g, mirror_stream_t stream_) {

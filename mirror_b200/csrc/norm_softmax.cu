@@ -124,6 +124,74 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
   }
 }
 
+// Same contract, E == ITERS*128: the per-column partial sums of dgamma / dbeta stay in registers (lane owns columns
+// lane*4 + 128*i), are combined across the 8 warps through shared memory once per CTA and leave as one global atomic
+// per column and CTA -- no shared-memory atomics in the row loop.
+template <int ITERS>
+__global__ void __launch_bounds__(kWarps * 32)
+ln_bwd_reg_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, int B, int S, int n_out, int pad, float* dx,
+                  const float* add, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int E = ITERS * 128;
+  __shared__ float sh[2 * E];
+  for (int c = threadIdx.x; c < 2 * E; c += blockDim.x) sh[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  float4 w[ITERS], ag[ITERS], ab[ITERS];
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    w[i] = *reinterpret_cast<const float4*>(gamma + lane * 4 + 128 * i);
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const long long rows = (long long)B * S;
+  for (long long ri = blockIdx.x * (long long)kWarps + (threadIdx.x >> 5); ri < rows; ri += (long long)gridDim.x * kWarps) {
+    const int b = (int)(ri / S), s = (int)(ri % S);
+    const float* xr = x + ri * E;
+    const float* gr = dy + ((long long)b * n_out + pad + s) * E;
+    const float mu = mean[ri], rs = rstd[ri];
+    float4 xv[ITERS], gv[ITERS];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      xv[i] = *reinterpret_cast<const float4*>(xr + lane * 4 + 128 * i);
+      gv[i] = *reinterpret_cast<const float4*>(gr + lane * 4 + 128 * i);
+      xv[i].x = (xv[i].x - mu) * rs; xv[i].y = (xv[i].y - mu) * rs; xv[i].z = (xv[i].z - mu) * rs; xv[i].w = (xv[i].w - mu) * rs;
+      const float gx = gv[i].x * w[i].x, gy = gv[i].y * w[i].y, gz = gv[i].z * w[i].z, gw = gv[i].w * w[i].w;
+      s1 += gx + gy + gz + gw;
+      s2 += gx * xv[i].x + gy * xv[i].y + gz * xv[i].z + gw * xv[i].w;
+    }
+    s1 = warp_sum(s1) / E;
+    s2 = warp_sum(s2) / E;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      float4 d;
+      d.x = rs * (gv[i].x * w[i].x - s1 - xv[i].x * s2);
+      d.y = rs * (gv[i].y * w[i].y - s1 - xv[i].y * s2);
+      d.z = rs * (gv[i].z * w[i].z - s1 - xv[i].z * s2);
+      d.w = rs * (gv[i].w * w[i].w - s1 - xv[i].w * s2);
+      if (add) {
+        const float4 o = *reinterpret_cast<const float4*>(add + ri * E + lane * 4 + 128 * i);
+        d.x += o.x; d.y += o.y; d.z += o.z; d.w += o.w;
+      }
+      *reinterpret_cast<float4*>(dx + ri * E + lane * 4 + 128 * i) = d;
+      ag[i].x += gv[i].x * xv[i].x; ag[i].y += gv[i].y * xv[i].y; ag[i].z += gv[i].z * xv[i].z; ag[i].w += gv[i].w * xv[i].w;
+      ab[i].x += gv[i].x; ab[i].y += gv[i].y; ab[i].z += gv[i].z; ab[i].w += gv[i].w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int c = lane * 4 + 128 * i;
+    atomicAdd(sh + c, ag[i].x); atomicAdd(sh + c + 1, ag[i].y); atomicAdd(sh + c + 2, ag[i].z); atomicAdd(sh + c + 3, ag[i].w);
+    atomicAdd(sh + E + c, ab[i].x); atomicAdd(sh + E + c + 1, ab[i].y); atomicAdd(sh + E + c + 2, ab[i].z); atomicAdd(sh + E + c + 3, ab[i].w);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    atomicAdd(dgamma + c, sh[c]);
+    atomicAdd(dbeta + c, sh[E + c]);
+  }
+}
+
 // -------------------------------------------------------------------- softmax
 // One warp per row, row staged in shared memory (cols floats per warp).
 __global__ void softmax_fwd_kernel(const float* __restrict__ x, long long rows, int cols, bf16* __restrict__ y16,
@@ -246,8 +314,12 @@ extern "C" int mirror_layernorm_bwd(const float* dy, const float* x, const float
   long long grid = (rows + kWarps * 4 - 1) / (kWarps * 4);  // >= 4 rows per warp to amortise the column atomics
   if (grid > (long long)num_sms() * 2) grid = (long long)num_sms() * 2;
   if (grid < 1) grid = 1;
-  ln_bwd_kernel<<<(int)grid, kWarps * 32, 2 * E * sizeof(float), STREAM>>>(dy, x, gamma, mean, rstd, B, S, E, n_out, pad, dx,
-                                                                           add, dgamma, dbeta);
+  if (E == 768) {
+    ln_bwd_reg_kernel<6><<<(int)grid, kWarps * 32, 0, STREAM>>>(dy, x, gamma, mean, rstd, B, S, n_out, pad, dx, add, dgamma, dbeta);
+  } else {
+    ln_bwd_kernel<<<(int)grid, kWarps * 32, 2 * E * sizeof(float), STREAM>>>(dy, x, gamma, mean, rstd, B, S, E, n_out, pad, dx,
+                                                                             add, dgamma, dbeta);
+  }
   MB_LAUNCH_CHECK();
   return 0;
 }

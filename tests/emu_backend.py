@@ -25,13 +25,20 @@ def release():
 
 
 def hash_u01(seed, idx):
-    """mb::hash_u01 (csrc/common.cuh) on numpy uint64."""
+    """mb::hash_u01 (csrc/common.cuh) on numpy uint32."""
+    M = np.uint64(0xFFFFFFFF)
+    idx = idx.astype(np.uint64)
+    seed = int(seed)
     with np.errstate(over="ignore"):
-        z = idx.astype(np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x632BE59BD9B4E019)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    return (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+        h = ((idx & M) + np.uint64((seed & 0xFFFFFFFF) * 0x9E3779B1 & 0xFFFFFFFF) + (((idx >> np.uint64(32)) & M) * np.uint64(0x85EBCA77) & M)) & M
+        h = h.astype(np.uint32)
+        h ^= np.uint32((seed >> 32) & 0xFFFFFFFF)
+        h ^= h >> np.uint32(16)
+        h *= np.uint32(0x7FEB352D)
+        h ^= h >> np.uint32(15)
+        h *= np.uint32(0x846CA68B)
+        h ^= h >> np.uint32(16)
+    return (h >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
 
 
 def keep_mask(seed, shape, p):

@@ -15,7 +15,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["basic", "majors", "batched", "epilogue", "splitk", "perf"]
+GROUPS = ["basic", "majors", "cluster3", "batched", "epilogue", "splitk", "perf"]
 
 
 def ref_gemm(a, b, alpha=1.0, bias=None, act=0, res=None, gamma=1.0, beta=0.0, old=None):
@@ -98,6 +98,22 @@ def run_group(group):
             ok &= simple(f"{nm} 384x96x2304", 384, 96, 2304, at, bt)
             ok &= simple(f"{nm} 300x200x72", 304, 200, 72, at, bt)
             ok &= simple(f"{nm} 768x768x4096", 768, 768, 4096, at, bt)
+    elif group == "cluster3":
+        # 384-row problems run on 3-CTA clusters with TMA-multicast B (the Moore-Penrose / landmark matrices)
+        for (at, bt, nm) in ((False, False, "NT"), (False, True, "NN"), (True, False, "TT"), (True, True, "TN")):
+            for (Bt, M, N, K_) in ((5, 384, 384, 384), (3, 384, 2304, 96), (2, 304, 192, 200), (70, 384, 384, 384)):
+                a = bf(Bt, K_, M).transpose(-1, -2) if at else bf(Bt, M, K_)
+                b = bf(Bt, K_, N).transpose(-1, -2) if bt else bf(Bt, N, K_)
+                r = bf(Bt, M, N)
+                o32 = torch.full((Bt, M, N), float("nan"), device=dev)
+                o16 = torch.zeros(Bt, M, N, device=dev, dtype=torch.bfloat16)
+                K.gemm(a, b, out_f32=o32, out_bf16=o16, alpha=0.25, res=r, gamma=1.0, diag=1.0 if M == N else 0.0)
+                torch.cuda.synchronize()
+                want = 0.25 * a.float() @ b.float().transpose(-1, -2) + r.float()
+                if M == N:
+                    want = want + torch.eye(M, device=dev)
+                ok &= report(f"{nm} batch{Bt} {M}x{N}x{K_} f32", o32, want, 2e-3)
+                ok &= report(f"{nm} batch{Bt} {M}x{N}x{K_} bf16", o16, want, 1.2e-2)
     elif group == "batched":
         B, n, E, h = 3, 512, 768, 8
         d, m = E // h, 128
@@ -165,6 +181,22 @@ def run_group(group):
             torch.cuda.synchronize()
             ok &= report(f"split-K TN {M}x{N}x{K_}", o, ref_gemm(a, b), 2e-3)
     elif group == "perf":
+        for (Bt, nm) in ((512, "NN"), (512, "NT")):
+            a = bf(Bt, 384, 384)
+            b = bf(Bt, 384, 384)
+            bb = b.transpose(-1, -2) if nm == "NN" else b
+            o = torch.empty(Bt, 384, 384, device=dev, dtype=torch.bfloat16)
+            for _ in range(3):
+                K.gemm(a, bb, out_bf16=o)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                K.gemm(a, bb, out_bf16=o)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print(f"[perf] {nm} batched 512 x 384^3 bf16-out: {ms:.3f} ms = {2 * Bt * 384 ** 3 / ms / 1e9:.0f} TFLOP/s", flush=True)
         for (nm, M, N, K_, at, bt) in (("NT qkv-like", 147456 // 4, 2304, 768, False, False),
                                        ("NT square 8192", 8192, 8192, 8192, False, False),
                                        ("NN 8192", 8192, 8192, 8192, False, True),
