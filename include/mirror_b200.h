@@ -39,7 +39,7 @@ int mirror_device_supported(void);
  *
  *   for every (b2,b1):  acc[M,N] = sum_k A[m,k] * B[n,k]            (bf16 x bf16 -> fp32)
  *   v = alpha*acc + diag*[m==n] + bias[n];  v = act(v);  v = dropout(v);
- *   v += gamma * R[m,n] + beta * out_f32_old[m,n];   out_f32 = v;  out_bf16 = bf16(v)
+ *   v += gamma * R[m,n] + gamma2 * R2[m,n] + beta * out_f32_old[m,n];   out_f32 = v;  out_bf16 = bf16(v)
  *
  * Replaces every nn.Linear / einsum / `@` of the hot path:
  *   models/mirror.py:346,654 (_fc1), :594-605 heads, :70-74,:100 RNA qkv/proj, timm Mlp
@@ -78,9 +78,16 @@ typedef struct {
   int32_t split_k; /* >1: K is split over CTAs and fp32 partials are atomically added into out_f32
                       (caller pre-zeroes it); only alpha is applied */
   float diag;      /* added to alpha*acc where m == n (e.g. E = I - a2.z of the Moore-Penrose step) */
+  const void* res2; /* optional second residual (bf16, same element strides as `res`): v += gamma2 * R2[m,n] */
+  float gamma2;
 } mirror_gemm_args;
 
 int mirror_gemm_bf16(const mirror_gemm_args* args, mirror_stream_t stream);
+/* D = epilogue( sum_t A_t * B_t^T ), 1 <= nterms <= 6: the terms share M, N and the batch dims; K and the operand layouts
+ * may differ.  terms[0] carries the epilogue and the outputs.  All products accumulate in the same TMEM tile, so a sum of
+ * products costs one epilogue pass (used by the backward of the 6-step Moore-Penrose iteration of nystrom_attention, where
+ * autograd would issue one fp32 accumulate pass per product). */
+int mirror_gemm_bf16_multi(const mirror_gemm_args* terms, int32_t nterms, mirror_stream_t stream);
 /* Same contract on CUDA cores (one thread per output element).  Test/diagnostic tool used by the
  * GPU unit tests to cross-check the tensor-core kernel at sizes where a host reference is slow. */
 int mirror_gemm_bf16_simt(const mirror_gemm_args* args, mirror_stream_t stream);

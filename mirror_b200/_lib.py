@@ -36,6 +36,8 @@ class GemmArgs(ctypes.Structure):
         ("ldc16", ctypes.c_int64), ("c16_bs1", ctypes.c_int64), ("c16_bs2", ctypes.c_int64),
         ("split_k", ctypes.c_int32),
         ("diag", ctypes.c_float),
+        ("res2", ctypes.c_void_p),
+        ("gamma2", ctypes.c_float),
     ]
 
 
@@ -59,6 +61,7 @@ def check(rc: int, what: str):
 _P, _I32, _I64, _F, _U64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_uint64
 SIGNATURES = {
     "mirror_gemm_bf16": [_P, _P],
+    "mirror_gemm_bf16_multi": [_P, _I32, _P],
     "mirror_gemm_bf16_simt": [_P, _P],
     "mirror_cast_f32_bf16": [_P, _I64, _I32, _I64, _P, _I32, _I64, _P],
     "mirror_cast_split3": [_P, _I64, _I32, _I64, _P, _I64, _I32, _I32, _I32, _P],

@@ -111,8 +111,9 @@ struct Epi {
   float drop_p, drop_scale;
   uint64_t drop_seed;
   const void* res;
+  const bf16* res2;  // second residual, bf16, same element strides as res
   int res_is_bf16;
-  float gamma;
+  float gamma, gamma2;
   long long ldr, r_bs1, r_bs2;
   float beta;
   float* o32;
@@ -139,6 +140,7 @@ __device__ __forceinline__ void epi_store_scalar(const Epi& e, float acc, int b1
   if (e.res) {
     const long long off = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)row * e.ldr + col;
     v += e.gamma * (e.res_is_bf16 ? __bfloat162float(((const bf16*)e.res)[off]) : ((const float*)e.res)[off]);
+    if (e.res2) v += e.gamma2 * __bfloat162float(e.res2[off]);
   }
   if (e.o32) {
     float* p = e.o32 + b2 * e.c32_bs2 + b1 * e.c32_bs1 + (long long)row * e.ldc32 + col;

@@ -159,6 +159,20 @@ __device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, uint32_t taddr,
       }
     }
   }
+  if (e.res2 && row_ok) {
+    const uint4* rp = reinterpret_cast<const uint4*>(e.res2 + b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)row * e.ldr + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 u = rp[j];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __bfloat1622float2(h[t]);
+        v[j * 8 + 2 * t] += e.gamma2 * f.x;
+        v[j * 8 + 2 * t + 1] += e.gamma2 * f.y;
+      }
+    }
+  }
   const int rowA = row0 + (lane & ~1);
   const bool okA = rowA < e.M, okB = rowA + 1 < e.M;
   if (e.o32) {
@@ -551,6 +565,176 @@ gemm_tcgen05_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-term variant: D = epilogue( sum_t A_t * B_t^T ) with up to kMaxTerms operand pairs that share M, N and the
+// batch dims but may differ in K and in their layouts (majors are runtime values here).  All terms accumulate into the
+// same TMEM tile, so a sum of matrix products costs ONE epilogue pass instead of one fp32 read-modify-write pass per
+// product -- the Moore-Penrose backward (g_E = g_F G1^T + g_G1 E^T + E^T g_G1, g_z = g F^T + a2^T g_E,
+// g_a2 = sum over the 6 iterations of g_E z^T) is built from such sums of 384^3 products.
+constexpr int kMaxTerms = 6;
+struct MultiMaps {
+  CUtensorMap a[kMaxTerms];
+  CUtensorMap b[kMaxTerms];
+};
+struct MultiInfo {
+  int nterms;
+  int kb[kMaxTerms];    // k-blocks of term t
+  int a_mn[kMaxTerms];  // operand majors of term t
+  int b_mn[kMaxTerms];
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_constant__ KParams p,
+                          const __grid_constant__ MultiInfo mi, const int vec_ok) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  const uint32_t epi_stage = smem_u32(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && elect_one()) {
+    for (int t = 0; t < mi.nterms; ++t) {
+      tma_prefetch_desc(&maps.a[t]);
+      tma_prefetch_desc(&maps.b[t]);
+    }
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < C::STAGES; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], 1);
+      }
+      for (int s = 0; s < kAccStages; ++s) {
+        mbar_init(&tfull[s], 1);
+        mbar_init(&tempty[s], kEpiWarps);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total = p.tiles_m * p.tiles_n * p.batch1 * p.batch2;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int nb = w % p.tiles_n;
+        int t = w / p.tiles_n;
+        const int mb_ = t % p.tiles_m;
+        t /= p.tiles_m;
+        const int b1 = t % p.batch1, b2 = t / p.batch1;
+        const int m0 = mb_ * BM, n0 = nb * BN;
+        for (int term = 0; term < mi.nterms; ++term) {
+          const CUtensorMap* ma = &maps.a[term];
+          const CUtensorMap* mbp = &maps.b[term];
+          const int a_mn = mi.a_mn[term], b_mn = mi.b_mn[term];
+          for (int kb = 0; kb < mi.kb[term]; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+            uint8_t* a = sA + stage * C::A_BYTES;
+            uint8_t* b = sB + stage * C::B_BYTES;
+            if (a_mn) {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i) tma_load_4d(ma, &full[stage], a + i * (BK * 128), m0 + i * 64, kb * BK, b1, b2);
+            } else {
+              tma_load_4d(ma, &full[stage], a, kb * BK, m0, b1, b2);
+            }
+            if (b_mn) {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i) tma_load_4d(mbp, &full[stage], b + i * (BK * 128), n0 + i * 64, kb * BK, b1, b2);
+            } else {
+              tma_load_4d(mbp, &full[stage], b, kb * BK, n0, b1, b2);
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        uint32_t accumulate = 0;
+        for (int term = 0; term < mi.nterms; ++term) {
+          const int a_mn = mi.a_mn[term], b_mn = mi.b_mn[term];
+          const uint32_t idesc = make_idesc_bf16(BM, BN, a_mn, b_mn);
+          const uint32_t a_lbo = a_mn ? BK * 128 : 0, b_lbo = b_mn ? BK * 128 : 0;
+          const uint32_t a_kstep = a_mn ? (UMMA_K / 8) * 1024 : UMMA_K * 2;
+          const uint32_t b_kstep = b_mn ? (UMMA_K / 8) * 1024 : UMMA_K * 2;
+          for (int kb = 0; kb < mi.kb[term]; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
+            const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+              umma_f16(tmem_d, ad, bd, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tfull[as]);
+        ++it;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const bool fast = vec_ok != 0 && p.e.act != MIRROR_ACT_GELU;
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int nb = w % p.tiles_n;
+      int t = w / p.tiles_n;
+      const int mb_ = t % p.tiles_m;
+      t /= p.tiles_m;
+      const int b1 = t % p.batch1, b2 = t / p.batch1;
+      const int cbase = nb * BN + half * (BN / 2);
+      const int row0 = mb_ * BM + q * 32;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), epi_stage + (warp - 2) * 4096, b1,
+                        b2, row0, cbase, lane, &tfull[as], aphase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      ++it;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -628,6 +812,23 @@ int launch_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams
   return 0;
 }
 
+
+template <int BN>
+int launch_multi(const MultiMaps& maps, const KParams& p, const MultiInfo& mi, int vec_ok, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  auto kern = gemm_tcgen05_multi_kernel<BN>;
+  static bool configured = false;
+  if (!configured) {
+    MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const long long total = (long long)p.tiles_m * p.tiles_n * p.batch1 * p.batch2;
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(maps, p, mi, vec_ok);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
 int fill_epi(const mirror_gemm_args* g, Epi* e) {
   MB_CHECK_ARG(g && g->a && g->b, "gemm: null operand");
   MB_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0 && g->batch1 > 0 && g->batch2 > 0, "gemm: bad shape M=%d N=%d K=%d", g->M,
@@ -635,12 +836,14 @@ int fill_epi(const mirror_gemm_args* g, Epi* e) {
   MB_CHECK_ARG(g->out_f32 || g->out_bf16, "gemm: no output");
   MB_CHECK_ARG(g->beta == 0.f || g->out_f32, "gemm: beta needs out_f32");
   MB_CHECK_ARG(g->drop_p >= 0.f && g->drop_p < 1.f, "gemm: drop_p out of range");
-  MB_CHECK_ARG(g->split_k <= 1 || (g->out_f32 && !g->out_bf16 && !g->bias && !g->res && g->act == 0 && g->drop_p == 0.f && g->diag == 0.f),
+  MB_CHECK_ARG(g->split_k <= 1 || (g->out_f32 && !g->out_bf16 && !g->bias && !g->res && !g->res2 && g->act == 0 && g->drop_p == 0.f && g->diag == 0.f),
                "gemm: split_k supports only alpha and an fp32 accumulate target");
   e->M = g->M; e->N = g->N; e->batch1 = g->batch1;
   e->alpha = g->alpha; e->diag = g->diag; e->bias = g->bias; e->act = g->act;
   e->drop_p = g->drop_p; e->drop_scale = 1.f / (1.f - g->drop_p); e->drop_seed = g->drop_seed;
   e->res = g->res; e->res_is_bf16 = g->res_is_bf16; e->gamma = g->gamma;
+  e->res2 = reinterpret_cast<const bf16*>(g->res2); e->gamma2 = g->gamma2;
+  MB_CHECK_ARG(!g->res2 || g->res, "gemm: res2 needs res (it shares its strides)");
   e->ldr = g->ldr; e->r_bs1 = g->r_bs1; e->r_bs2 = g->r_bs2;
   e->beta = g->beta;
   e->o32 = g->out_f32; e->ldc32 = g->ldc32; e->c32_bs1 = g->c32_bs1; e->c32_bs2 = g->c32_bs2;
@@ -658,6 +861,7 @@ bool epi_vec_ok(const mirror_gemm_args* g) {
   if (g->res) {
     const int q = g->res_is_bf16 ? 8 : 4;
     ok = ok && al(g->res, 16) && g->ldr % q == 0 && g->r_bs1 % q == 0 && g->r_bs2 % q == 0;
+    if (g->res2) ok = ok && al(g->res2, 16) && g->ldr % 8 == 0 && g->r_bs1 % 8 == 0 && g->r_bs2 % 8 == 0;
   }
   return ok;
 }
@@ -775,6 +979,52 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
   if (BN == 192) { MB_DISPATCH(192) }
   MB_DISPATCH(128)
 #undef MB_DISPATCH
+}
+
+
+extern "C" int mirror_gemm_bf16_multi(const mirror_gemm_args* terms, int32_t nterms, mirror_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(terms && nterms >= 1 && nterms <= kMaxTerms, "gemm_multi: 1..%d terms", kMaxTerms);
+  const mirror_gemm_args* g = &terms[0];
+  KParams p;
+  int rc = fill_epi(g, &p.e);
+  if (rc) return rc;
+  MB_CHECK_ARG(g->split_k <= 1, "gemm_multi: split_k is not supported");
+  const int BN = (g->N % 256 == 0 || g->N >= 1024) ? 256 : (g->N % 192 == 0 ? 192 : 128);
+  p.K = g->K;
+  p.batch1 = g->batch1;
+  p.batch2 = g->batch2;
+  p.tiles_m = (g->M + BM - 1) / BM;
+  p.tiles_n = (g->N + BN - 1) / BN;
+  p.split_k = 1;
+  p.a_b1 = p.a_b2 = p.b_b1 = p.b_b2 = 1;
+  MultiMaps maps;
+  MultiInfo mi;
+  mi.nterms = nterms;
+  for (int t = 0; t < nterms; ++t) {
+    const mirror_gemm_args* x = &terms[t];
+    MB_CHECK_ARG(x->a && x->b && x->M == g->M && x->N == g->N && x->batch1 == g->batch1 && x->batch2 == g->batch2 && x->K > 0,
+                 "gemm_multi: term %d does not match M/N/batch of term 0", t);
+    MB_CHECK_ARG((g->batch1 == 1 || (x->a_bs1 && x->b_bs1)) && (g->batch2 == 1 || (x->a_bs2 && x->b_bs2)),
+                 "gemm_multi: broadcast operands are not supported");
+    mi.kb[t] = (x->K + BK - 1) / BK;
+    mi.a_mn[t] = x->a_mn_major ? 1 : 0;
+    mi.b_mn[t] = x->b_mn_major ? 1 : 0;
+    rc = make_operand_map(&maps.a[t], x->a, x->a_mn_major, x->M, x->K, x->lda, x->a_bs1, x->batch1, x->a_bs2, x->batch2, BM);
+    if (rc) return rc;
+    rc = make_operand_map(&maps.b[t], x->b, x->b_mn_major, x->N, x->K, x->ldb, x->b_bs1, x->batch1, x->b_bs2, x->batch2, BN);
+    if (rc) return rc;
+  }
+  for (int t = nterms; t < kMaxTerms; ++t) {
+    mi.kb[t] = 0;
+    mi.a_mn[t] = mi.b_mn[t] = 0;
+    maps.a[t] = maps.a[0];
+    maps.b[t] = maps.b[0];
+  }
+  const int vec = epi_vec_ok(g) ? 1 : 0;
+  if (BN == 256) return launch_multi<256>(maps, p, mi, vec, stream);
+  if (BN == 192) return launch_multi<192>(maps, p, mi, vec, stream);
+  return launch_multi<128>(maps, p, mi, vec, stream);
 }
 
 extern "C" int mirror_gemm_bf16_simt(const mirror_gemm_args* g, mirror_stream_t stream_) {

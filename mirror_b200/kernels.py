@@ -52,29 +52,39 @@ def _major(t):
     raise ValueError(f"gemm operand needs a unit stride in one of its last two dims, got {t.stride()}")
 
 
-def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NONE, drop_p=0.0, drop_seed=0,
-         res=None, gamma=1.0, beta=0.0, split_k=1, diag=0.0, simt=False):
-    """C[..,M,N] = epilogue(A[..,M,K] @ B[..,N,K]^T); see mirror_gemm_args.
-
-    ``a`` / ``b`` are bf16 views whose last two dims are (M,K) / (N,K); either
-    of the two may carry the unit stride, so ``x.transpose(-1,-2)`` views give
-    the NN / TN forms without copies.  Up to two leading batch dims.
-    """
-    if _TEST_BACKEND is not None:
-        return _TEST_BACKEND.gemm(a, b, out_f32=out_f32, out_bf16=out_bf16, alpha=alpha, bias=bias, act=act,
-                                  drop_p=drop_p, drop_seed=drop_seed, res=res, gamma=gamma, beta=beta, split_k=split_k,
-                                  diag=diag)
+def _operands(g, a, b):
     a4, b4 = _as4(_cuda(a, torch.bfloat16)), _as4(_cuda(b, torch.bfloat16))
     B2, B1, M, K = a4.shape
     N = b4.shape[2]
     if b4.shape != (B2, B1, N, K):
         raise ValueError(f"gemm shape mismatch {tuple(a.shape)} x {tuple(b.shape)}")
-    g = _lib.GemmArgs()
     g.a, g.b = a4.data_ptr(), b4.data_ptr()
     g.a_mn_major, g.lda = _major(a4)
     g.b_mn_major, g.ldb = _major(b4)
     g.a_bs1, g.a_bs2, g.b_bs1, g.b_bs2 = a4.stride(1), a4.stride(0), b4.stride(1), b4.stride(0)
     g.M, g.N, g.K, g.batch1, g.batch2 = M, N, K, B1, B2
+    return B2, B1, M, N
+
+
+def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NONE, drop_p=0.0, drop_seed=0,
+         res=None, gamma=1.0, beta=0.0, split_k=1, diag=0.0, more=None, res2=None, gamma2=1.0, simt=False):
+    """C[..,M,N] = epilogue(A[..,M,K] @ B[..,N,K]^T [+ sum of A_t @ B_t^T for (A_t, B_t) in `more`]); see mirror_gemm_args.
+
+    ``a`` / ``b`` are bf16 views whose last two dims are (M,K) / (N,K); either of the two may carry the unit stride, so
+    ``x.transpose(-1,-2)`` views give the NN / TN forms without copies.  Up to two leading batch dims.  ``more``: up to
+    five further operand pairs with the same M, N and batch dims, accumulated into the same tile (one epilogue pass).
+    """
+    if _TEST_BACKEND is not None:
+        return _TEST_BACKEND.gemm(a, b, out_f32=out_f32, out_bf16=out_bf16, alpha=alpha, bias=bias, act=act,
+                                  drop_p=drop_p, drop_seed=drop_seed, res=res, gamma=gamma, beta=beta, split_k=split_k,
+                                  diag=diag, more=more, res2=res2, gamma2=gamma2)
+    nterms = 1 + (len(more) if more else 0)
+    terms = (_lib.GemmArgs * nterms)()
+    g = terms[0]
+    B2, B1, M, N = _operands(g, a, b)
+    for t, (at, bt) in enumerate(more or (), start=1):
+        if _operands(terms[t], at, bt) != (B2, B1, M, N):
+            raise ValueError("gemm: every term must share M, N and the batch dims")
     g.alpha = alpha
     g.bias = _cuda(bias, torch.float32).data_ptr() if bias is not None else None
     g.act, g.drop_p, g.drop_seed = act, drop_p, drop_seed
@@ -86,6 +96,13 @@ def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NON
         if r4.dtype not in (torch.bfloat16, torch.float32):
             raise TypeError("residual must be bf16 or f32")
         g.ldr, g.r_bs1, g.r_bs2 = r4.stride(2), r4.stride(1), r4.stride(0)
+        if res2 is not None:
+            q4 = _as4(_cuda(res2, torch.bfloat16))
+            if q4.shape != r4.shape or q4.stride() != r4.stride():
+                raise ValueError("gemm res2 must be bf16 with the shape and element strides of res")
+            g.res2, g.gamma2 = q4.data_ptr(), gamma2
+    elif res2 is not None:
+        raise ValueError("gemm res2 needs res")
     g.gamma, g.beta, g.split_k, g.diag = gamma, beta, split_k, diag
     for o, dt, name in ((out_f32, torch.float32, "32"), (out_bf16, torch.bfloat16, "16")):
         if o is None:
@@ -97,8 +114,13 @@ def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NON
             g.out_f32, g.ldc32, g.c32_bs1, g.c32_bs2 = o4.data_ptr(), o4.stride(2), o4.stride(1), o4.stride(0)
         else:
             g.out_bf16, g.ldc16, g.c16_bs1, g.c16_bs2 = o4.data_ptr(), o4.stride(2), o4.stride(1), o4.stride(0)
-    fn = _lib.lib().mirror_gemm_bf16_simt if simt else _lib.lib().mirror_gemm_bf16
-    _lib.check(fn(ctypes.byref(g), _stream()), "gemm")
+    if nterms > 1:
+        if simt:
+            raise ValueError("the SIMT cross-check kernel has no multi-term form")
+        _lib.check(_lib.fn("mirror_gemm_bf16_multi")(ctypes.cast(terms, ctypes.c_void_p), nterms, _stream()), "gemm_multi")
+    else:
+        fn = _lib.lib().mirror_gemm_bf16_simt if simt else _lib.lib().mirror_gemm_bf16
+        _lib.check(fn(ctypes.byref(g), _stream()), "gemm")
     LAUNCHES[0] += 1
 
 

@@ -322,7 +322,7 @@ class NystromLayerFn(Function):
 
     Differences from the reference evaluation order, all exact in real arithmetic: q's 1/sqrt(d) is folded into the three
     similarity GEMMs; (attn1 z)(attn3 v) is evaluated as attn1 (z (attn3 v)); each Moore-Penrose step
-    z' = 0.25 z (13I - xz(15I - xz(7I - xz))) is evaluated in the residual E = I - a2 z as z' = z + z(E + E^2 + 0.25 E^3),
+    z' = 0.25 z (13I - xz(15I - xz(7I - xz))) is evaluated in the residual E = I - a2 z as z' = z + z E (I + E + 0.25 E^2),
     the same cubic without the cancellation between O(10)-sized terms that costs bf16 operands their accuracy.
     """
 
@@ -363,7 +363,8 @@ class NystromLayerFn(Function):
         mm = (B, hd, m, m)
         for _ in range(PINV_ITERS):
             # z' = 0.25 z (13 I - xz (15 I - xz (7 I - xz))) written in the residual E = I - xz:
-            #   z' = z + z (E + E^2 + 0.25 E^3)  --  same polynomial, but no cancellation between O(10) terms
+            #   z' = z + z F,  F = E + E G1,  G1 = E + 0.25 E^2      (= z + z (E + E^2 + 0.25 E^3))
+            # -- the same cubic, but no cancellation between O(10) terms; the leading terms are added in the fp32 epilogue.
             Em = torch.empty(mm, device=dev, dtype=BF16)
             K.gemm(a2_16, _T(z16), out_bf16=Em, alpha=-1.0, diag=1.0)              # E  = I - a2 z
             G1 = torch.empty(mm, device=dev, dtype=BF16)
@@ -372,7 +373,7 @@ class NystromLayerFn(Function):
             K.gemm(Em, _T(G1), out_bf16=Fm, res=Em)                                # F  = E + E G1
             zn32 = torch.empty(mm, device=dev, dtype=F32)
             zn16 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(z16, _T(Fm), out_f32=zn32, out_bf16=zn16, res=z32)              # z' = z + z F
+            K.gemm(z16, _T(Fm), out_f32=zn32, out_bf16=zn16, res=z32)              # z'  = z + z F
             iters += [z16, Em, G1, Fm]
             z32, z16 = zn32, zn16
         kv = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
@@ -440,25 +441,28 @@ class NystromLayerFn(Function):
         ds3, _ = K.softmax_bwd(a3, da3, scale)
         del da3
 
-        # ---- Moore-Penrose iterations, reversed
-        ga2 = torch.empty(mm, device=dev, dtype=F32)
+        # ---- Moore-Penrose iterations, reversed.  With gEn := -g_E every sum of products is ONE multi-term GEMM:
+        #   gF   = z^T g                gG1q = 0.25 E^T gF
+        #   gEn  = -(gF G1^T + gG1q E^T + E^T gG1q) - gF - 4 gG1q
+        #   g   <- g + g F^T + a2^T gEn           and after the loop   g_a2 = sum_it gEn_it z_it^T
+        gens = []
         for it in reversed(range(PINV_ITERS)):
             z16, Em, G1, Fm = iters[4 * it:4 * it + 4]
             gF = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(_T(z16), _T(gz16), out_bf16=gF)                                        # gF  = z^T g
+            K.gemm(_T(z16), _T(gz16), out_bf16=gF)
+            gG1q = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(_T(Em), _T(gF), out_bf16=gG1q, alpha=0.25)
+            gEn = torch.empty(mm, device=dev, dtype=BF16)
+            K.gemm(gF, G1, more=[(gG1q, Em), (_T(Em), _T(gG1q))], out_bf16=gEn, alpha=-1.0, res=gF, gamma=-1.0, res2=gG1q,
+                   gamma2=-4.0)
             gzn32 = torch.empty(mm, device=dev, dtype=F32)
-            K.gemm(gz16, Fm, out_f32=gzn32, res=gz32)                                     # gz  = g + g F^T
-            gE32 = torch.empty(mm, device=dev, dtype=F32)
-            K.gemm(gF, G1, out_f32=gE32, res=gF)                                          # gE  = gF + gF G1^T
-            gG1 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(_T(Em), _T(gF), out_bf16=gG1)                                          # gG1 = E^T gF
-            K.gemm(gG1, Em, out_f32=gE32, alpha=0.25, res=gG1, beta=1.0)                  # gE += gG1 + 0.25 gG1 E^T
-            gE16 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(_T(Em), _T(gG1), out_f32=gE32, out_bf16=gE16, alpha=0.25, beta=1.0)    # gE += 0.25 E^T gG1
-            K.gemm(gE16, z16, out_f32=ga2, alpha=-1.0, beta=0.0 if it == PINV_ITERS - 1 else 1.0)  # ga2 -= gE z^T
             gzn16 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(_T(a2_16), _T(gE16), out_f32=gzn32, out_bf16=gzn16, alpha=-1.0, beta=1.0)       # gz  -= a2^T gE
+            K.gemm(gz16, Fm, more=[(_T(a2_16), _T(gEn))], out_f32=gzn32, out_bf16=gzn16, res=gz32)
+            gens.append((gEn, z16))
             gz32, gz16 = gzn32, gzn16
+        ga2 = torch.empty(mm, device=dev, dtype=F32)
+        K.gemm(gens[0][0], gens[0][1], more=gens[1:], out_f32=ga2)
+        del gens
         K.pinv_init_bwd(gz32, z0_32, scratch, ga2, True)
         ds2, _ = K.softmax_bwd(a2_16, ga2, scale)
         del ga2, gz32, gz16

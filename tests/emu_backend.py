@@ -61,7 +61,7 @@ class Emu:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=0, drop_p=0.0, drop_seed=0, res=None,
-             gamma=1.0, beta=0.0, split_k=1, diag=0.0):
+             gamma=1.0, beta=0.0, split_k=1, diag=0.0, more=None, res2=None, gamma2=1.0):
         assert a.dtype == BF16 and b.dtype == BF16
         assert a.stride(-1) == 1 or a.stride(-2) == 1
         assert b.stride(-1) == 1 or b.stride(-2) == 1
@@ -72,6 +72,9 @@ class Emu:
             for s, n in zip(t.stride()[:-2], t.shape[:-2]):
                 assert n == 1 or s % 8 == 0, f"batch stride {s}"
         acc = torch.matmul(a.float(), b.float().transpose(-1, -2))
+        for (at, bt) in (more or ()):
+            assert at.dtype == BF16 and bt.dtype == BF16
+            acc = acc + torch.matmul(at.float(), bt.float().transpose(-1, -2))
         if split_k > 1:
             assert out_f32 is not None and out_bf16 is None and bias is None and res is None and act == 0 and drop_p == 0
             out_f32 += alpha * acc.view(out_f32.shape)
@@ -87,6 +90,9 @@ class Emu:
         if res is not None:
             assert res.shape == v.shape and res.stride(-1) == 1
             v = v + gamma * res.float()
+            if res2 is not None:
+                assert res2.dtype == BF16 and res2.shape == res.shape and res2.stride() == res.stride()
+                v = v + gamma2 * res2.float()
         if out_f32 is not None:
             assert out_f32.shape == v.shape and out_f32.stride(-1) == 1
             if beta != 0.0:

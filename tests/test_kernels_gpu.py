@@ -285,3 +285,27 @@ def test_gemm_broadcast_weight_over_batch():
     xd = x.cuda()
     K.gemm(xd[:, 5:, :], w.cuda().unsqueeze(0).expand(B, E, E), out_f32=out)
     close(out, out_cpu, 1e-5, "broadcast gemm")
+
+
+def test_gemm_multi_term_mixed_layouts_and_second_residual():
+    Bt, M = 3, 384
+    mk = lambda seed: rn(Bt, M, M, seed=seed, scale=0.2).to(BF16)
+    gF, G1, gq, Em, r = mk(1), mk(2), mk(3), mk(4), mk(5)
+    o_cpu, o16_cpu = torch.zeros(Bt, M, M), torch.zeros(Bt, M, M, dtype=BF16)
+    T = lambda x: x.transpose(-1, -2)
+    kw = dict(alpha=-1.0, gamma=-1.0, gamma2=-4.0)
+    EMU.gemm(gF, G1, more=[(gq, Em), (T(Em), T(gq))], out_f32=o_cpu, out_bf16=o16_cpu, res=gF, res2=r, **kw)
+    d = lambda x: x.cuda()
+    gFd, G1d, gqd, Emd, rd = d(gF), d(G1), d(gq), d(Em), d(r)
+    o, o16 = torch.zeros(Bt, M, M, device="cuda"), torch.zeros(Bt, M, M, device="cuda", dtype=BF16)
+    K.gemm(gFd, G1d, more=[(gqd, Emd), (T(Emd), T(gqd))], out_f32=o, out_bf16=o16, res=gFd, res2=rd, **kw)
+    close(o, o_cpu, 2e-5, "multi f32")
+    close(o16, o16_cpu, 8e-3, "multi bf16")
+    # six terms with different K (the g_a2 reduction over the Moore-Penrose iterations)
+    pairs = [(rn(2, 200, 64 + 8 * i, seed=10 + i).to(BF16), rn(2, 136, 64 + 8 * i, seed=20 + i).to(BF16)) for i in range(6)]
+    o_cpu = torch.zeros(2, 200, 136)
+    EMU.gemm(pairs[0][0], pairs[0][1], more=pairs[1:], out_f32=o_cpu)
+    pd = [(a.cuda(), b.cuda()) for a, b in pairs]
+    o = torch.zeros(2, 200, 136, device="cuda")
+    K.gemm(pd[0][0], pd[0][1], more=pd[1:], out_f32=o)
+    close(o, o_cpu, 2e-5, "six-term")
