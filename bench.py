@@ -270,7 +270,11 @@ def main():
             bt *= d
         sig = (bt, a.shape[-2], b.shape[-2], a.shape[-1], "T" if a.stride(-1) != 1 else "N", "N" if b.stride(-1) != 1 else "T",
                "f32" if kw.get("out_f32") is not None else "", "b16" if kw.get("out_bf16") is not None else "", kw.get("split_k", 1))
-        rec.append((s_, e_, 2.0 * bt * a.shape[-2] * a.shape[-1] * b.shape[-2], sig))
+        flop = 2.0 * bt * a.shape[-2] * a.shape[-1] * b.shape[-2]
+        for (am, bm) in (kw.get("more") or ()):  # multi-term launches: every product counts
+            flop += 2.0 * bt * am.shape[-2] * am.shape[-1] * bm.shape[-2]
+        sig = sig + (1 + len(kw.get("more") or ()),)
+        rec.append((s_, e_, flop, sig))
 
     K.gemm = timed_gemm
     import mirror_b200.ops as _ops
@@ -291,9 +295,9 @@ def main():
             t_[1] += s_.elapsed_time(e_)
             t_[2] += f
         print(f"GEMM launches of one step: {len(rec)}, {gemm_ms:.2f} ms of {ei0.elapsed_time(ei1):.2f} ms", file=sys.stderr)
-        print("batch      M      N      K  AB  outs      sk  count       ms   TFLOP/s", file=sys.stderr)
+        print("batch      M      N      K  AB  outs      sk terms  count       ms   TFLOP/s", file=sys.stderr)
         for sig, (c, ms_, f) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
-            print(f"{sig[0]:5d} {sig[1]:6d} {sig[2]:6d} {sig[3]:6d}  {sig[4]}{sig[5]}  {sig[6]:3s} {sig[7]:3s} {sig[8]:3d} {c:6d} {ms_:8.3f} {f / ms_ / 1e9:9.0f}",
+            print(f"{sig[0]:5d} {sig[1]:6d} {sig[2]:6d} {sig[3]:6d}  {sig[4]}{sig[5]}  {sig[6]:3s} {sig[7]:3s} {sig[8]:3d} {sig[9]:5d} {c:6d} {ms_:8.3f} {f / ms_ / 1e9:9.0f}",
                   file=sys.stderr)
     inst_ms = ei0.elapsed_time(ei1)
     achieved = gemm_flop / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
