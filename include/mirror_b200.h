@@ -80,7 +80,22 @@ typedef struct {
   float diag;      /* added to alpha*acc where m == n (e.g. E = I - a2.z of the Moore-Penrose step) */
   const void* res2; /* optional second residual (bf16, same element strides as `res`): v += gamma2 * R2[m,n] */
   float gamma2;
+  int32_t res_row_div; /* >1: the residuals are read at row m / res_row_div (a row of R feeds res_row_div consecutive output
+                          rows: the landmark-mean backward of the Nystrom layer) */
+  int32_t mode;        /* MIRROR_GEMM_*: fused row-softmax epilogues (two GEMM passes, the logits never reach HBM) */
+  float* stats;        /* [batch2,batch1,M,nparts] float2 partials exchanged between the two passes, nparts = mirror_gemm_nparts(N) */
 } mirror_gemm_args;
+
+/* Fused row softmax of the Nystrom similarity matrices and its backward, as epilogue modes of the
+ * GEMM that produces the logits / the probability gradient.  Rows span several N tiles, so each takes two passes over the
+ * (cheap, K = head_dim) product: pass 1 leaves per-row partials per half tile, pass 2 recomputes the product and applies them.
+ *   ROWSTATS      stats[part] = (max, sum exp) of alpha*acc over the part's columns
+ *   SOFTMAX       out = exp(alpha*acc - max) / sum          (bf16 and/or f32)
+ *   ROWDOT        stats[part].x = sum_j acc_j * P_j over the part's columns, P = `res` (bf16 probabilities)
+ *   SOFTMAX_BWD   out = alpha * P * (acc - sum of partial dots)   (bf16): d logits-before-alpha
+ * Needs N % 32 == 0; alpha is the only other epilogue term honoured. */
+enum { MIRROR_GEMM_NORMAL = 0, MIRROR_GEMM_ROWSTATS = 1, MIRROR_GEMM_SOFTMAX = 2, MIRROR_GEMM_ROWDOT = 3, MIRROR_GEMM_SOFTMAX_BWD = 4 };
+int mirror_gemm_nparts(int32_t N);
 
 int mirror_gemm_bf16(const mirror_gemm_args* args, mirror_stream_t stream);
 /* D = epilogue( sum_t A_t * B_t^T ), 1 <= nterms <= 6: the terms share M, N and the batch dims; K and the operand layouts
@@ -135,9 +150,6 @@ int mirror_mask_pos_bwd(float* dy, const float* mask, float* dtok, int32_t tok_s
 /* Nyström landmarks: lm[b,j,0:2E] = mean of `seg` consecutive rows of the q and k slots of qkv[B,n,3E] */
 int mirror_landmark_fwd(const void* qkv_bf16, void* lm_bf16, int32_t B, int32_t n, int32_t m, int32_t seg, int32_t E,
                         mirror_stream_t stream);
-/* dqkv16 = bf16(dqkv32 + broadcast(dlm32)/seg) : landmark backward fused with the cast for the qkv weight/data gradients */
-int mirror_dqkv_finish(const float* dqkv32, const float* dlm32, void* dqkv_bf16, int32_t B, int32_t n, int32_t m, int32_t seg,
-                       int32_t E, mirror_stream_t stream);
 /* out[c] += sum_r x[r,c] (bias gradients) */
 int mirror_colsum(const void* x, int32_t is_bf16, int64_t rows, int32_t cols, int64_t ld, float* out, mirror_stream_t stream);
 /* z = mu + exp(0.5*logvar)*eps (Normal.rsample with injected eps, models/mirror.py:830-833) and its backward */
@@ -172,8 +184,8 @@ int mirror_l2norm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx
  * ---------------------------------------------------------------------------------------------- */
 /* out[b,t,c] = sum_j w[h(c),j] * v[b,t+j-16,c]  (res_conv: Conv2d(h,h,(33,1),groups=h,bias=False) on the value slot) */
 int mirror_res_conv_fwd(const void* qkv_bf16, const float* w, int32_t B, int32_t n, int32_t E, void* out_bf16, mirror_stream_t stream);
-/* dqkv32[..,2E:3E] += conv^T(dout);  dw[8,33] += weight gradient */
-int mirror_res_conv_bwd(const void* dout_bf16, const void* qkv_bf16, const float* w, int32_t B, int32_t n, int32_t E, float* dqkv32,
+/* dv_bf16[B,n,E] = conv^T(dout) (data gradient w.r.t. the value slot);  dw[8,33] += weight gradient */
+int mirror_res_conv_bwd(const void* dout_bf16, const void* qkv_bf16, const float* w, int32_t B, int32_t n, int32_t E, void* dv_bf16,
                         float* dw, mirror_stream_t stream);
 /* z0 = a2^T / (max_rowsum * max_colsum), maxima over the WHOLE [BH,m,m] tensor (moore_penrose_iter_pinv init).
  * scratch32: 32 bytes of device memory kept by the caller until the backward call. */

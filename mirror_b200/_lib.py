@@ -38,6 +38,9 @@ class GemmArgs(ctypes.Structure):
         ("diag", ctypes.c_float),
         ("res2", ctypes.c_void_p),
         ("gamma2", ctypes.c_float),
+        ("res_row_div", ctypes.c_int32),
+        ("mode", ctypes.c_int32),
+        ("stats", ctypes.c_void_p),
     ]
 
 
@@ -62,6 +65,7 @@ _P, _I32, _I64, _F, _U64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctyp
 SIGNATURES = {
     "mirror_gemm_bf16": [_P, _P],
     "mirror_gemm_bf16_multi": [_P, _I32, _P],
+    "mirror_gemm_nparts": [_I32],
     "mirror_gemm_bf16_simt": [_P, _P],
     "mirror_cast_f32_bf16": [_P, _I64, _I32, _I64, _P, _I32, _I64, _P],
     "mirror_cast_split3": [_P, _I64, _I32, _I64, _P, _I64, _I32, _I32, _I32, _P],
@@ -75,7 +79,6 @@ SIGNATURES = {
     "mirror_mask_pos_fwd": [_P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P],
     "mirror_mask_pos_bwd": [_P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P],
     "mirror_landmark_fwd": [_P, _P, _I32, _I32, _I32, _I32, _I32, _P],
-    "mirror_dqkv_finish": [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P],
     "mirror_colsum": [_P, _I32, _I64, _I32, _I64, _P, _P],
     "mirror_reparam_fwd": [_P, _P, _P, _I64, _P, _P, _P],
     "mirror_reparam_bwd": [_P, _P, _P, _I64, _P, _P, _P],

@@ -115,12 +115,16 @@ struct Epi {
   int res_is_bf16;
   float gamma, gamma2;
   long long ldr, r_bs1, r_bs2;
+  int res_row_div;  // residual row = output row / res_row_div (>= 1)
   float beta;
   float* o32;
   long long ldc32, c32_bs1, c32_bs2;
   bf16* o16;
   long long ldc16, c16_bs1, c16_bs2;
   int atomic;  // split-K partial: atomically add alpha*acc into o32
+  int mode;    // MIRROR_GEMM_*: fused row-softmax epilogues
+  float* stats;
+  int nparts;  // partial slots per row (two per N tile)
 };
 
 __device__ __forceinline__ void epi_store_scalar(const Epi& e, float acc, int b1, int b2, int row, int col) {
@@ -138,7 +142,7 @@ __device__ __forceinline__ void epi_store_scalar(const Epi& e, float acc, int b1
     v = hash_u01(e.drop_seed, idx) >= e.drop_p ? v * e.drop_scale : 0.f;
   }
   if (e.res) {
-    const long long off = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)row * e.ldr + col;
+    const long long off = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)(row / e.res_row_div) * e.ldr + col;
     v += e.gamma * (e.res_is_bf16 ? __bfloat162float(((const bf16*)e.res)[off]) : ((const float*)e.res)[off]);
     if (e.res2) v += e.gamma2 * __bfloat162float(e.res2[off]);
   }

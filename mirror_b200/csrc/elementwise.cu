@@ -225,27 +225,6 @@ __global__ void landmark_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restri
     reinterpret_cast<__nv_bfloat162*>(lm + ((long long)b * m + j) * C2)[c2] = __floats2bfloat162_rn(sx * inv, sy * inv);
   }
 }
-// dqkv16[b,t,c] = bf16(dqkv32[b,t,c] + (c < 2E ? dlm32[b,t/seg,c]/seg : 0))
-__global__ void dqkv_finish_kernel(const float* __restrict__ dqkv32, const float* __restrict__ dlm32,
-                                   bf16* __restrict__ dqkv16, int B, int n, int m, int seg, int E) {
-  const int C3 = 3 * E, C2 = 2 * E;
-  const long long total = (long long)B * n * (C3 / 2);
-  const float inv = 1.f / seg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = 2 * (int)(i % (C3 / 2));
-    const long long bt = i / (C3 / 2);
-    const int t = (int)(bt % n);
-    const int b = (int)(bt / n);
-    float2 v = *reinterpret_cast<const float2*>(dqkv32 + bt * C3 + c);
-    if (c < C2) {
-      const float2 l = *reinterpret_cast<const float2*>(dlm32 + ((long long)b * m + t / seg) * C2 + c);
-      v.x += l.x * inv;
-      v.y += l.y * inv;
-    }
-    *reinterpret_cast<__nv_bfloat162*>(dqkv16 + bt * C3 + c) = __floats2bfloat162_rn(v.x, v.y);
-  }
-}
-
 // out[c] += sum_r x[r, c]   (bias gradients).  Block = 32 x 8 threads over a [rows_chunk, 32-col] tile.
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, long long rows, int cols, long long ld, float* __restrict__ out,
@@ -409,15 +388,6 @@ extern "C" int mirror_landmark_fwd(const void* qkv, void* lm, int32_t B, int32_t
   MB_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int mirror_dqkv_finish(const float* dqkv32, const float* dlm32, void* dqkv16, int32_t B, int32_t n, int32_t m,
-                                  int32_t seg, int32_t E, mirror_stream_t stream) {
-  MB_CHECK_ARG(dqkv32 && dlm32 && dqkv16 && B > 0 && n == m * seg && E % 2 == 0, "dqkv_finish: bad args");
-  dqkv_finish_kernel<<<grid_for((long long)B * n * 3 * E / 2, 256), 256, 0, STREAM>>>(
-      dqkv32, dlm32, reinterpret_cast<bf16*>(dqkv16), B, n, m, seg, E);
-  MB_LAUNCH_CHECK();
-  return 0;
-}
-
 extern "C" int mirror_colsum(const void* x, int32_t is_bf16, int64_t rows, int32_t cols, int64_t ld, float* out,
                              mirror_stream_t stream) {
   MB_CHECK_ARG(x && out && rows > 0 && cols > 0 && ld >= cols, "colsum: bad args");

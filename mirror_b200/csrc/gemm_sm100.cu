@@ -65,7 +65,7 @@ __device__ __forceinline__ void res_prefetch(const Epi& e, ResBuf& rb, int b1, i
   const int row = row0 + lane;
   if (row >= e.M) return;
   if (e.res) {
-    const long long off = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)row * e.ldr + col0;
+    const long long off = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)(row / e.res_row_div) * e.ldr + col0;
     if (e.res_is_bf16) {
       const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res) + off);
 #pragma unroll
@@ -160,7 +160,7 @@ __device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, uint32_t taddr,
     }
   }
   if (e.res2 && row_ok) {
-    const uint4* rp = reinterpret_cast<const uint4*>(e.res2 + b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)row * e.ldr + col0);
+    const uint4* rp = reinterpret_cast<const uint4*>(e.res2 + b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)(row / e.res_row_div) * e.ldr + col0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint4 u = rp[j];
@@ -205,12 +205,126 @@ __device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, uint32_t taddr,
   }
 }
 
+// Fused row-softmax epilogues (MIRROR_GEMM_ROWSTATS / SOFTMAX / ROWDOT / SOFTMAX_BWD): thread = row, this warp's BN/2
+// columns are one "part" of the row.  Logits live in the base-2 domain (x2 = alpha*log2(e)*acc) so exp is one MUFU.EX2.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, uint32_t taddr, int b1, int b2, int row0, int cbase, int lane,
+                                                      uint64_t* tfull_bar, uint32_t aphase, int part) {
+  constexpr int NCH = BN / 64;
+  const int row = row0 + lane;
+  const bool row_ok = row < e.M;
+  float2* stats = reinterpret_cast<float2*>(e.stats) + ((long long)(b2 * e.batch1 + b1) * e.M + (row_ok ? row : 0)) * e.nparts;
+  const float a2 = e.alpha * 1.4426950408889634f;
+  float M2 = 0.f, invS = 0.f, dot = 0.f;
+  if (row_ok && e.mode == MIRROR_GEMM_SOFTMAX) {  // combine the partials of pass 1 (these loads overlap the tile's MMAs)
+    float m = -INFINITY;
+    for (int i = 0; i < e.nparts; ++i) m = fmaxf(m, stats[i].x);
+    float ssum = 0.f;
+    for (int i = 0; i < e.nparts; ++i) {
+      const float2 t = stats[i];
+      ssum += t.y * exp2f(t.x - m);
+    }
+    M2 = m;
+    invS = 1.f / ssum;
+  } else if (row_ok && e.mode == MIRROR_GEMM_SOFTMAX_BWD) {
+    for (int i = 0; i < e.nparts; ++i) dot += stats[i].x;
+  }
+  mbar_wait(tfull_bar, aphase);
+  tc_fence_after();
+  if (row0 >= e.M) return;
+  const bf16* prow = reinterpret_cast<const bf16*>(e.res) + b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)(row_ok ? row : 0) * e.ldr;
+  const int rowA = row0 + (lane & ~1);
+  const bool okA = rowA < e.M, okB = rowA + 1 < e.M;
+  float run_m = -INFINITY, run_s = 0.f, run_dot = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col0 = cbase + c * 32;
+    if (col0 >= e.N) continue;  // warp-uniform; N % 32 == 0, so a chunk is either complete or absent
+    uint32_t acc[32];
+    tmem_ld_32x32(taddr + c * 32, acc);
+    tmem_ld_wait();
+    float v[32];
+    if (e.mode == MIRROR_GEMM_ROWSTATS) {
+      float cm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = a2 * __uint_as_float(acc[j]);
+        cm = fmaxf(cm, v[j]);
+      }
+      if (cm > run_m) {
+        run_s *= exp2f(run_m - cm);
+        run_m = cm;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) run_s += exp2f(v[j] - run_m);
+      continue;
+    }
+    if (e.mode == MIRROR_GEMM_SOFTMAX) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = exp2f(a2 * __uint_as_float(acc[j]) - M2) * invS;
+    } else {  // ROWDOT / SOFTMAX_BWD read the probabilities
+      uint4 pu[4];
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pu[j] = reinterpret_cast<const uint4*>(prow + col0)[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pu[j] = make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pu[j]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __bfloat1622float2(h[t]);
+          v[j * 8 + 2 * t] = f.x;
+          v[j * 8 + 2 * t + 1] = f.y;
+        }
+      }
+      if (e.mode == MIRROR_GEMM_ROWDOT) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) run_dot += v[j] * __uint_as_float(acc[j]);
+        continue;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = e.alpha * v[j] * (__uint_as_float(acc[j]) - dot);
+    }
+    if (e.o32) {
+      uint4 pc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        pc[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+      store_rows_paired<8>(pc, reinterpret_cast<char*>(e.o32 + b2 * e.c32_bs2 + b1 * e.c32_bs1 + col0 + (long long)rowA * e.ldc32),
+                           e.ldc32 * 4, okA, okB, lane);
+    }
+    if (e.o16) {
+      uint4 pc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pc[j]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j * 8 + 2 * t], v[j * 8 + 2 * t + 1]);
+      }
+      store_rows_paired<4>(pc, reinterpret_cast<char*>(e.o16 + b2 * e.c16_bs2 + b1 * e.c16_bs1 + col0 + (long long)rowA * e.ldc16),
+                           e.ldc16 * 2, okA, okB, lane);
+    }
+  }
+  if (row_ok) {
+    if (e.mode == MIRROR_GEMM_ROWSTATS) stats[part] = make_float2(run_m, run_s);
+    else if (e.mode == MIRROR_GEMM_ROWDOT) stats[part] = make_float2(run_dot, 0.f);
+  }
+}
+
 // One epilogue warp's share of a finished tile: the 32 rows of its TMEM lane quarter (first row row0) x BN/2 columns
 // starting at cbase.  `stage`: this warp's 4 KB shared transpose tile (transposed mapping only).
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t taddr, uint32_t stage, int b1, int b2, int row0,
-                                              int cbase, int lane, uint64_t* tfull_bar, uint32_t aphase) {
+                                              int cbase, int lane, uint64_t* tfull_bar, uint32_t aphase, int part) {
   constexpr int NCH = BN / 64;  // 32-column chunks per thread
+  if (e.mode != MIRROR_GEMM_NORMAL) {
+    epilogue_tile_softmax<BN>(e, taddr, b1, b2, row0, cbase, lane, tfull_bar, aphase, part);
+    return;
+  }
   const bool rows_ok = row0 < e.M;  // warp-uniform
   ResBuf rb0, rb1;
   if (fast && rows_ok) {  // start the residual loads of the first two chunks while the MMAs of this tile still run
@@ -374,7 +488,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), epi_stage + (warp - 2) * 4096, b1,
-                        b2, row0, cbase, lane, &tfull[as], aphase);
+                        b2, row0, cbase, lane, &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -551,7 +665,7 @@ gemm_tcgen05_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), epi_stage + (warp - 2) * 4096, b1,
-                        b2, row0, cbase, lane, &tfull[as], aphase);
+                        b2, row0, cbase, lane, &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -719,7 +833,7 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), epi_stage + (warp - 2) * 4096, b1,
-                        b2, row0, cbase, lane, &tfull[as], aphase);
+                        b2, row0, cbase, lane, &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -833,7 +947,7 @@ int fill_epi(const mirror_gemm_args* g, Epi* e) {
   MB_CHECK_ARG(g && g->a && g->b, "gemm: null operand");
   MB_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0 && g->batch1 > 0 && g->batch2 > 0, "gemm: bad shape M=%d N=%d K=%d", g->M,
                g->N, g->K);
-  MB_CHECK_ARG(g->out_f32 || g->out_bf16, "gemm: no output");
+  MB_CHECK_ARG(g->out_f32 || g->out_bf16 || g->mode == MIRROR_GEMM_ROWSTATS || g->mode == MIRROR_GEMM_ROWDOT, "gemm: no output");
   MB_CHECK_ARG(g->beta == 0.f || g->out_f32, "gemm: beta needs out_f32");
   MB_CHECK_ARG(g->drop_p >= 0.f && g->drop_p < 1.f, "gemm: drop_p out of range");
   MB_CHECK_ARG(g->split_k <= 1 || (g->out_f32 && !g->out_bf16 && !g->bias && !g->res && !g->res2 && g->act == 0 && g->drop_p == 0.f && g->diag == 0.f),
@@ -843,6 +957,15 @@ int fill_epi(const mirror_gemm_args* g, Epi* e) {
   e->drop_p = g->drop_p; e->drop_scale = 1.f / (1.f - g->drop_p); e->drop_seed = g->drop_seed;
   e->res = g->res; e->res_is_bf16 = g->res_is_bf16; e->gamma = g->gamma;
   e->res2 = reinterpret_cast<const bf16*>(g->res2); e->gamma2 = g->gamma2;
+  e->res_row_div = g->res_row_div > 1 ? g->res_row_div : 1;
+  e->mode = g->mode; e->stats = g->stats; e->nparts = 0;
+  if (g->mode != MIRROR_GEMM_NORMAL) {
+    MB_CHECK_ARG(g->mode >= 1 && g->mode <= 4 && g->stats && g->N % 32 == 0 && g->split_k <= 1 && g->res_row_div <= 1,
+                 "gemm: softmax modes need stats, N %% 32 == 0 and no split-K");
+    MB_CHECK_ARG((g->mode != MIRROR_GEMM_ROWDOT && g->mode != MIRROR_GEMM_SOFTMAX_BWD) || (g->res && g->res_is_bf16),
+                 "gemm: ROWDOT / SOFTMAX_BWD read the bf16 probabilities through `res`");
+    MB_CHECK_ARG(g->mode == MIRROR_GEMM_ROWSTATS || g->mode == MIRROR_GEMM_ROWDOT || g->out_f32 || g->out_bf16, "gemm: no output");
+  }
   MB_CHECK_ARG(!g->res2 || g->res, "gemm: res2 needs res (it shares its strides)");
   e->ldr = g->ldr; e->r_bs1 = g->r_bs1; e->r_bs2 = g->r_bs2;
   e->beta = g->beta;
@@ -894,6 +1017,13 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restr
 
 using namespace mb;
 
+static int tile_n_for(int N) { return (N % 256 == 0 || N >= 1024) ? 256 : (N % 192 == 0 ? 192 : 128); }
+
+extern "C" int mirror_gemm_nparts(int32_t N) {
+  const int bn = tile_n_for(N);
+  return 2 * ((N + bn - 1) / bn);
+}
+
 extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   KParams p;
@@ -909,7 +1039,7 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
     return v && v[0] && v[0] != '0';
   }();
   const int mt = (g->M + BM - 1) / BM;
-  if (mt >= 2 && cluster_enabled) {
+  if (mt >= 2 && cluster_enabled && g->mode == MIRROR_GEMM_NORMAL) {
     const int CL = (mt == 3) ? 3 : 2;
     const int BNc = (CL == 3) ? ((g->N % 192 == 0 || g->N > 128) ? 192 : 0)
                               : ((g->N % 256 == 0 || g->N >= 1024) ? 256 : 128);
@@ -947,12 +1077,13 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
     }
   }
   // N tile: 256 when it divides N (or N is large), 192 for N = 384-like sizes (the Nystrom landmark matrices), else 128.
-  const int BN = (g->N % 256 == 0 || g->N >= 1024) ? 256 : (g->N % 192 == 0 ? 192 : 128);
+  const int BN = tile_n_for(g->N);
   p.K = g->K;
   p.batch1 = g->batch1;
   p.batch2 = g->batch2;
   p.tiles_m = (g->M + BM - 1) / BM;
   p.tiles_n = (g->N + BN - 1) / BN;
+  p.e.nparts = 2 * p.tiles_n;
   p.split_k = g->split_k > 1 ? g->split_k : 1;
   // a batch stride of 0 broadcasts that operand (e.g. one weight matrix for every slide)
   p.a_b1 = (g->batch1 > 1 && g->a_bs1 == 0) ? 0 : 1;
@@ -989,7 +1120,7 @@ extern "C" int mirror_gemm_bf16_multi(const mirror_gemm_args* terms, int32_t nte
   KParams p;
   int rc = fill_epi(g, &p.e);
   if (rc) return rc;
-  MB_CHECK_ARG(g->split_k <= 1, "gemm_multi: split_k is not supported");
+  MB_CHECK_ARG(g->split_k <= 1 && g->mode == MIRROR_GEMM_NORMAL, "gemm_multi: split_k / softmax modes are not supported");
   const int BN = (g->N % 256 == 0 || g->N >= 1024) ? 256 : (g->N % 192 == 0 ? 192 : 128);
   p.K = g->K;
   p.batch1 = g->batch1;

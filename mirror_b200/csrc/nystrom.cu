@@ -14,13 +14,13 @@ constexpr int TAPS = 33;
 // tokens: the TT+32 inputs of the strip are loaded once into registers and reused by all 33 taps (3 loads per
 // output pair instead of 33), threads of a warp cover 64 consecutive channels (128-byte coalesced rows).
 //   FWD: out16[b,t,c] = sum_j w[h(c),j] * v[b,t+j-16,c]      (v = value slot of qkv [B,n,3E], column 2E+c)
-//   BWD: dst32[b,t,2E+c] += sum_j w[h(c),j] * dout[b,t-j+16,c]   (data gradient, accumulated into dqkv32)
+//   BWD: dv16[b,t,c]   = sum_j w[h(c),j] * dout[b,t-j+16,c]        (data gradient: the same FIR with flipped taps)
 constexpr int TT = 16;
 
 template <bool BWD>
 __global__ void __launch_bounds__(128)
 res_conv_kernel(const bf16* __restrict__ src, long long src_ld, int src_col0, const float* __restrict__ w, int n, int E, int d,
-                bf16* __restrict__ dst16, float* __restrict__ dst32, long long dst_ld, int dst_col0) {
+                bf16* __restrict__ dst16, long long dst_ld, int dst_col0) {
   __shared__ float sw[8 * TAPS];
   for (int i = threadIdx.x; i < 8 * TAPS; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -53,15 +53,7 @@ res_conv_kernel(const bf16* __restrict__ src, long long src_ld, int src_col0, co
   for (int i = 0; i < TT; ++i) {
     const int t = t0 + i;
     if (t >= n) break;
-    if (BWD) {
-      float2* p = reinterpret_cast<float2*>(dst32 + (b * n + t) * dst_ld + dst_col0 + c);
-      float2 o = *p;
-      o.x += acc[i].x;
-      o.y += acc[i].y;
-      *p = o;
-    } else {
-      *reinterpret_cast<__nv_bfloat162*>(dst16 + (b * n + t) * dst_ld + dst_col0 + c) = __floats2bfloat162_rn(acc[i].x, acc[i].y);
-    }
+    *reinterpret_cast<__nv_bfloat162*>(dst16 + (b * n + t) * dst_ld + dst_col0 + c) = __floats2bfloat162_rn(acc[i].x, acc[i].y);
   }
 }
 
@@ -228,16 +220,16 @@ extern "C" int mirror_res_conv_fwd(const void* qkv, const float* w, int32_t B, i
   MB_CHECK_ARG(qkv && w && out_bf16 && B > 0 && n > 0 && E % 16 == 0, "res_conv_fwd: bad args");
   dim3 grid((E / 2 + 127) / 128, (n + TT - 1) / TT, B);
   res_conv_kernel<false><<<grid, 128, 0, STREAM>>>(reinterpret_cast<const bf16*>(qkv), 3LL * E, 2 * E, w, n, E, E / 8,
-                                                  reinterpret_cast<bf16*>(out_bf16), nullptr, E, 0);
+                                                  reinterpret_cast<bf16*>(out_bf16), E, 0);
   MB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int mirror_res_conv_bwd(const void* dout_bf16, const void* qkv, const float* w, int32_t B, int32_t n, int32_t E,
-                                   float* dqkv32, float* dw, mirror_stream_t stream) {
-  MB_CHECK_ARG(dout_bf16 && qkv && w && dqkv32 && dw && B > 0 && n > 0 && E % 16 == 0, "res_conv_bwd: bad args");
+                                   void* dv_bf16, float* dw, mirror_stream_t stream) {
+  MB_CHECK_ARG(dout_bf16 && qkv && w && dv_bf16 && dw && B > 0 && n > 0 && E % 16 == 0, "res_conv_bwd: bad args");
   dim3 grid((E / 2 + 127) / 128, (n + TT - 1) / TT, B);
-  res_conv_kernel<true><<<grid, 128, 0, STREAM>>>(reinterpret_cast<const bf16*>(dout_bf16), E, 0, w, n, E, E / 8, nullptr, dqkv32,
-                                                 3LL * E, 2 * E);
+  res_conv_kernel<true><<<grid, 128, 0, STREAM>>>(reinterpret_cast<const bf16*>(dout_bf16), E, 0, w, n, E, E / 8,
+                                                 reinterpret_cast<bf16*>(dv_bf16), E, 0);
   MB_LAUNCH_CHECK();
   const int strips = (n + TT - 1) / TT;
   int chunks = (2 * num_sms() + 3 * B - 1) / (3 * B);  // ~2 waves of CTAs in total

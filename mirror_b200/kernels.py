@@ -66,18 +66,36 @@ def _operands(g, a, b):
     return B2, B1, M, N
 
 
+GEMM_NORMAL, GEMM_ROWSTATS, GEMM_SOFTMAX, GEMM_ROWDOT, GEMM_SOFTMAX_BWD = range(5)
+
+
+def gemm_nparts(n):
+    """Partial-statistics slots per row of an N-column product (two per N tile of the tcgen05 kernel)."""
+    if _TEST_BACKEND is not None:
+        return _TEST_BACKEND.gemm_nparts(n)
+    return int(_lib.fn("mirror_gemm_nparts")(n))
+
+
+def softmax_stats(batch_shape, m, n, device):
+    """Scratch for the two-pass fused softmax GEMMs: [*batch, M, nparts, 2] f32."""
+    return torch.empty(*batch_shape, m, gemm_nparts(n), 2, dtype=torch.float32, device=device)
+
+
 def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NONE, drop_p=0.0, drop_seed=0,
-         res=None, gamma=1.0, beta=0.0, split_k=1, diag=0.0, more=None, res2=None, gamma2=1.0, simt=False):
+         res=None, gamma=1.0, beta=0.0, split_k=1, diag=0.0, more=None, res2=None, gamma2=1.0, res_row_div=1, mode=GEMM_NORMAL,
+         stats=None, simt=False):
     """C[..,M,N] = epilogue(A[..,M,K] @ B[..,N,K]^T [+ sum of A_t @ B_t^T for (A_t, B_t) in `more`]); see mirror_gemm_args.
 
     ``a`` / ``b`` are bf16 views whose last two dims are (M,K) / (N,K); either of the two may carry the unit stride, so
     ``x.transpose(-1,-2)`` views give the NN / TN forms without copies.  Up to two leading batch dims.  ``more``: up to
     five further operand pairs with the same M, N and batch dims, accumulated into the same tile (one epilogue pass).
+    ``mode`` / ``stats``: fused row-softmax epilogues (GEMM_ROWSTATS .. GEMM_SOFTMAX_BWD), stats = softmax_stats(...).
     """
     if _TEST_BACKEND is not None:
         return _TEST_BACKEND.gemm(a, b, out_f32=out_f32, out_bf16=out_bf16, alpha=alpha, bias=bias, act=act,
                                   drop_p=drop_p, drop_seed=drop_seed, res=res, gamma=gamma, beta=beta, split_k=split_k,
-                                  diag=diag, more=more, res2=res2, gamma2=gamma2)
+                                  diag=diag, more=more, res2=res2, gamma2=gamma2, res_row_div=res_row_div, mode=mode,
+                                  stats=stats)
     nterms = 1 + (len(more) if more else 0)
     terms = (_lib.GemmArgs * nterms)()
     g = terms[0]
@@ -90,8 +108,9 @@ def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NON
     g.act, g.drop_p, g.drop_seed = act, drop_p, drop_seed
     if res is not None:
         r4 = _as4(_cuda(res))
-        if r4.shape != (B2, B1, M, N) or r4.stride(-1) != 1:
-            raise ValueError("gemm residual must be [..,M,N] with unit column stride")
+        if r4.shape != (B2, B1, (M + res_row_div - 1) // res_row_div, N) or r4.stride(-1) != 1:
+            raise ValueError("gemm residual must be [..,ceil(M/res_row_div),N] with unit column stride")
+        g.res_row_div = res_row_div
         g.res, g.res_is_bf16 = r4.data_ptr(), int(r4.dtype == torch.bfloat16)
         if r4.dtype not in (torch.bfloat16, torch.float32):
             raise TypeError("residual must be bf16 or f32")
@@ -104,6 +123,11 @@ def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NON
     elif res2 is not None:
         raise ValueError("gemm res2 needs res")
     g.gamma, g.beta, g.split_k, g.diag = gamma, beta, split_k, diag
+    if mode != GEMM_NORMAL:
+        _cuda(stats, torch.float32)
+        if tuple(stats.shape) != (*a.shape[:-2], M, gemm_nparts(N), 2) or not stats.is_contiguous():
+            raise ValueError("gemm: stats must come from softmax_stats() for this product")
+        g.mode, g.stats = mode, stats.data_ptr()
     for o, dt, name in ((out_f32, torch.float32, "32"), (out_bf16, torch.bfloat16, "16")):
         if o is None:
             continue
@@ -282,15 +306,6 @@ def landmark_fwd(qkv, m, seg):
 
 
 @_op
-def dqkv_finish(dqkv32, dlm32, seg):
-    B, n, E3 = dqkv32.shape
-    m = dlm32.shape[1]
-    out = torch.empty(B, n, E3, device=dqkv32.device, dtype=BF16)
-    _call("mirror_dqkv_finish", _p(_contig(dqkv32), F32), _p(_contig(dlm32), F32), _p(out), B, n, m, seg, E3 // 3)
-    return out
-
-
-@_op
 def colsum_(x, out):
     """out[c] += sum_r x[r,c]; x is a 2-D view with unit column stride (bf16 or f32)."""
     rows, cols = x.shape
@@ -381,10 +396,13 @@ def res_conv_fwd(qkv, w):
 
 
 @_op
-def res_conv_bwd_(dout16, qkv, w, dqkv32, dw):
+def res_conv_bwd(dout16, qkv, w, dw):
+    """-> dv16 [B,n,E] = conv^T(dout) (gradient w.r.t. the value slot); dw [8,33] is accumulated."""
     B, n, E3 = qkv.shape
+    dv = torch.empty(B, n, E3 // 3, device=qkv.device, dtype=BF16)
     _call("mirror_res_conv_bwd", _p(_contig(dout16), BF16), _p(_contig(qkv), BF16), _p(_contig(w), F32), B, n, E3 // 3,
-          _p(_contig(dqkv32), F32), _p(_contig(dw), F32), launches=2)
+          _p(dv), _p(_contig(dw), F32), launches=2)
+    return dv
 
 
 @_op

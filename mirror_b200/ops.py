@@ -317,6 +317,37 @@ def _heads(t, col0, E, h=WSI_HEADS):
     return t[:, :, col0:col0 + E].unflatten(-1, (h, E // h)).permute(0, 2, 1, 3)
 
 
+def _softmax_gemm(a, b, rows, cols, alpha, want_f32=False):
+    """softmax_rows(alpha * a @ b^T) -> (bf16, f32 | None) without the logits touching HBM: two GEMM passes over the
+    (K = head_dim) product, row statistics then normalised probabilities (MIRROR_GEMM_ROWSTATS / SOFTMAX)."""
+    batch, dev = a.shape[:-2], a.device
+    if cols % 32:  # unfused: fp32 logits + row softmax kernel
+        s_ = torch.empty(*batch, rows, cols, device=dev, dtype=F32)
+        K.gemm(a, b, out_f32=s_, alpha=alpha)
+        return K.softmax_fwd(s_, want_f32=want_f32)
+    st = K.softmax_stats(batch, rows, cols, dev)
+    K.gemm(a, b, alpha=alpha, mode=K.GEMM_ROWSTATS, stats=st)
+    p16 = torch.empty(*batch, rows, cols, device=dev, dtype=BF16)
+    p32 = torch.empty(*batch, rows, cols, device=dev, dtype=F32) if want_f32 else None
+    K.gemm(a, b, alpha=alpha, mode=K.GEMM_SOFTMAX, stats=st, out_bf16=p16, out_f32=p32)
+    return p16, p32
+
+
+def _softmax_bwd_gemm(a, b, p16, alpha):
+    """d logits = alpha * P * (G - rowsum(G * P)) with G = a @ b^T never materialised (MIRROR_GEMM_ROWDOT / SOFTMAX_BWD)."""
+    batch, dev = a.shape[:-2], a.device
+    rows, cols = p16.shape[-2:]
+    if cols % 32:
+        g = torch.empty(*batch, rows, cols, device=dev, dtype=F32)
+        K.gemm(a, b, out_f32=g)
+        return K.softmax_bwd(p16, g, alpha)[0]
+    st = K.softmax_stats(batch, rows, cols, dev)
+    K.gemm(a, b, mode=K.GEMM_ROWDOT, stats=st, res=p16)
+    ds = torch.empty_like(p16)
+    K.gemm(a, b, alpha=alpha, mode=K.GEMM_SOFTMAX_BWD, stats=st, res=p16, out_bf16=ds)
+    return ds
+
+
 class NystromLayerFn(Function):
     """TransLayer: x + NystromAttention(LayerNorm(x)) (models/mirror.py:295-314; nystrom_attention forward).
 
@@ -345,18 +376,9 @@ class NystromLayerFn(Function):
         lm = K.landmark_fwd(qkv, m, seg)
         q, k, v = _heads(qkv, 0, E), _heads(qkv, E, E), _heads(qkv, 2 * E, E)
         ql, kl = _heads(lm, 0, E), _heads(lm, E, E)
-        s1 = torch.empty(B, hd, n, m, device=dev, dtype=F32)
-        K.gemm(q, kl, out_f32=s1, alpha=scale)
-        a1, _ = K.softmax_fwd(s1)
-        del s1
-        s2 = torch.empty(B, hd, m, m, device=dev, dtype=F32)
-        K.gemm(ql, kl, out_f32=s2, alpha=scale)
-        a2_16, a2_32 = K.softmax_fwd(s2, want_f32=True)
-        del s2
-        s3 = torch.empty(B, hd, m, n, device=dev, dtype=F32)
-        K.gemm(ql, k, out_f32=s3, alpha=scale)
-        a3, _ = K.softmax_fwd(s3)
-        del s3
+        a1, _ = _softmax_gemm(q, kl, n, m, scale)
+        a2_16, a2_32 = _softmax_gemm(ql, kl, m, m, scale, want_f32=True)
+        a3, _ = _softmax_gemm(ql, k, m, n, scale)
         z32, z16, scratch = K.pinv_init(a2_32)
         z0_32 = z32
         iters = []
@@ -371,11 +393,10 @@ class NystromLayerFn(Function):
             K.gemm(Em, _T(Em), out_bf16=G1, alpha=0.25, res=Em)                    # G1 = E + 0.25 E E
             Fm = torch.empty(mm, device=dev, dtype=BF16)
             K.gemm(Em, _T(G1), out_bf16=Fm, res=Em)                                # F  = E + E G1
-            zn32 = torch.empty(mm, device=dev, dtype=F32)
             zn16 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(z16, _T(Fm), out_f32=zn32, out_bf16=zn16, res=z32)              # z'  = z + z F
-            iters += [z16, Em, G1, Fm]
-            z32, z16 = zn32, zn16
+            K.gemm(z16, _T(Fm), out_bf16=zn16, res=z16)                            # z' = z + z F  (bf16 iterate: measured
+            iters += [z16, Em, G1, Fm]                                             #  +3e-4 grad rel-L2 vs an fp32 master copy)
+            z16 = zn16
         kv = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
         K.gemm(a3, _T(v), out_bf16=kv)
         w_ = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
@@ -418,28 +439,22 @@ class NystromLayerFn(Function):
         do_h = _heads(do16, 0, E)
 
         # ---- out = a1 @ w + res_conv(v)
-        da1 = torch.empty(B, hd, n, m, device=dev, dtype=F32)
-        K.gemm(do_h, w_, out_f32=da1)
+        ds1 = _softmax_bwd_gemm(do_h, w_, a1, scale)                                   # da1 = dO w^T stays in TMEM
         dw16 = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
         K.gemm(_T(a1), _T(do_h), out_bf16=dw16)
-        ds1, _ = K.softmax_bwd(a1, da1, scale)
-        del da1
 
         # ---- w = z @ kv ; kv = a3 @ v
-        gz32 = torch.empty(mm, device=dev, dtype=F32)
         gz16 = torch.empty(mm, device=dev, dtype=BF16)
-        K.gemm(dw16, kv, out_f32=gz32, out_bf16=gz16)
+        K.gemm(dw16, kv, out_bf16=gz16)
         dkv16 = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
         K.gemm(_T(zf16), _T(dw16), out_bf16=dkv16)
-        da3 = torch.empty(B, hd, m, n, device=dev, dtype=F32)
-        K.gemm(dkv16, v, out_f32=da3)
-        dqkv32 = torch.empty(B, n, 3 * E, device=dev, dtype=F32)
-        K.gemm(_T(a3), _T(dkv16), out_f32=_heads(dqkv32, 2 * E, E))
+        ds3 = _softmax_bwd_gemm(dkv16, v, a3, scale)                                   # da3 = dkv v^T
         d_conv = torch.zeros(hd, conv_w.numel() // hd, device=dev, dtype=F32)
-        K.res_conv_bwd_(do16, qkv, conv_w.reshape(hd, -1), dqkv32, d_conv)
+        dvc = K.res_conv_bwd(do16, qkv, conv_w.reshape(hd, -1), d_conv)              # conv^T(dO), bf16 [B,n,E]
         del do16
-        ds3, _ = K.softmax_bwd(a3, da3, scale)
-        del da3
+        dqkv16 = torch.empty(B, n, 3 * E, device=dev, dtype=BF16)
+        K.gemm(_T(a3), _T(dkv16), out_bf16=_heads(dqkv16, 2 * E, E), res=_heads(dvc, 0, E))  # dv = a3^T dkv + conv^T(dO)
+        del dvc
 
         # ---- Moore-Penrose iterations, reversed.  With gEn := -g_E every sum of products is ONE multi-term GEMM:
         #   gF   = z^T g                gG1q = 0.25 E^T gF
@@ -455,9 +470,9 @@ class NystromLayerFn(Function):
             gEn = torch.empty(mm, device=dev, dtype=BF16)
             K.gemm(gF, G1, more=[(gG1q, Em), (_T(Em), _T(gG1q))], out_bf16=gEn, alpha=-1.0, res=gF, gamma=-1.0, res2=gG1q,
                    gamma2=-4.0)
-            gzn32 = torch.empty(mm, device=dev, dtype=F32)
             gzn16 = torch.empty(mm, device=dev, dtype=BF16)
-            K.gemm(gz16, Fm, more=[(_T(a2_16), _T(gEn))], out_f32=gzn32, out_bf16=gzn16, res=gz32)
+            gzn32 = torch.empty(mm, device=dev, dtype=F32) if it == 0 else None  # only d/dz0 is needed in fp32
+            K.gemm(gz16, Fm, more=[(_T(a2_16), _T(gEn))], out_f32=gzn32, out_bf16=gzn16, res=gz16)
             gens.append((gEn, z16))
             gz32, gz16 = gzn32, gzn16
         ga2 = torch.empty(mm, device=dev, dtype=F32)
@@ -467,17 +482,14 @@ class NystromLayerFn(Function):
         ds2, _ = K.softmax_bwd(a2_16, ga2, scale)
         del ga2, gz32, gz16
 
-        # ---- similarities (1/sqrt(d) already folded into ds*)
+        # ---- similarities (1/sqrt(d) already folded into ds*).  Landmark gradients first (each a two-term GEMM), then dq / dk
+        # with the landmark-mean backward fused as a row-broadcast residual: row t of q receives dql[t // seg] / seg.
         dlm32 = torch.empty(B, m, 2 * E, device=dev, dtype=F32)
-        K.gemm(ds1, _T(kl), out_f32=_heads(dqkv32, 0, E))            # dq  = ds1 kl
-        K.gemm(_T(ds1), _T(q), out_f32=_heads(dlm32, E, E))          # dkl = ds1^T q
-        K.gemm(ds2, _T(kl), out_f32=_heads(dlm32, 0, E))             # dql = ds2 kl
-        K.gemm(_T(ds2), _T(ql), out_f32=_heads(dlm32, E, E), beta=1.0)  # dkl += ds2^T ql
-        K.gemm(ds3, _T(k), out_f32=_heads(dlm32, 0, E), beta=1.0)    # dql += ds3 k
-        K.gemm(_T(ds3), _T(ql), out_f32=_heads(dqkv32, E, E))        # dk  = ds3^T ql
-        del ds1, ds2, ds3
-        dqkv16 = K.dqkv_finish(dqkv32, dlm32, seg)
-        del dqkv32, dlm32
+        K.gemm(ds2, _T(kl), more=[(ds3, _T(k))], out_f32=_heads(dlm32, 0, E))             # dql = ds2 kl + ds3 k
+        K.gemm(_T(ds1), _T(q), more=[(_T(ds2), _T(ql))], out_f32=_heads(dlm32, E, E))     # dkl = ds1^T q + ds2^T ql
+        K.gemm(ds1, _T(kl), out_bf16=_heads(dqkv16, 0, E), res=_heads(dlm32, 0, E), gamma=1.0 / seg, res_row_div=seg)      # dq
+        K.gemm(_T(ds3), _T(ql), out_bf16=_heads(dqkv16, E, E), res=_heads(dlm32, E, E), gamma=1.0 / seg, res_row_div=seg)  # dk
+        del ds1, ds2, ds3, dlm32
 
         # ---- to_qkv and LayerNorm
         dxn = torch.empty(B, n, E, device=dev, dtype=F32)

@@ -61,7 +61,7 @@ class Emu:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=0, drop_p=0.0, drop_seed=0, res=None,
-             gamma=1.0, beta=0.0, split_k=1, diag=0.0, more=None, res2=None, gamma2=1.0):
+             gamma=1.0, beta=0.0, split_k=1, diag=0.0, more=None, res2=None, gamma2=1.0, res_row_div=1, mode=0, stats=None):
         assert a.dtype == BF16 and b.dtype == BF16
         assert a.stride(-1) == 1 or a.stride(-2) == 1
         assert b.stride(-1) == 1 or b.stride(-2) == 1
@@ -75,6 +75,8 @@ class Emu:
         for (at, bt) in (more or ()):
             assert at.dtype == BF16 and bt.dtype == BF16
             acc = acc + torch.matmul(at.float(), bt.float().transpose(-1, -2))
+        if mode != 0:
+            return self._gemm_softmax(acc, mode, stats, alpha, res, out_f32, out_bf16)
         if split_k > 1:
             assert out_f32 is not None and out_bf16 is None and bias is None and res is None and act == 0 and drop_p == 0
             out_f32 += alpha * acc.view(out_f32.shape)
@@ -88,11 +90,18 @@ class Emu:
         if drop_p > 0:
             v = v * keep_mask(drop_seed, tuple(v.shape), drop_p)
         if res is not None:
-            assert res.shape == v.shape and res.stride(-1) == 1
-            v = v + gamma * res.float()
+            assert res.stride(-1) == 1
+            rr = res.float()
+            if res_row_div > 1:
+                rr = rr.repeat_interleave(res_row_div, dim=-2)[..., : v.shape[-2], :]
+            assert rr.shape == v.shape
+            v = v + gamma * rr
             if res2 is not None:
                 assert res2.dtype == BF16 and res2.shape == res.shape and res2.stride() == res.stride()
-                v = v + gamma2 * res2.float()
+                r2 = res2.float()
+                if res_row_div > 1:
+                    r2 = r2.repeat_interleave(res_row_div, dim=-2)[..., : v.shape[-2], :]
+                v = v + gamma2 * r2
         if out_f32 is not None:
             assert out_f32.shape == v.shape and out_f32.stride(-1) == 1
             if beta != 0.0:
@@ -100,6 +109,47 @@ class Emu:
             out_f32.copy_(v)
         if out_bf16 is not None:
             assert out_bf16.shape == v.shape and out_bf16.stride(-1) == 1
+            out_bf16.copy_(v.to(BF16))
+
+    def gemm_nparts(self, n):
+        bn = 256 if (n % 256 == 0 or n >= 1024) else (192 if n % 192 == 0 else 128)
+        return 2 * ((n + bn - 1) // bn)
+
+    def _gemm_softmax(self, acc, mode, stats, alpha, res, out_f32, out_bf16):
+        """Fused row-softmax epilogue modes: the partials go through `stats` split per half tile as the kernel does."""
+        n = acc.shape[-1]
+        assert n % 32 == 0 and stats.shape == (*acc.shape[:-1], self.gemm_nparts(n), 2)
+        bn = 256 if (n % 256 == 0 or n >= 1024) else (192 if n % 192 == 0 else 128)
+        hw = bn // 2
+        log2e = 1.4426950408889634
+        if mode == 1:
+            x2 = alpha * log2e * acc
+            stats[..., 0].fill_(float("-inf"))
+            stats[..., 1].zero_()
+            for p in range(stats.shape[-2]):
+                blk = x2[..., p * hw:(p + 1) * hw]
+                if blk.shape[-1] == 0:
+                    continue
+                m = blk.amax(-1)
+                stats[..., p, 0] = m
+                stats[..., p, 1] = torch.exp2(blk - m[..., None]).sum(-1)
+            return
+        if mode == 3:
+            stats.zero_()
+            prod = acc * res.float()
+            for p in range(stats.shape[-2]):
+                stats[..., p, 0] = prod[..., p * hw:(p + 1) * hw].sum(-1)
+            return
+        if mode == 2:
+            m = stats[..., 0].amax(-1)
+            ssum = (stats[..., 1] * torch.exp2(stats[..., 0] - m[..., None])).sum(-1)
+            v = torch.exp2(alpha * log2e * acc - m[..., None]) / ssum[..., None]
+        else:
+            assert mode == 4 and res.dtype == BF16
+            v = alpha * res.float() * (acc - stats[..., 0].sum(-1)[..., None])
+        if out_f32 is not None:
+            out_f32.copy_(v)
+        if out_bf16 is not None:
             out_bf16.copy_(v.to(BF16))
 
     # ------------------------------------------------------------ elementwise
@@ -190,13 +240,6 @@ class Emu:
         E = E3 // 3
         return qkv[:, :, :2 * E].float().view(B, m, seg, 2 * E).sum(2).div(seg).to(BF16)
 
-    def dqkv_finish(self, dqkv32, dlm32, seg):
-        B, n, E3 = dqkv32.shape
-        E = E3 // 3
-        out = dqkv32.clone()
-        out[:, :, :2 * E] += dlm32.repeat_interleave(seg, dim=1) / seg
-        return out.to(BF16)
-
     def colsum_(self, x, out):
         out += x.float().sum(0)
         return out
@@ -257,7 +300,7 @@ class Emu:
         return o.permute(0, 2, 1, 3).reshape(B, n, E).to(BF16)
 
     @torch.enable_grad()
-    def res_conv_bwd_(self, dout16, qkv, w, dqkv32, dw):
+    def res_conv_bwd(self, dout16, qkv, w, dw):
         B, n, E3 = qkv.shape
         E = E3 // 3
         h = w.shape[0]
@@ -266,8 +309,8 @@ class Emu:
         o = F.conv2d(v, ww, padding=(w.shape[1] // 2, 0), groups=h)
         go = dout16.float().view(B, n, h, E // h).permute(0, 2, 1, 3)
         gv, gw = torch.autograd.grad(o, (v, ww), go)
-        dqkv32[:, :, 2 * E:] += gv.permute(0, 2, 1, 3).reshape(B, n, E)
         dw += gw.view(h, -1)
+        return gv.permute(0, 2, 1, 3).reshape(B, n, E).to(BF16)
 
     def pinv_init(self, a2):
         ax = a2.abs()

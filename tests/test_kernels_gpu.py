@@ -140,11 +140,22 @@ def test_mask_pos(first, E, tok_stride):
          check_args=(0, 2, 4))
 
 
-def test_landmark_and_dqkv_finish():
+def test_landmark():
     B, m, seg, E = 2, 24, 3, 48
     qkv = rn(B, m * seg, 3 * E).to(BF16)
     both("landmark_fwd", (qkv, m, seg), tol=8e-3)
-    both("dqkv_finish", (rn(B, m * seg, 3 * E, seed=1), rn(B, m, 2 * E, seed=2), seg), tol=8e-3)
+
+
+def test_gemm_row_broadcast_residual():
+    # dq = ds1 @ kl + dql[t // seg] / seg  (landmark-mean backward fused into the GEMM epilogue)
+    Bt, n, m, d, seg = 2, 288, 96, 64, 3
+    a, b = rn(Bt, n, m, seed=1).to(BF16), rn(Bt, d, m, seed=2).to(BF16)
+    r = rn(Bt, m, d, seed=3)
+    o_cpu = torch.zeros(Bt, n, d, dtype=BF16)
+    EMU.gemm(a, b, out_bf16=o_cpu, res=r, gamma=1.0 / seg, res_row_div=seg)
+    o = torch.zeros(Bt, n, d, device="cuda", dtype=BF16)
+    K.gemm(a.cuda(), b.cuda(), out_bf16=o, res=r.cuda(), gamma=1.0 / seg, res_row_div=seg)
+    close(o, o_cpu, 8e-3, "row-broadcast residual")
 
 
 def test_colsum():
@@ -193,7 +204,7 @@ def test_res_conv(B, n, E):
     w = rn(8, 33, scale=0.2)
     both("res_conv_fwd", (qkv, w), tol=8e-3)
     dout = rn(B, n, E, seed=1).to(BF16)
-    both("res_conv_bwd_", (dout, qkv, w, rn(B, n, 3 * E, seed=2), torch.zeros(8, 33)), tol=2e-4, check_args=(3, 4))
+    both("res_conv_bwd", (dout, qkv, w, torch.zeros(8, 33)), tol=2e-4, check_args=(3,))
 
 
 def test_pinv_init_and_bwd():
@@ -309,3 +320,38 @@ def test_gemm_multi_term_mixed_layouts_and_second_residual():
     o = torch.zeros(2, 200, 136, device="cuda")
     K.gemm(pd[0][0], pd[0][1], more=pd[1:], out_f32=o)
     close(o, o_cpu, 2e-5, "six-term")
+
+
+@pytest.mark.parametrize("rows,cols,kd", [(300, 96, 24), (384, 384, 96), (96, 608, 96), (130, 2048, 64), (2048, 384, 96)])
+def test_gemm_fused_softmax_fwd_bwd(rows, cols, kd):
+    # softmax(alpha q k^T) and its backward as GEMM epilogue modes, checked against an fp32 softmax of the same product
+    Bt, hd, alpha = 2, 3, kd ** -0.5
+    a, b = (3 * rn(Bt, hd, rows, kd, seed=1)).to(BF16), rn(Bt, hd, cols, kd, seed=2).to(BF16)
+    logits = alpha * a.float() @ b.float().transpose(-1, -2)
+    p_ref = torch.softmax(logits, -1)
+    ad, bd = a.cuda(), b.cuda()
+    st = K.softmax_stats((Bt, hd), rows, cols, "cuda")
+    assert st.shape[-2] == K.gemm_nparts(cols)
+    K.gemm(ad, bd, alpha=alpha, mode=K.GEMM_ROWSTATS, stats=st)
+    p16 = torch.zeros(Bt, hd, rows, cols, device="cuda", dtype=BF16)
+    p32 = torch.zeros(Bt, hd, rows, cols, device="cuda")
+    K.gemm(ad, bd, alpha=alpha, mode=K.GEMM_SOFTMAX, stats=st, out_bf16=p16, out_f32=p32)
+    assert (p32.cpu() - p_ref).abs().max() <= 2e-6 + 1e-5 * p_ref.abs().max()
+    close(p16, p_ref, 6e-3, "softmax bf16")
+    assert (p32.sum(-1) - 1).abs().max() < 1e-5
+    # backward: G = ga gb^T, ds = alpha * P * (G - rowsum(G P)) with P the stored bf16 probabilities
+    ga, gb = rn(Bt, hd, rows, 40, seed=3).to(BF16), rn(Bt, hd, cols, 40, seed=4).to(BF16)
+    G = ga.float() @ gb.float().transpose(-1, -2)
+    P = p16.cpu().float()
+    ds_ref = alpha * P * (G - (G * P).sum(-1, keepdim=True))
+    st2 = K.softmax_stats((Bt, hd), rows, cols, "cuda")
+    K.gemm(ga.cuda(), gb.cuda(), mode=K.GEMM_ROWDOT, stats=st2, res=p16)
+    ds = torch.zeros(Bt, hd, rows, cols, device="cuda", dtype=BF16)
+    K.gemm(ga.cuda(), gb.cuda(), alpha=alpha, mode=K.GEMM_SOFTMAX_BWD, stats=st2, res=p16, out_bf16=ds)
+    close(ds, ds_ref, 6e-3, "softmax bwd")
+    # and the emulation used by the CPU suite follows the same contract
+    st_c = torch.zeros(Bt, hd, rows, K.gemm_nparts(cols), 2)
+    EMU.gemm(a, b, alpha=alpha, mode=1, stats=st_c)
+    p_c = torch.zeros(Bt, hd, rows, cols)
+    EMU.gemm(a, b, alpha=alpha, mode=2, stats=st_c, out_f32=p_c)
+    assert (p_c - p_ref).abs().max() < 1e-5
