@@ -47,7 +47,14 @@ inline int num_sms() {
 
 // ---- stateless counter-based uniform in [0,1): keep-mask of the fused dropout.  32-bit "lowbias32" finaliser over the
 // element index mixed with the 64-bit seed: ~10 integer ops per element (the epilogues evaluate it for every output).
-__host__ __device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t idx) {
+__host__ // 2^x as ONE MUFU.EX2 (flush-to-zero; exp2f without .ftz costs a range check and two extra multiplies per element)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t idx) {
   uint32_t h = (uint32_t)idx + (uint32_t)seed * 0x9E3779B1u + (uint32_t)(idx >> 32) * 0x85EBCA77u;
   h ^= (uint32_t)(seed >> 32);
   h ^= h >> 16;

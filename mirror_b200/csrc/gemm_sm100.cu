@@ -27,13 +27,17 @@ struct KParams {
   int a_b1, a_b2, b_b1, b_b2;  // 0 where an operand is broadcast along that batch dim (batch stride 0), else 1
 };
 
-template <int BN>
+constexpr int kSinkBytes = 6144;  // per epilogue warp: one 32x32 f32 box (4 KB, 128B swizzle) + one bf16 box (2 KB, 64B swizzle)
+
+// TMAS: the epilogue hands finished 32x32 chunks to TMA (bulk tensor stores out of a per-warp staging box) instead of
+// storing from registers; one pipeline stage is traded for the staging boxes.
+template <int BN, bool TMAS = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = 0;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int EPI_BYTES = TMAS ? kEpiWarps * kSinkBytes : 0;
+  static constexpr int STAGES = ((BN == 256) ? 4 : (BN == 192 ? 5 : 6)) - (TMAS ? 1 : 0);
   static constexpr int TMEM_COLS = (kAccStages * BN <= 256) ? 256 : 512;  // power of two >= 2 accumulator stages
   static constexpr int BAR_BYTES = (2 * STAGES + 2 * kAccStages) * 8 + 16;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
@@ -50,8 +54,10 @@ struct ResBuf {
 };
 
 // slow path (ragged N tail, unaligned views, split-K atomics, GELU).  Out of line, and it re-reads TMEM itself so that
-// the hot path never has to keep the accumulator chunk addressable (= spilled to local memory).
-__device__ __noinline__ void epilogue_chunk_scalar(const Epi& e, uint32_t taddr, int b1, int b2, int row, int col0) {
+// the hot path never has to keep the accumulator chunk addressable (= spilled to local memory).  Epi travels BY VALUE: a
+// reference would let the address of the kernel parameter escape, and then every e.field of the hot path becomes a generic
+// LD.E (re-issued after each asm volatile) instead of a constant-bank operand -- measured: long-scoreboard stalls all over.
+__device__ __noinline__ void epilogue_chunk_scalar(const Epi e, uint32_t taddr, int b1, int b2, int row, int col0) {
   uint32_t acc[32];
   tmem_ld_32x32(taddr, acc);
   tmem_ld_wait();
@@ -82,6 +88,52 @@ __device__ __forceinline__ void res_prefetch(const Epi& e, ResBuf& rb, int b1, i
   }
 }
 
+// Where finished chunks go.  tma = 0: straight from registers (store_rows_paired).  tma = 1: through this warp's staging
+// boxes and a bulk tensor store -- the warp only pays conflict-free st.shared, the TMA unit writes whole lines
+// asynchronously, and row/column tails are clipped by the tensor map.
+struct Sink {
+  const CUtensorMap* tm32;
+  const CUtensorMap* tm16;
+  uint32_t buf;  // shared address of this warp's kSinkBytes
+  int tma;
+  int flip;      // bf16-only output: alternates between two staging boxes
+};
+
+// f32 chunk: lane = row, 8 pieces of 16 B.  128B swizzle: piece j of row r lives at r*128 + ((j ^ (r & 7)) * 16).
+__device__ __forceinline__ void sink_tma_f32(Sink& s, const uint4 (&pc)[8], bool both, int b1, int b2, int row0, int col0, int lane) {
+  if (lane == 0) {
+    if (both) bulk_wait_read<1>();  // the bf16 box of the previous chunk may still be in flight
+    else bulk_wait_read<0>();
+  }
+  __syncwarp();
+  const uint32_t base = s.buf + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) st_shared_v4(base + ((j ^ (lane & 7)) << 4), pc[j]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_4d(s.tm32, s.buf, col0, row0, b1, b2);
+    bulk_commit();
+  }
+}
+
+// bf16 chunk: 4 pieces of 16 B per row.  64B swizzle: piece j of row r lives at r*64 + ((j ^ ((r >> 1) & 3)) * 16).
+__device__ __forceinline__ void sink_tma_bf16(Sink& s, const uint4 (&pc)[4], bool both, int b1, int b2, int row0, int col0, int lane) {
+  if (lane == 0) bulk_wait_read<1>();  // two boxes in rotation (or the f32 box of this chunk): one group may stay in flight
+  __syncwarp();
+  const uint32_t box = s.buf + (both ? 4096 : (s.flip ? 2048 : 0));
+  s.flip ^= 1;
+  const uint32_t base = box + lane * 64;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st_shared_v4(base + ((j ^ ((lane >> 1) & 3)) << 4), pc[j]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_4d(s.tm16, box, col0, row0, b1, b2);
+    bulk_commit();
+  }
+}
+
 // Store NP 16-byte pieces per row so that every warp-wide store instruction writes FULL 32-byte sectors: lanes 2i and
 // 2i+1 (rows A = row0+2i and B = A+1) swap half of their pieces, then both write into the same row -- instruction j
 // covers bytes [32j, 32j+32) of row A (first NP/2 instructions) or row B (last NP/2).  With one row per lane each
@@ -108,7 +160,7 @@ __device__ __forceinline__ void store_rows_paired(uint4 (&pc)[NP], char* rowA, l
     if (okB) *reinterpret_cast<uint4*>(b + 32 * j) = odd ? pc[2 * j + 1] : rc[j];
 }
 
-__device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, uint32_t taddr, const ResBuf& rb, uint32_t /*stage*/, int b1, int b2,
+__device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, uint32_t taddr, const ResBuf& rb, Sink& sink, int b1, int b2,
                                                    int row0, int col0, int lane) {
   uint32_t acc[32];
   tmem_ld_32x32(taddr, acc);
@@ -190,7 +242,8 @@ __device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, uint32_t taddr,
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       pc[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-    store_rows_paired<8>(pc, reinterpret_cast<char*>(e.o32 + off + (long long)rowA * e.ldc32), e.ldc32 * 4, okA, okB, lane);
+    if (sink.tma) sink_tma_f32(sink, pc, e.o16 != nullptr, b1, b2, row0, col0, lane);
+    else store_rows_paired<8>(pc, reinterpret_cast<char*>(e.o32 + off + (long long)rowA * e.ldc32), e.ldc32 * 4, okA, okB, lane);
   }
   if (e.o16) {
     uint4 pc[4];
@@ -200,16 +253,17 @@ __device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, uint32_t taddr,
 #pragma unroll
       for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j * 8 + 2 * t], v[j * 8 + 2 * t + 1]);
     }
-    store_rows_paired<4>(pc, reinterpret_cast<char*>(e.o16 + b2 * e.c16_bs2 + b1 * e.c16_bs1 + col0 + (long long)rowA * e.ldc16),
-                         e.ldc16 * 2, okA, okB, lane);
+    if (sink.tma) sink_tma_bf16(sink, pc, e.o32 != nullptr, b1, b2, row0, col0, lane);
+    else store_rows_paired<4>(pc, reinterpret_cast<char*>(e.o16 + b2 * e.c16_bs2 + b1 * e.c16_bs1 + col0 + (long long)rowA * e.ldc16),
+                              e.ldc16 * 2, okA, okB, lane);
   }
 }
 
 // Fused row-softmax epilogues (MIRROR_GEMM_ROWSTATS / SOFTMAX / ROWDOT / SOFTMAX_BWD): thread = row, this warp's BN/2
 // columns are one "part" of the row.  Logits live in the base-2 domain (x2 = alpha*log2(e)*acc) so exp is one MUFU.EX2.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, uint32_t taddr, int b1, int b2, int row0, int cbase, int lane,
-                                                      uint64_t* tfull_bar, uint32_t aphase, int part) {
+__device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, uint32_t taddr, int b1, int b2, int row0, int cbase,
+                                                      int lane, uint64_t* tfull_bar, uint32_t aphase, int part) {
   constexpr int NCH = BN / 64;
   const int row = row0 + lane;
   const bool row_ok = row < e.M;
@@ -222,7 +276,7 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, uint32_t tad
     float ssum = 0.f;
     for (int i = 0; i < e.nparts; ++i) {
       const float2 t = stats[i];
-      ssum += t.y * exp2f(t.x - m);
+      ssum += t.y * fast_exp2(t.x - m);
     }
     M2 = m;
     invS = 1.f / ssum;
@@ -252,16 +306,18 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, uint32_t tad
         cm = fmaxf(cm, v[j]);
       }
       if (cm > run_m) {
-        run_s *= exp2f(run_m - cm);
+        run_s *= fast_exp2(run_m - cm);
         run_m = cm;
       }
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};  // four chains: the adds must not serialise behind the MUFU results
 #pragma unroll
-      for (int j = 0; j < 32; ++j) run_s += exp2f(v[j] - run_m);
+      for (int j = 0; j < 32; ++j) s4[j & 3] += fast_exp2(v[j] - run_m);
+      run_s += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       continue;
     }
     if (e.mode == MIRROR_GEMM_SOFTMAX) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = exp2f(a2 * __uint_as_float(acc[j]) - M2) * invS;
+      for (int j = 0; j < 32; ++j) v[j] = fast_exp2(a2 * __uint_as_float(acc[j]) - M2) * invS;
     } else {  // ROWDOT / SOFTMAX_BWD read the probabilities
       uint4 pu[4];
       if (row_ok) {
@@ -282,8 +338,10 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, uint32_t tad
         }
       }
       if (e.mode == MIRROR_GEMM_ROWDOT) {
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) run_dot += v[j] * __uint_as_float(acc[j]);
+        for (int j = 0; j < 32; ++j) d4[j & 3] += v[j] * __uint_as_float(acc[j]);
+        run_dot += (d4[0] + d4[1]) + (d4[2] + d4[3]);
         continue;
       }
 #pragma unroll
@@ -294,8 +352,9 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, uint32_t tad
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         pc[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-      store_rows_paired<8>(pc, reinterpret_cast<char*>(e.o32 + b2 * e.c32_bs2 + b1 * e.c32_bs1 + col0 + (long long)rowA * e.ldc32),
-                           e.ldc32 * 4, okA, okB, lane);
+      if (sink.tma) sink_tma_f32(sink, pc, e.o16 != nullptr, b1, b2, row0, col0, lane);
+      else store_rows_paired<8>(pc, reinterpret_cast<char*>(e.o32 + b2 * e.c32_bs2 + b1 * e.c32_bs1 + col0 + (long long)rowA * e.ldc32),
+                                e.ldc32 * 4, okA, okB, lane);
     }
     if (e.o16) {
       uint4 pc[4];
@@ -305,8 +364,9 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, uint32_t tad
 #pragma unroll
         for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j * 8 + 2 * t], v[j * 8 + 2 * t + 1]);
       }
-      store_rows_paired<4>(pc, reinterpret_cast<char*>(e.o16 + b2 * e.c16_bs2 + b1 * e.c16_bs1 + col0 + (long long)rowA * e.ldc16),
-                           e.ldc16 * 2, okA, okB, lane);
+      if (sink.tma) sink_tma_bf16(sink, pc, e.o32 != nullptr, b1, b2, row0, col0, lane);
+      else store_rows_paired<4>(pc, reinterpret_cast<char*>(e.o16 + b2 * e.c16_bs2 + b1 * e.c16_bs1 + col0 + (long long)rowA * e.ldc16),
+                                e.ldc16 * 2, okA, okB, lane);
     }
   }
   if (row_ok) {
@@ -316,13 +376,13 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, uint32_t tad
 }
 
 // One epilogue warp's share of a finished tile: the 32 rows of its TMEM lane quarter (first row row0) x BN/2 columns
-// starting at cbase.  `stage`: this warp's 4 KB shared transpose tile (transposed mapping only).
+// starting at cbase.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t taddr, uint32_t stage, int b1, int b2, int row0,
+__device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t taddr, Sink& sink, int b1, int b2, int row0,
                                               int cbase, int lane, uint64_t* tfull_bar, uint32_t aphase, int part) {
   constexpr int NCH = BN / 64;  // 32-column chunks per thread
   if (e.mode != MIRROR_GEMM_NORMAL) {
-    epilogue_tile_softmax<BN>(e, taddr, b1, b2, row0, cbase, lane, tfull_bar, aphase, part);
+    epilogue_tile_softmax<BN>(e, sink, taddr, b1, b2, row0, cbase, lane, tfull_bar, aphase, part);
     return;
   }
   const bool rows_ok = row0 < e.M;  // warp-uniform
@@ -341,7 +401,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t 
     for (int u = 0; u < 2; ++u) {
       const int col0 = cbase + (c + u) * 32;
       if (c + u < NCH && col0 < e.N) {  // warp-uniform
-        if (fast && col0 + 32 <= e.N) epilogue_chunk_vec(e, taddr + (c + u) * 32, u ? rb1 : rb0, stage, b1, b2, row0, col0, lane);
+        if (fast && col0 + 32 <= e.N) epilogue_chunk_vec(e, taddr + (c + u) * 32, u ? rb1 : rb0, sink, b1, b2, row0, col0, lane);
         else epilogue_chunk_scalar(e, taddr + (c + u) * 32, b1, b2, row0 + lane, col0);
         if (c + u + 2 < NCH && fast && col0 + 96 <= e.N) res_prefetch(e, u ? rb1 : rb0, b1, b2, row0, col0 + 64, lane);
       }
@@ -349,11 +409,12 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t 
   }
 }
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, bool TMAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC32, const __grid_constant__ CUtensorMap tmC16,
                     const __grid_constant__ KParams p, const int vec_ok) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TMAS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -473,6 +534,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;            // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
     const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
     const bool fast = vec_ok != 0 && !p.e.atomic && p.e.act != MIRROR_ACT_GELU;
+    Sink sink{&tmC32, &tmC16, epi_stage + (warp - 2) * kSinkBytes, TMAS ? 1 : 0, 0};
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int tile = w / p.split_k, ks = w - tile * p.split_k;
@@ -487,13 +549,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row0 = mb_ * BM + q * 32;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), epi_stage + (warp - 2) * 4096, b1,
-                        b2, row0, cbase, lane, &tfull[as], aphase, nb * 2 + half);
+      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
+                        &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
       ++it;
     }
+    if (TMAS && lane == 0) bulk_wait_read<0>();  // the staging boxes must outlive their stores
   }
 
   tc_fence_before();
@@ -527,7 +590,6 @@ gemm_tcgen05_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  const uint32_t epi_stage = smem_u32(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
@@ -650,6 +712,7 @@ gemm_tcgen05_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const bool fast = vec_ok != 0 && !p.e.atomic && p.e.act != MIRROR_ACT_GELU;
+    Sink sink{nullptr, nullptr, 0u, 0, 0};
     int it = 0;
     for (int w = cid; w < total; w += nclusters) {
       const int tile = w / p.split_k, ks = w - tile * p.split_k;
@@ -664,8 +727,8 @@ gemm_tcgen05_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int row0 = (mg * CL + rank) * BM + q * 32;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), epi_stage + (warp - 2) * 4096, b1,
-                        b2, row0, cbase, lane, &tfull[as], aphase, nb * 2 + half);
+      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
+                        &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -707,7 +770,6 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  const uint32_t epi_stage = smem_u32(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
@@ -821,6 +883,7 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const bool fast = vec_ok != 0 && p.e.act != MIRROR_ACT_GELU;
+    Sink sink{nullptr, nullptr, 0u, 0, 0};
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int nb = w % p.tiles_n;
@@ -832,8 +895,8 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
       const int row0 = mb_ * BM + q * 32;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), epi_stage + (warp - 2) * 4096, b1,
-                        b2, row0, cbase, lane, &tfull[as], aphase, nb * 2 + half);
+      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
+                        &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -893,10 +956,11 @@ int make_operand_map(CUtensorMap* map, const void* ptr, int mn_major, long long 
   return 0;
 }
 
-template <int BN, int A_MN, int B_MN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int vec_ok, cudaStream_t stream) {
-  using C = Cfg<BN>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+template <int BN, int A_MN, int B_MN, bool TMAS>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC32, const CUtensorMap& tmC16, const KParams& p,
+           int vec_ok, cudaStream_t stream) {
+  using C = Cfg<BN, TMAS>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TMAS>;
   static bool configured = false;  // benign race: attribute set is idempotent
   if (!configured) {
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -904,9 +968,42 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.batch1 * p.batch2 * p.split_k;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, p, vec_ok);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC32, tmC16, p, vec_ok);
   MB_LAUNCH_CHECK();
   return 0;
+}
+
+// Output tensor map of the TMA-store epilogue: [batch2, batch1, M, N] with element strides (bs2, bs1, ld, 1), 32 x 32 boxes.
+int make_output_map(CUtensorMap* map, void* ptr, bool f32, long long M, long long N, long long ld, long long bs1, int batch1,
+                    long long bs2, int batch2) {
+  auto enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MB_ERR_DRIVER;
+  }
+  const cuuint64_t es = f32 ? 4 : 2;
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)batch1, (cuuint64_t)batch2};
+  const cuuint64_t fallback = (cuuint64_t)ld * es;
+  cuuint64_t strides[3] = {(cuuint64_t)ld * es, batch1 > 1 ? (cuuint64_t)bs1 * es : fallback, batch2 > 1 ? (cuuint64_t)bs2 * es : fallback};
+  cuuint32_t box[4] = {32, 32, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed (%d): M=%lld N=%lld ld=%lld", (int)r, M, N, ld);
+    return MB_ERR_DRIVER;
+  }
+  return 0;
+}
+
+// the bulk-store epilogue needs 16-byte aligned bases and strides (a TMA rule); everything else keeps register stores
+bool tma_store_ok(const mirror_gemm_args* g) {
+  auto ok = [&](const void* ptr, long long es, long long ld, long long bs1, long long bs2) {
+    return !ptr || (((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) && (ld * es) % 16 == 0 &&
+                    (g->batch1 <= 1 || (bs1 > 0 && (bs1 * es) % 16 == 0)) && (g->batch2 <= 1 || (bs2 > 0 && (bs2 * es) % 16 == 0)));
+  };
+  return ok(g->out_f32, 4, g->ldc32, g->c32_bs1, g->c32_bs2) && ok(g->out_bf16, 2, g->ldc16, g->c16_bs1, g->c16_bs2);
 }
 
 template <int BN, int A_MN, int B_MN, int CL>
@@ -1099,16 +1196,28 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
   if (rc) return rc;
   const int vec = epi_vec_ok(g) ? 1 : 0;
   const int key = (g->a_mn_major ? 2 : 0) | (g->b_mn_major ? 1 : 0);
-#define MB_DISPATCH(BNV)                                          \
-  switch (key) {                                                  \
-    case 0: return launch<BNV, 0, 0>(tmA, tmB, p, vec, stream);   \
-    case 1: return launch<BNV, 0, 1>(tmA, tmB, p, vec, stream);   \
-    case 2: return launch<BNV, 1, 0>(tmA, tmB, p, vec, stream);   \
-    default: return launch<BNV, 1, 1>(tmA, tmB, p, vec, stream);  \
+  // Epilogue-bound products (short K: the tile's stores, not its MMAs, set the pace) hand their output to TMA.
+  static const int tmas_env = [] { const char* v = getenv("MIRROR_B200_TMA_STORE"); return v && *v ? atoi(v) : -1; }();
+  const bool has_out = g->out_f32 || g->out_bf16;
+  bool tmas = BN != 256 && has_out && vec && !p.e.atomic && p.e.act != MIRROR_ACT_GELU && p.split_k == 1 && g->K <= 1024 &&
+              g->N % 32 == 0 && tma_store_ok(g);
+  if (tmas_env == 0) tmas = false;
+  CUtensorMap tmC32 = tmA, tmC16 = tmA;  // placeholders when unused
+  if (tmas) {
+    if (g->out_f32) { rc = make_output_map(&tmC32, g->out_f32, true, g->M, g->N, g->ldc32, g->c32_bs1, g->batch1, g->c32_bs2, g->batch2); if (rc) return rc; }
+    if (g->out_bf16) { rc = make_output_map(&tmC16, g->out_bf16, false, g->M, g->N, g->ldc16, g->c16_bs1, g->batch1, g->c16_bs2, g->batch2); if (rc) return rc; }
   }
-  if (BN == 256) { MB_DISPATCH(256) }
-  if (BN == 192) { MB_DISPATCH(192) }
-  MB_DISPATCH(128)
+#define MB_DISPATCH(BNV, TM)                                                        \
+  switch (key) {                                                                    \
+    case 0: return launch<BNV, 0, 0, TM>(tmA, tmB, tmC32, tmC16, p, vec, stream);   \
+    case 1: return launch<BNV, 0, 1, TM>(tmA, tmB, tmC32, tmC16, p, vec, stream);   \
+    case 2: return launch<BNV, 1, 0, TM>(tmA, tmB, tmC32, tmC16, p, vec, stream);   \
+    default: return launch<BNV, 1, 1, TM>(tmA, tmB, tmC32, tmC16, p, vec, stream);  \
+  }
+  if (BN == 256) { MB_DISPATCH(256, false) }
+  if (BN == 192) { if (tmas) { MB_DISPATCH(192, true) } MB_DISPATCH(192, false) }
+  if (tmas) { MB_DISPATCH(128, true) }
+  MB_DISPATCH(128, false)
 #undef MB_DISPATCH
 }
 

@@ -355,3 +355,27 @@ def test_gemm_fused_softmax_fwd_bwd(rows, cols, kd):
     p_c = torch.zeros(Bt, hd, rows, cols)
     EMU.gemm(a, b, alpha=alpha, mode=2, stats=st_c, out_f32=p_c)
     assert (p_c - p_ref).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("M,N,Kd,outs", [(300, 96, 64, "both"), (130, 384, 96, "b16"), (384, 192, 384, "f32"), (77, 160, 40, "both")])
+def test_gemm_bulk_store_epilogue(M, N, Kd, outs):
+    # short-K products hand finished 32x32 chunks to TMA (staging box -> bulk tensor store); row tails are clipped by the
+    # tensor map, outputs may be head-strided views.  Checked against the emulation, residual + diag + alpha included.
+    Bt, hd = 2, 3
+    a, b = rn(Bt, hd, M, Kd, seed=1).to(BF16), rn(Bt, hd, N, Kd, seed=2).to(BF16)
+    r = rn(Bt, hd, M, N, seed=3).to(BF16)
+    kw = dict(alpha=0.37, diag=1.0, res=r, gamma=-0.5)
+    o32c = torch.zeros(Bt, hd, M, N) if outs != "b16" else None
+    o16c = torch.zeros(Bt, M, hd * N, dtype=BF16).unflatten(-1, (hd, N)).permute(0, 2, 1, 3) if outs != "f32" else None
+    EMU.gemm(a, b, out_f32=o32c, out_bf16=o16c, **kw)
+    o32 = torch.full((Bt, hd, M + 1, N), 7.0, device="cuda") if outs != "b16" else None           # one guard row per matrix
+    o16s = torch.full((Bt, M + 1, hd * N), 7.0, device="cuda", dtype=BF16) if outs != "f32" else None
+    o16 = o16s[:, :M].unflatten(-1, (hd, N)).permute(0, 2, 1, 3) if o16s is not None else None
+    kwd = dict(kw, res=r.cuda())
+    K.gemm(a.cuda(), b.cuda(), out_f32=o32[:, :, :M] if o32 is not None else None, out_bf16=o16, **kwd)
+    if o32 is not None:
+        close(o32[:, :, :M], o32c, 2e-5, "bulk-store f32")
+        assert (o32[:, :, M] == 7.0).all(), "rows past M must be clipped"
+    if o16 is not None:
+        close(o16, o16c, 8e-3, "bulk-store bf16")
+        assert (o16s[:, M] == 7.0).all(), "rows past M must be clipped"
