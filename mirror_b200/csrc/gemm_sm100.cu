@@ -753,6 +753,7 @@ constexpr int kMaxTerms = 6;
 struct MultiMaps {
   CUtensorMap a[kMaxTerms];
   CUtensorMap b[kMaxTerms];
+  CUtensorMap c32, c16;  // outputs (bulk-store epilogue)
 };
 struct MultiInfo {
   int nterms;
@@ -761,15 +762,16 @@ struct MultiInfo {
   int b_mn[kMaxTerms];
 };
 
-template <int BN>
+template <int BN, bool TMAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_constant__ KParams p,
                           const __grid_constant__ MultiInfo mi, const int vec_ok) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TMAS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  const uint32_t epi_stage = smem_u32(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
@@ -883,7 +885,7 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const bool fast = vec_ok != 0 && p.e.act != MIRROR_ACT_GELU;
-    Sink sink{nullptr, nullptr, 0u, 0, 0};
+    Sink sink{&maps.c32, &maps.c16, epi_stage + (warp - 2) * kSinkBytes, TMAS ? 1 : 0, 0};
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int nb = w % p.tiles_n;
@@ -902,6 +904,7 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
       if (lane == 0) mbar_arrive(&tempty[as]);
       ++it;
     }
+    if (TMAS && lane == 0) bulk_wait_read<0>();
   }
 
   tc_fence_before();
@@ -1006,6 +1009,22 @@ bool tma_store_ok(const mirror_gemm_args* g) {
   return ok(g->out_f32, 4, g->ldc32, g->c32_bs1, g->c32_bs2) && ok(g->out_bf16, 2, g->ldc16, g->c16_bs1, g->c16_bs2);
 }
 
+// Epilogue-bound products (short K: the tile's stores, not its MMAs, set the pace) hand their output to TMA.
+// MIRROR_B200_TMA_STORE=0 keeps the register stores everywhere (A/B switch).
+bool use_tma_store(const mirror_gemm_args* g, const Epi* e, int vec, long long ktot) {
+  static const int env = [] { const char* v = getenv("MIRROR_B200_TMA_STORE"); return v && *v ? atoi(v) : -1; }();
+  if (env == 0) return false;
+  return (g->out_f32 || g->out_bf16) && vec && !e->atomic && e->act != MIRROR_ACT_GELU && g->split_k <= 1 && ktot <= 1024 &&
+         g->N % 32 == 0 && tma_store_ok(g);
+}
+
+int make_output_maps(const mirror_gemm_args* g, CUtensorMap* c32, CUtensorMap* c16) {
+  int rc = 0;
+  if (g->out_f32) rc = make_output_map(c32, g->out_f32, true, g->M, g->N, g->ldc32, g->c32_bs1, g->batch1, g->c32_bs2, g->batch2);
+  if (!rc && g->out_bf16) rc = make_output_map(c16, g->out_bf16, false, g->M, g->N, g->ldc16, g->c16_bs1, g->batch1, g->c16_bs2, g->batch2);
+  return rc;
+}
+
 template <int BN, int A_MN, int B_MN, int CL>
 int launch_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int vec_ok, cudaStream_t stream) {
   using C = Cfg<BN>;
@@ -1024,10 +1043,10 @@ int launch_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams
 }
 
 
-template <int BN>
+template <int BN, bool TMAS>
 int launch_multi(const MultiMaps& maps, const KParams& p, const MultiInfo& mi, int vec_ok, cudaStream_t stream) {
-  using C = Cfg<BN>;
-  auto kern = gemm_tcgen05_multi_kernel<BN>;
+  using C = Cfg<BN, TMAS>;
+  auto kern = gemm_tcgen05_multi_kernel<BN, TMAS>;
   static bool configured = false;
   if (!configured) {
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -1196,16 +1215,11 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
   if (rc) return rc;
   const int vec = epi_vec_ok(g) ? 1 : 0;
   const int key = (g->a_mn_major ? 2 : 0) | (g->b_mn_major ? 1 : 0);
-  // Epilogue-bound products (short K: the tile's stores, not its MMAs, set the pace) hand their output to TMA.
-  static const int tmas_env = [] { const char* v = getenv("MIRROR_B200_TMA_STORE"); return v && *v ? atoi(v) : -1; }();
-  const bool has_out = g->out_f32 || g->out_bf16;
-  bool tmas = BN != 256 && has_out && vec && !p.e.atomic && p.e.act != MIRROR_ACT_GELU && p.split_k == 1 && g->K <= 1024 &&
-              g->N % 32 == 0 && tma_store_ok(g);
-  if (tmas_env == 0) tmas = false;
+  const bool tmas = use_tma_store(g, &p.e, vec, g->K);
   CUtensorMap tmC32 = tmA, tmC16 = tmA;  // placeholders when unused
   if (tmas) {
-    if (g->out_f32) { rc = make_output_map(&tmC32, g->out_f32, true, g->M, g->N, g->ldc32, g->c32_bs1, g->batch1, g->c32_bs2, g->batch2); if (rc) return rc; }
-    if (g->out_bf16) { rc = make_output_map(&tmC16, g->out_bf16, false, g->M, g->N, g->ldc16, g->c16_bs1, g->batch1, g->c16_bs2, g->batch2); if (rc) return rc; }
+    rc = make_output_maps(g, &tmC32, &tmC16);
+    if (rc) return rc;
   }
 #define MB_DISPATCH(BNV, TM)                                                        \
   switch (key) {                                                                    \
@@ -1214,7 +1228,7 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
     case 2: return launch<BNV, 1, 0, TM>(tmA, tmB, tmC32, tmC16, p, vec, stream);   \
     default: return launch<BNV, 1, 1, TM>(tmA, tmB, tmC32, tmC16, p, vec, stream);  \
   }
-  if (BN == 256) { MB_DISPATCH(256, false) }
+  if (BN == 256) { if (tmas) { MB_DISPATCH(256, true) } MB_DISPATCH(256, false) }
   if (BN == 192) { if (tmas) { MB_DISPATCH(192, true) } MB_DISPATCH(192, false) }
   if (tmas) { MB_DISPATCH(128, true) }
   MB_DISPATCH(128, false)
@@ -1262,9 +1276,17 @@ extern "C" int mirror_gemm_bf16_multi(const mirror_gemm_args* terms, int32_t nte
     maps.b[t] = maps.b[0];
   }
   const int vec = epi_vec_ok(g) ? 1 : 0;
-  if (BN == 256) return launch_multi<256>(maps, p, mi, vec, stream);
-  if (BN == 192) return launch_multi<192>(maps, p, mi, vec, stream);
-  return launch_multi<128>(maps, p, mi, vec, stream);
+  long long ktot = 0;
+  for (int t = 0; t < nterms; ++t) ktot += terms[t].K;
+  bool tmas = use_tma_store(g, &p.e, vec, ktot);
+  maps.c32 = maps.c16 = maps.a[0];
+  if (tmas) {
+    rc = make_output_maps(g, &maps.c32, &maps.c16);
+    if (rc) return rc;
+  }
+  if (BN == 256) return tmas ? launch_multi<256, true>(maps, p, mi, vec, stream) : launch_multi<256, false>(maps, p, mi, vec, stream);
+  if (BN == 192) return tmas ? launch_multi<192, true>(maps, p, mi, vec, stream) : launch_multi<192, false>(maps, p, mi, vec, stream);
+  return tmas ? launch_multi<128, true>(maps, p, mi, vec, stream) : launch_multi<128, false>(maps, p, mi, vec, stream);
 }
 
 extern "C" int mirror_gemm_bf16_simt(const mirror_gemm_args* g, mirror_stream_t stream_) {
