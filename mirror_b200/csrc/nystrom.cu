@@ -10,60 +10,80 @@ namespace {
 
 constexpr int TAPS = 33;
 
-// Depthwise 33-tap FIR along the token axis.  Each thread owns one bf16 channel pair and a strip of TT consecutive
-// tokens: the TT+32 inputs of the strip are loaded once into registers and reused by all 33 taps (3 loads per
-// output pair instead of 33), threads of a warp cover 64 consecutive channels (128-byte coalesced rows).
+// Depthwise 33-tap FIR along the token axis.  Each thread owns one bf16 channel pair (a warp covers 64 consecutive
+// channels = 128-byte rows) and walks a CHUNK of consecutive TT-token strips with a sliding register window: the 48
+// inputs a strip needs are the previous strip's last 32 plus 16 new ones, and those 16 are fetched (still packed) while
+// the 33 x 16 x 2 FMAs of the current strip issue -- the load latency hides inside the warp instead of needing occupancy
+// (the first version loaded all 48 inputs per strip up front: 0.7 IPC per SM, 0.72 ms per call at the benchmark shape).
 //   FWD: out16[b,t,c] = sum_j w[h(c),j] * v[b,t+j-16,c]      (v = value slot of qkv [B,n,3E], column 2E+c)
 //   BWD: dv16[b,t,c]   = sum_j w[h(c),j] * dout[b,t-j+16,c]        (data gradient: the same FIR with flipped taps)
 constexpr int TT = 16;
+constexpr int HALO = TAPS - 1;  // 32
+
+__device__ __forceinline__ uint32_t ld_pair(const bf16* base, long long ld, long long b, int n, int tt) {
+  return (tt >= 0 && tt < n) ? *reinterpret_cast<const uint32_t*>(base + (b * n + tt) * ld) : 0u;
+}
+__device__ __forceinline__ float2 unpack_pair(uint32_t u) {  // bf16 -> f32 is a shift
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
 
 template <bool BWD>
 __global__ void __launch_bounds__(128)
 res_conv_kernel(const bf16* __restrict__ src, long long src_ld, int src_col0, const float* __restrict__ w, int n, int E, int d,
-                bf16* __restrict__ dst16, long long dst_ld, int dst_col0) {
+                bf16* __restrict__ dst16, long long dst_ld, int dst_col0, int strips_per_chunk) {
   __shared__ float sw[8 * TAPS];
   for (int i = threadIdx.x; i < 8 * TAPS; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
   const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   if (c >= E) return;
-  const int t0 = blockIdx.y * TT;
   const long long b = blockIdx.z;
   const float* wh = sw + (c / d) * TAPS;
-  float2 in[TT + TAPS - 1];
+  const bf16* sp = src + src_col0 + c;
+  const int strips = (n + TT - 1) / TT;
+  const int s0 = blockIdx.y * strips_per_chunk, s1 = min(strips, s0 + strips_per_chunk);
+  if (s0 >= s1) return;
+  float2 win[TT + HALO];  // tokens t0-16 .. t0+31 of the current strip
 #pragma unroll
-  for (int i = 0; i < TT + TAPS - 1; ++i) {
-    const int tt = t0 + i - 16;
-    in[i] = (tt >= 0 && tt < n)
-                ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + (b * n + tt) * src_ld + src_col0 + c))
-                : make_float2(0.f, 0.f);
-  }
-  float2 acc[TT];
+  for (int i = 0; i < HALO; ++i) win[i] = unpack_pair(ld_pair(sp, src_ld, b, n, s0 * TT + i - 16));
+  uint32_t nxt[TT];
 #pragma unroll
-  for (int i = 0; i < TT; ++i) acc[i] = make_float2(0.f, 0.f);
+  for (int i = 0; i < TT; ++i) nxt[i] = ld_pair(sp, src_ld, b, n, s0 * TT + HALO + i - 16);
+  for (int s = s0; s < s1; ++s) {
+    const int t0 = s * TT;
 #pragma unroll
-  for (int j = 0; j < TAPS; ++j) {
-    const float wj = BWD ? wh[TAPS - 1 - j] : wh[j];  // BWD: out[t] = sum_j w[j] in[t-j+16] = sum_j' w[32-j'] in[t+j'-16]
+    for (int i = 0; i < TT; ++i) win[HALO + i] = unpack_pair(nxt[i]);
+    if (s + 1 < s1) {  // the next strip's new inputs travel while this strip computes
+#pragma unroll
+      for (int i = 0; i < TT; ++i) nxt[i] = ld_pair(sp, src_ld, b, n, t0 + TT + HALO + i - 16);
+    }
+    float2 acc[TT];
+#pragma unroll
+    for (int i = 0; i < TT; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < TAPS; ++j) {
+      const float wj = BWD ? wh[TAPS - 1 - j] : wh[j];  // BWD: out[t] = sum_j w[j] in[t-j+16] = sum_j' w[32-j'] in[t+j'-16]
+#pragma unroll
+      for (int i = 0; i < TT; ++i) {
+        acc[i].x += wj * win[i + j].x;
+        acc[i].y += wj * win[i + j].y;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < TT; ++i) {
-      acc[i].x += wj * in[i + j].x;
-      acc[i].y += wj * in[i + j].y;
+      const int t = t0 + i;
+      if (t < n) *reinterpret_cast<__nv_bfloat162*>(dst16 + (b * n + t) * dst_ld + dst_col0 + c) = __floats2bfloat162_rn(acc[i].x, acc[i].y);
     }
-  }
 #pragma unroll
-  for (int i = 0; i < TT; ++i) {
-    const int t = t0 + i;
-    if (t >= n) break;
-    *reinterpret_cast<__nv_bfloat162*>(dst16 + (b * n + t) * dst_ld + dst_col0 + c) = __floats2bfloat162_rn(acc[i].x, acc[i].y);
+    for (int i = 0; i < HALO; ++i) win[i] = win[i + TT];
   }
 }
 
-// dw[h,j] += sum_{b,t,c in head h} dout[b,t,c] * v[b,t+j-16,c].  Same strip decomposition, but a thread keeps its 33
-// partial sums in registers across ALL token strips of its chunk (grid.y chunks per slide); only then are they reduced
-// (warp shuffle -> shared atomics -> one global atomic per (head, tap) and CTA).  One global atomic per strip and tap
-// (the first version) serialised 7 M atomics on 264 addresses and took 2.8 ms.
+// dw[h,j] += sum_{b,t,c in head h} dout[b,t,c] * v[b,t+j-16,c].  The same sliding window over v plus the strip's 16
+// gradients, both prefetched one strip ahead; a thread keeps its 33 partial sums in registers across ALL strips of its
+// chunk and only then reduces them (warp shuffle -> shared atomics -> one global atomic per (head, tap) and CTA).
 __global__ void __launch_bounds__(128)
 res_conv_wgrad_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ qkv, int n, int E, int d, float* __restrict__ dw,
-                      int strips_per_block) {
+                      int strips_per_chunk) {
   __shared__ float sacc[8 * TAPS];
   for (int i = threadIdx.x; i < 8 * TAPS; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
@@ -72,34 +92,45 @@ res_conv_wgrad_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ qk
   // warp-uniform fast path: all 32 lanes active and inside one head -> shuffle-reduce, one shared atomic per tap
   const int c_first = 2 * (blockIdx.x * blockDim.x + (threadIdx.x & ~31));
   const bool warp_one_head = (c_first + 62 < E) && (c_first / d == (c_first + 62) / d);
-  if (c < E) {
+  const int strips = (n + TT - 1) / TT;
+  const int s0 = blockIdx.y * strips_per_chunk, s1 = min(strips, s0 + strips_per_chunk);
+  if (c < E && s0 < s1) {
+    const bf16* vp = qkv + 2 * E + c;
+    const bf16* gp = dout + c;
     float acc[TAPS];
 #pragma unroll
     for (int j = 0; j < TAPS; ++j) acc[j] = 0.f;
-    const int s0 = blockIdx.y * strips_per_block;
-    for (int s = s0; s < s0 + strips_per_block; ++s) {
-      const int t0 = s * TT;
-      if (t0 >= n) break;
-      float2 vin[TT + TAPS - 1];
+    float2 win[TT + HALO];
 #pragma unroll
-      for (int i = 0; i < TT + TAPS - 1; ++i) {
-        const int tt = t0 + i - 16;
-        vin[i] = (tt >= 0 && tt < n)
-                     ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qkv + (b * n + tt) * 3LL * E + 2 * E + c))
-                     : make_float2(0.f, 0.f);
-      }
+    for (int i = 0; i < HALO; ++i) win[i] = unpack_pair(ld_pair(vp, 3LL * E, b, n, s0 * TT + i - 16));
+    uint32_t nxt[TT], gn[TT];
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+      nxt[i] = ld_pair(vp, 3LL * E, b, n, s0 * TT + HALO + i - 16);
+      gn[i] = ld_pair(gp, E, b, n, s0 * TT + i);
+    }
+    for (int s = s0; s < s1; ++s) {
+      const int t0 = s * TT;
       float2 g[TT];
 #pragma unroll
       for (int i = 0; i < TT; ++i) {
-        const int t = t0 + i;
-        g[i] = t < n ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + (b * n + t) * (long long)E + c))
-                     : make_float2(0.f, 0.f);
+        win[HALO + i] = unpack_pair(nxt[i]);
+        g[i] = unpack_pair(gn[i]);
+      }
+      if (s + 1 < s1) {
+#pragma unroll
+        for (int i = 0; i < TT; ++i) {
+          nxt[i] = ld_pair(vp, 3LL * E, b, n, t0 + TT + HALO + i - 16);
+          gn[i] = ld_pair(gp, E, b, n, t0 + TT + i);
+        }
       }
 #pragma unroll
       for (int j = 0; j < TAPS; ++j) {
 #pragma unroll
-        for (int i = 0; i < TT; ++i) acc[j] += g[i].x * vin[i + j].x + g[i].y * vin[i + j].y;
+        for (int i = 0; i < TT; ++i) acc[j] += g[i].x * win[i + j].x + g[i].y * win[i + j].y;
       }
+#pragma unroll
+      for (int i = 0; i < HALO; ++i) win[i] = win[i + TT];
     }
     const int h = c / d;
 #pragma unroll
@@ -123,22 +154,42 @@ res_conv_wgrad_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ qk
 __device__ __forceinline__ unsigned long long pack_key(float v, unsigned idx) {
   return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
 }
-__global__ void pinv_scale_kernel(const float* __restrict__ a2, int m, unsigned long long* __restrict__ keys) {
+// One CTA per matrix.  Column sums: thread j walks down column j (a warp reads 128 contiguous bytes per row, rows in
+// index order so the sum order is that of a sequential loop).  Row sums: one warp per row, lanes strided, shuffle tree.
+// (The first version let every thread walk its own ROW: 32 sectors per load instruction, 0.35 ms per call.)
+__global__ void __launch_bounds__(512)
+pinv_scale_kernel(const float* __restrict__ a2, int m, unsigned long long* __restrict__ keys) {
+  __shared__ unsigned long long sk[2];
+  if (threadIdx.x < 2) sk[threadIdx.x] = 0ull;
+  __syncthreads();
   const int bh = blockIdx.x;
   const float* a = a2 + (long long)bh * m * m;
   unsigned long long best_r = 0, best_c = 0;
-  for (int i = threadIdx.x; i < m; i += blockDim.x) {  // thread i: row-sum of row i (strided reads, L1-resident tile)
-    float rs = 0.f, cs = 0.f;
-    for (int j = 0; j < m; ++j) {
-      rs += fabsf(a[(long long)i * m + j]);
-      cs += fabsf(a[(long long)j * m + i]);
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;  // four loads in flight; rows still enter each partial in index order
+    int i = 0;
+    for (; i + 4 <= m; i += 4) {
+      c0 += fabsf(a[(long long)i * m + j]);
+      c1 += fabsf(a[(long long)(i + 1) * m + j]);
+      c2 += fabsf(a[(long long)(i + 2) * m + j]);
+      c3 += fabsf(a[(long long)(i + 3) * m + j]);
     }
-    const unsigned long long kr = pack_key(rs, (unsigned)(bh * m + i)), kc = pack_key(cs, (unsigned)(bh * m + i));
-    best_r = kr > best_r ? kr : best_r;
+    for (; i < m; ++i) c0 += fabsf(a[(long long)i * m + j]);
+    const unsigned long long kc = pack_key((c0 + c1) + (c2 + c3), (unsigned)(bh * m + j));
     best_c = kc > best_c ? kc : best_c;
   }
-  atomicMax(keys, best_r);
-  atomicMax(keys + 1, best_c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < m; i += nw) {
+    float rs = 0.f;
+    for (int j = lane; j < m; j += 32) rs += fabsf(a[(long long)i * m + j]);
+    rs = warp_sum(rs);
+    const unsigned long long kr = pack_key(rs, (unsigned)(bh * m + i));
+    best_r = kr > best_r ? kr : best_r;
+  }
+  atomicMax(&sk[0], best_r);
+  atomicMax(&sk[1], best_c);
+  __syncthreads();
+  if (threadIdx.x < 2) atomicMax(keys + threadIdx.x, sk[threadIdx.x]);
 }
 __device__ __forceinline__ float key_val(unsigned long long k) { return __uint_as_float((unsigned)(k >> 32)); }
 __device__ __forceinline__ unsigned key_idx(unsigned long long k) { return 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFu); }
@@ -215,29 +266,40 @@ static int ew_grid(long long n, int block) {
   return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
+// strips a thread walks: long chunks amortise the 32-token halo and keep the prefetch pipeline running (measured at the
+// benchmark shape: 16 strips 0.255 ms vs 4 strips 0.271 ms forward; weight-grad 0.56 vs 1.05 ms), but the grid should still
+// hold ~6 CTAs per SM.  MIRROR_B200_CONV_SPC overrides (tuning).
+static int conv_strips_per_chunk(int B, int n, int E, int max_spc) {
+  static const int env = [] { const char* v = getenv("MIRROR_B200_CONV_SPC"); return v && *v ? atoi(v) : 0; }();
+  const int strips = (n + TT - 1) / TT;
+  const long long cols = (E / 2 + 127) / 128;
+  const long long want_chunks = (6LL * num_sms() + cols * B - 1) / (cols * B);
+  int spc = env > 0 ? env : (int)(strips / want_chunks);
+  if (env <= 0) spc = spc < 4 ? 4 : (spc > max_spc ? max_spc : spc);
+  return spc > strips ? strips : spc;
+}
+
 extern "C" int mirror_res_conv_fwd(const void* qkv, const float* w, int32_t B, int32_t n, int32_t E, void* out_bf16,
                                    mirror_stream_t stream) {
   MB_CHECK_ARG(qkv && w && out_bf16 && B > 0 && n > 0 && E % 16 == 0, "res_conv_fwd: bad args");
-  dim3 grid((E / 2 + 127) / 128, (n + TT - 1) / TT, B);
+  const int spc = conv_strips_per_chunk(B, n, E, 16);
+  dim3 grid((E / 2 + 127) / 128, ((n + TT - 1) / TT + spc - 1) / spc, B);
   res_conv_kernel<false><<<grid, 128, 0, STREAM>>>(reinterpret_cast<const bf16*>(qkv), 3LL * E, 2 * E, w, n, E, E / 8,
-                                                  reinterpret_cast<bf16*>(out_bf16), E, 0);
+                                                  reinterpret_cast<bf16*>(out_bf16), E, 0, spc);
   MB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int mirror_res_conv_bwd(const void* dout_bf16, const void* qkv, const float* w, int32_t B, int32_t n, int32_t E,
                                    void* dv_bf16, float* dw, mirror_stream_t stream) {
   MB_CHECK_ARG(dout_bf16 && qkv && w && dv_bf16 && dw && B > 0 && n > 0 && E % 16 == 0, "res_conv_bwd: bad args");
-  dim3 grid((E / 2 + 127) / 128, (n + TT - 1) / TT, B);
+  const int spc = conv_strips_per_chunk(B, n, E, 16);
+  dim3 grid((E / 2 + 127) / 128, ((n + TT - 1) / TT + spc - 1) / spc, B);
   res_conv_kernel<true><<<grid, 128, 0, STREAM>>>(reinterpret_cast<const bf16*>(dout_bf16), E, 0, w, n, E, E / 8,
-                                                 reinterpret_cast<bf16*>(dv_bf16), E, 0);
+                                                 reinterpret_cast<bf16*>(dv_bf16), E, 0, spc);
   MB_LAUNCH_CHECK();
-  const int strips = (n + TT - 1) / TT;
-  int chunks = (2 * num_sms() + 3 * B - 1) / (3 * B);  // ~2 waves of CTAs in total
-  if (chunks < 1) chunks = 1;
-  if (chunks > strips) chunks = strips;
-  const int spb = (strips + chunks - 1) / chunks;
-  res_conv_wgrad_kernel<<<dim3(grid.x, (strips + spb - 1) / spb, B), 128, 0, STREAM>>>(
-      reinterpret_cast<const bf16*>(dout_bf16), reinterpret_cast<const bf16*>(qkv), n, E, E / 8, dw, spb);
+  const int wspc = conv_strips_per_chunk(B, n, E, 24);
+  res_conv_wgrad_kernel<<<dim3(grid.x, ((n + TT - 1) / TT + wspc - 1) / wspc, B), 128, 0, STREAM>>>(
+      reinterpret_cast<const bf16*>(dout_bf16), reinterpret_cast<const bf16*>(qkv), n, E, E / 8, dw, wspc);
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -247,7 +309,7 @@ extern "C" int mirror_pinv_init(const float* a2, int32_t BH, int32_t m, void* sc
                                 mirror_stream_t stream) {
   MB_CHECK_ARG(a2 && scratch32 && (z_f32 || z_bf16) && BH > 0 && m > 0, "pinv_init: bad args");
   MB_CUDA(cudaMemsetAsync(scratch32, 0, 32, STREAM));
-  pinv_scale_kernel<<<BH, 128, 0, STREAM>>>(a2, m, reinterpret_cast<unsigned long long*>(scratch32));
+  pinv_scale_kernel<<<BH, 512, 0, STREAM>>>(a2, m, reinterpret_cast<unsigned long long*>(scratch32));
   MB_LAUNCH_CHECK();
   dim3 grid((m + 31) / 32, (m + 31) / 32, BH), block(32, 8);
   pinv_init_kernel<<<grid, block, 0, STREAM>>>(a2, m, reinterpret_cast<const unsigned long long*>(scratch32), z_f32,

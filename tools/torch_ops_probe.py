@@ -1,0 +1,45 @@
+"""List the torch (non-product) kernels of one training step with shapes and python call sites:  python tools/torch_ops_probe.py [B]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+from mirror_b200.losses import MIRRORLoss  # noqa: E402
+from mirror_b200.models import MIRROR  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+N, Dw, Dr = 2048, 768, 10234
+dev = torch.device("cuda")
+torch.manual_seed(0)
+model = MIRROR(wsi_embed_dim=Dw, rna_embed_dim=Dr, embed_dim=768, wsi_num_tokens=N, rna_mlp_ratio=4.0, rna_norm_layer="layernorm",
+               rna_act_layer="gelu").to(dev).train()
+loss_fn = MIRRORLoss().to(dev)
+wsi, rna = torch.randn(B, N, Dw, device=dev), torch.randn(B, Dr, device=dev)
+
+
+def step():
+    for p in model.parameters():
+        p.grad = None
+    losses = loss_fn(*model(wsi, rna, 0.75, 0.75))
+    losses[0].backward()
+
+
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as prof:
+    step()
+    torch.cuda.synchronize()
+rows = []
+for e in prof.key_averages(group_by_input_shape=True, group_by_stack_n=6):
+    t = getattr(e, "device_time_total", 0) or getattr(e, "cuda_time_total", 0)
+    self_t = getattr(e, "self_device_time_total", 0) or getattr(e, "self_cuda_time_total", 0)
+    if e.key.startswith("aten::") and self_t > 20:
+        stack = [s for s in e.stack if "mirror_b200" in s or "bench" in s or "losses" in s]
+        rows.append((self_t, e.count, e.key, str(e.input_shapes)[:90], " <- ".join(s.split("/")[-1][:60] for s in stack[:3])))
+rows.sort(reverse=True)
+print(f"{'self us':>9s} {'n':>4s}  op / shapes / python site")
+for r in rows[:45]:
+    print(f"{r[0]:9.0f} {r[1]:4d}  {r[2]:28s} {r[3]}\n{'':16s}{r[4]}")
