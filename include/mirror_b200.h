@@ -126,6 +126,12 @@ int mirror_cast_split3(const float* src, int64_t rows, int32_t cols, int64_t lds
 int mirror_copy_rows_f32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd, mirror_stream_t stream);
 /* dst += alpha*src  (gradient accumulation of the autograd graph) */
 int mirror_axpy_f32(float* dst, const float* src, int64_t n, float alpha, mirror_stream_t stream);
+/* Gradient of the encoder output h:[B,T,E] that the model reads three ways (models/mirror.py:889-905: the whole matrix for the
+ * retention decoder, row 0 for the alignment head and the style encoder, rows 1.. as the retention target):
+ * out[b,0] = d_full[b,0] + d_cls[b];  out[b,t] = d_full[b,t] + d_tok[b,t-1].  Any of the three may be NULL (= zero).
+ * d_tok is a [B,T-1,E] view with batch / row strides tok_bs / tok_ld. */
+int mirror_token_fanout_bwd(const float* d_full, const float* d_cls, const float* d_tok, int64_t tok_bs, int64_t tok_ld, int32_t B,
+                            int32_t T, int32_t E, float* out, mirror_stream_t stream);
 /* out = dropout(act(pre)); keep(idx)=hash(seed,idx)>=p.  GELU of timm Mlp / Block (models/mirror.py:138-143,217-224). */
 int mirror_act_fwd(const float* pre, int64_t n, int32_t act, float drop_p, uint64_t seed, void* out_bf16, float* out_f32,
                    mirror_stream_t stream);
@@ -161,14 +167,18 @@ int mirror_reparam_bwd(const float* dz, const float* logvar, const float* eps, i
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm / softmax / L2-normalise (norm_softmax.cu)
  * ---------------------------------------------------------------------------------------------- */
-/* x:[B,S,E] f32 -> outputs in a padded layout [B,n_out,E] at row offset `pad` (rows<pad zero): the Nyström layer front-pads
- * with zero rows.  nn.LayerNorm at models/mirror.py:298,350,604 (eps 1e-5) and :122,137,255,494 (eps 1e-6). */
-int mirror_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t B, int32_t S, int32_t E,
-                         int32_t n_out, int32_t pad, void* out_bf16, float* out_f32, float* mean, float* rstd, mirror_stream_t stream);
-/* dx = (add ? add : 0) + LN-gradient; `add` may alias dx (the residual branch of models/mirror.py:312) */
+/* x:[B,x_rows,E] f32, the first S rows of every slide are normalised (x_rows > S: the encoder's final norm feeds only the
+ * N+1 real tokens onward, models/mirror.py:372 `h[:, :-add_length]`, without a copy) -> outputs in a padded layout
+ * [B,n_out,E] at row offset `pad` (rows<pad zero): the Nyström layer front-pads with zero rows.  mean/rstd: [B,S].
+ * nn.LayerNorm at models/mirror.py:298,350,604 (eps 1e-5) and :122,137,255,494 (eps 1e-6). */
+int mirror_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t B, int32_t S, int32_t x_rows,
+                         int32_t E, int32_t n_out, int32_t pad, void* out_bf16, float* out_f32, float* mean, float* rstd,
+                         mirror_stream_t stream);
+/* dx:[B,x_rows,E] = (add ? add : 0) + LN-gradient (rows >= S: no LN term); `add` may alias dx (the residual branch of
+ * models/mirror.py:312) */
 int mirror_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int32_t B,
-                         int32_t S, int32_t E, int32_t n_out, int32_t pad, float* dx, const float* add, float* dgamma,
-                         float* dbeta, mirror_stream_t stream);
+                         int32_t S, int32_t x_rows, int32_t E, int32_t n_out, int32_t pad, float* dx, const float* add,
+                         float* dgamma, float* dbeta, mirror_stream_t stream);
 /* row softmax of the three Nyström similarity matrices */
 int mirror_softmax_fwd(const float* x, int64_t rows, int32_t cols, void* y_bf16, float* y_f32, mirror_stream_t stream);
 int mirror_softmax_bwd(const void* y_bf16, const float* dy, int64_t rows, int32_t cols, float scale, void* dx_bf16, float* dx_f32,

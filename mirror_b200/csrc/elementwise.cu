@@ -265,6 +265,27 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __
   }
 }
 
+// out[b,0,:] = full[b,0,:] + cls[b,:];  out[b,t,:] = full[b,t,:] + tok[b,t-1,:] (t >= 1); absent terms are zero.
+// The gradient of "one token matrix read as a whole, as its cls row and as its patch rows" in ONE pass (float4 lanes).
+__global__ void token_fanout_bwd_kernel(const float* __restrict__ full, const float* __restrict__ cls, const float* __restrict__ tok,
+                                        long long tok_bs, long long tok_ld, int B, int T, int E, float* __restrict__ out) {
+  const int e4 = E / 4;
+  const long long n = (long long)B * T * e4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % e4) * 4;
+    const long long r = i / e4;
+    const int t = (int)(r % T);
+    const long long b = r / T;
+    float4 v = full ? *reinterpret_cast<const float4*>(full + r * E + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* add = t == 0 ? (cls ? cls + b * E + c : nullptr) : (tok ? tok + b * tok_bs + (long long)(t - 1) * tok_ld + c : nullptr);
+    if (add) {
+      const float4 a = *reinterpret_cast<const float4*>(add);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    *reinterpret_cast<float4*>(out + r * E + c) = v;
+  }
+}
+
 }  // namespace
 }  // namespace mb
 
@@ -309,6 +330,15 @@ extern "C" int mirror_axpy_f32(float* dst, const float* src, int64_t n, float al
   MB_CHECK_ARG(dst && src && n >= 0, "axpy: bad args");
   if (n == 0) return 0;
   axpy_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(dst, src, n, alpha);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_token_fanout_bwd(const float* d_full, const float* d_cls, const float* d_tok, int64_t tok_bs, int64_t tok_ld,
+                                       int32_t B, int32_t T, int32_t E, float* out, mirror_stream_t stream) {
+  MB_CHECK_ARG(out && B > 0 && T > 0 && E > 0 && E % 4 == 0 && (!d_tok || (tok_bs % 4 == 0 && tok_ld % 4 == 0)),
+               "token_fanout_bwd: bad args (E and the strides must be multiples of 4)");
+  token_fanout_bwd_kernel<<<grid_for((long long)B * T * (E / 4), 256), 256, 0, STREAM>>>(d_full, d_cls, d_tok, tok_bs, tok_ld, B, T, E, out);
   MB_LAUNCH_CHECK();
   return 0;
 }

@@ -8,11 +8,12 @@ namespace {
 constexpr int kWarps = 8;
 
 // ------------------------------------------------------------------ LayerNorm
-// x: [B, S, E] f32.  Outputs are written in a padded row layout [B, n_out, E] at row offset `pad`
+// x: [B, X, E] f32, of which the first S rows per slide are normalised (X > S drops the wrap-padding tokens of the WSI
+// encoder without a copy).  Outputs are written in a padded row layout [B, n_out, E] at row offset `pad`
 // (rows < pad are zero-filled: the Nyström layer front-pads the sequence with zero rows).
 __global__ void __launch_bounds__(kWarps * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-              int B, int S, int E, int n_out, int pad, bf16* __restrict__ o16, float* __restrict__ o32,
+              int B, int S, int X, int E, int n_out, int pad, bf16* __restrict__ o16, float* __restrict__ o32,
               float* __restrict__ mean, float* __restrict__ rstd) {
   const int lane = threadIdx.x & 31;
   const long long rows_out = (long long)B * n_out;
@@ -28,7 +29,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
     const int s = t - pad;
     if (s >= S) continue;
     const long long ri = (long long)b * S + s;
-    const float* xr = x + ri * E;
+    const float* xr = x + ((long long)b * X + s) * E;
     float sum = 0.f;
     for (int c = lane * 4; c < E; c += 128) {
       const float4 v = *reinterpret_cast<const float4*>(xr + c);
@@ -67,10 +68,11 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 }
 
 // dy: [B, n_out, E] (f32) at row offset pad.  dx = [add +] rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma.
+// x, dx, add: [B, X, E]; rows S..X-1 of a slide did not take part in the forward and receive dx = add (or 0).
 // dgamma/dbeta accumulate through shared-memory partials and one atomicAdd per block and column.
 __global__ void __launch_bounds__(kWarps * 32)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-              const float* __restrict__ mean, const float* __restrict__ rstd, int B, int S, int E, int n_out, int pad,
+              const float* __restrict__ mean, const float* __restrict__ rstd, int B, int S, int X, int E, int n_out, int pad,
               float* dx, const float* add, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float sh[];  // [2][E]
   float* sg = sh;
@@ -78,12 +80,17 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
   for (int c = threadIdx.x; c < 2 * E; c += blockDim.x) sh[c] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long rows = (long long)B * S;
+  const long long rows = (long long)B * X;
   for (long long ri = blockIdx.x * (long long)kWarps + (threadIdx.x >> 5); ri < rows; ri += (long long)gridDim.x * kWarps) {
-    const int b = (int)(ri / S), s = (int)(ri % S);
+    const int b = (int)(ri / X), s = (int)(ri % X);
+    if (s >= S) {
+      for (int c = lane * 4; c < E; c += 128)
+        *reinterpret_cast<float4*>(dx + ri * E + c) = add ? *reinterpret_cast<const float4*>(add + ri * E + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
     const float* xr = x + ri * E;
     const float* gr = dy + ((long long)b * n_out + pad + s) * E;
-    const float mu = mean[ri], rs = rstd[ri];
+    const float mu = mean[(long long)b * S + s], rs = rstd[(long long)b * S + s];
     float s1 = 0.f, s2 = 0.f;
     for (int c = lane * 4; c < E; c += 128) {
       const float4 v = *reinterpret_cast<const float4*>(xr + c);
@@ -130,8 +137,8 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
 template <int ITERS>
 __global__ void __launch_bounds__(kWarps * 32)
 ln_bwd_reg_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-                  const float* __restrict__ mean, const float* __restrict__ rstd, int B, int S, int n_out, int pad, float* dx,
-                  const float* add, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                  const float* __restrict__ mean, const float* __restrict__ rstd, int B, int S, int X, int n_out, int pad,
+                  float* dx, const float* add, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   constexpr int E = ITERS * 128;
   __shared__ float sh[2 * E];
   for (int c = threadIdx.x; c < 2 * E; c += blockDim.x) sh[c] = 0.f;
@@ -144,12 +151,20 @@ ln_bwd_reg_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
     ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const long long rows = (long long)B * S;
+  const long long rows = (long long)B * X;
   for (long long ri = blockIdx.x * (long long)kWarps + (threadIdx.x >> 5); ri < rows; ri += (long long)gridDim.x * kWarps) {
-    const int b = (int)(ri / S), s = (int)(ri % S);
+    const int b = (int)(ri / X), s = (int)(ri % X);
+    if (s >= S) {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const long long o = ri * E + lane * 4 + 128 * i;
+        *reinterpret_cast<float4*>(dx + o) = add ? *reinterpret_cast<const float4*>(add + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      continue;
+    }
     const float* xr = x + ri * E;
     const float* gr = dy + ((long long)b * n_out + pad + s) * E;
-    const float mu = mean[ri], rs = rstd[ri];
+    const float mu = mean[(long long)b * S + s], rs = rstd[(long long)b * S + s];
     float4 xv[ITERS], gv[ITERS];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -292,32 +307,34 @@ using namespace mb;
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
 
 extern "C" int mirror_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t B, int32_t S,
-                                    int32_t E, int32_t n_out, int32_t pad, void* out_bf16, float* out_f32, float* mean,
-                                    float* rstd, mirror_stream_t stream) {
+                                    int32_t x_rows, int32_t E, int32_t n_out, int32_t pad, void* out_bf16, float* out_f32,
+                                    float* mean, float* rstd, mirror_stream_t stream) {
   MB_CHECK_ARG(x && gamma && beta && mean && rstd && (out_bf16 || out_f32), "layernorm_fwd: null pointer");
-  MB_CHECK_ARG(B > 0 && S > 0 && E % 4 == 0 && pad >= 0 && n_out >= S + pad, "layernorm_fwd: bad shape (E must be a multiple of 4)");
+  MB_CHECK_ARG(B > 0 && S > 0 && x_rows >= S && E % 4 == 0 && pad >= 0 && n_out >= S + pad,
+               "layernorm_fwd: bad shape (E must be a multiple of 4)");
   const long long rows = (long long)B * n_out;
   long long grid = (rows + kWarps - 1) / kWarps;
   if (grid > (long long)num_sms() * 8) grid = (long long)num_sms() * 8;
-  ln_fwd_kernel<<<(int)grid, kWarps * 32, 0, STREAM>>>(x, gamma, beta, eps, B, S, E, n_out, pad,
+  ln_fwd_kernel<<<(int)grid, kWarps * 32, 0, STREAM>>>(x, gamma, beta, eps, B, S, x_rows, E, n_out, pad,
                                                        reinterpret_cast<bf16*>(out_bf16), out_f32, mean, rstd);
   MB_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int mirror_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
-                                    int32_t B, int32_t S, int32_t E, int32_t n_out, int32_t pad, float* dx, const float* add,
-                                    float* dgamma, float* dbeta, mirror_stream_t stream) {
+                                    int32_t B, int32_t S, int32_t x_rows, int32_t E, int32_t n_out, int32_t pad, float* dx,
+                                    const float* add, float* dgamma, float* dbeta, mirror_stream_t stream) {
   MB_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
-  MB_CHECK_ARG(B > 0 && S > 0 && E % 4 == 0 && pad >= 0 && n_out >= S + pad, "layernorm_bwd: bad shape");
-  const long long rows = (long long)B * S;
+  MB_CHECK_ARG(B > 0 && S > 0 && x_rows >= S && E % 4 == 0 && pad >= 0 && n_out >= S + pad, "layernorm_bwd: bad shape");
+  const long long rows = (long long)B * x_rows;
   long long grid = (rows + kWarps * 4 - 1) / (kWarps * 4);  // >= 4 rows per warp to amortise the column atomics
   if (grid > (long long)num_sms() * 2) grid = (long long)num_sms() * 2;
   if (grid < 1) grid = 1;
   if (E == 768) {
-    ln_bwd_reg_kernel<6><<<(int)grid, kWarps * 32, 0, STREAM>>>(dy, x, gamma, mean, rstd, B, S, n_out, pad, dx, add, dgamma, dbeta);
+    ln_bwd_reg_kernel<6><<<(int)grid, kWarps * 32, 0, STREAM>>>(dy, x, gamma, mean, rstd, B, S, x_rows, n_out, pad, dx, add, dgamma,
+                                                                dbeta);
   } else {
-    ln_bwd_kernel<<<(int)grid, kWarps * 32, 2 * E * sizeof(float), STREAM>>>(dy, x, gamma, mean, rstd, B, S, E, n_out, pad, dx,
+    ln_bwd_kernel<<<(int)grid, kWarps * 32, 2 * E * sizeof(float), STREAM>>>(dy, x, gamma, mean, rstd, B, S, x_rows, E, n_out, pad, dx,
                                                                              add, dgamma, dbeta);
   }
   MB_LAUNCH_CHECK();

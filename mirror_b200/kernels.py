@@ -231,6 +231,19 @@ def axpy_(dst, src, alpha=1.0):
 
 
 @_op
+def token_fanout_bwd(d_full, d_cls, d_tok, B, T, E, device):
+    """-> [B,T,E] f32 = d_full + (row 0: d_cls) + (rows 1..: d_tok); absent terms are zero (one pass)."""
+    out = torch.empty(B, T, E, device=device, dtype=F32)
+    bs = ld = 0
+    if d_tok is not None:
+        assert d_tok.shape == (B, T - 1, E) and d_tok.stride(2) == 1
+        bs, ld = d_tok.stride(0), d_tok.stride(1)
+    _call("mirror_token_fanout_bwd", _p(_contig(d_full) if d_full is not None else None, F32),
+          _p(_contig(d_cls) if d_cls is not None else None, F32), _p(d_tok, F32), bs, ld, B, T, E, _p(out))
+    return out
+
+
+@_op
 def act_fwd(pre, act, drop_p=0.0, seed=0, want_bf16=True, want_f32=False):
     _contig(pre)
     o16 = torch.empty_like(pre, dtype=BF16) if want_bf16 else None
@@ -327,25 +340,27 @@ def reparam_bwd_(dz, logvar, eps, dmu, dlogvar):
 
 
 @_op
-def layernorm_fwd(x, gamma, beta, eps, n_out=None, pad=0, want_bf16=True, want_f32=False):
-    """x: [B,S,E] f32 -> (y16 [B,n_out,E], y32 [B,n_out,E], mean [B,S], rstd [B,S])."""
-    B, S, E = x.shape
+def layernorm_fwd(x, gamma, beta, eps, n_out=None, pad=0, want_bf16=True, want_f32=False, rows=None):
+    """x: [B,X,E] f32, first S = ``rows`` (default X) rows per slide -> (y16 [B,n_out,E], y32 [B,n_out,E], mean [B,S], rstd [B,S])."""
+    B, X, E = x.shape
+    S = rows or X
     n_out = n_out or S
     y16 = torch.empty(B, n_out, E, device=x.device, dtype=BF16) if want_bf16 else None
     y32 = torch.empty(B, n_out, E, device=x.device, dtype=F32) if want_f32 else None
     mean = torch.empty(B, S, device=x.device, dtype=F32)
     rstd = torch.empty(B, S, device=x.device, dtype=F32)
-    _call("mirror_layernorm_fwd", _p(_contig(x), F32), _p(gamma, F32), _p(beta, F32), eps, B, S, E, n_out, pad, _p(y16), _p(y32),
+    _call("mirror_layernorm_fwd", _p(_contig(x), F32), _p(gamma, F32), _p(beta, F32), eps, B, S, X, E, n_out, pad, _p(y16), _p(y32),
           _p(mean), _p(rstd))
     return y16, y32, mean, rstd
 
 
 @_op
 def layernorm_bwd(dy, x, gamma, mean, rstd, pad, dx, add, dgamma, dbeta):
-    """dy: [B,n_out,E] f32; dx: [B,S,E] f32 = (add or 0) + LN gradient; dgamma/dbeta accumulate."""
-    B, S, E = x.shape
-    _call("mirror_layernorm_bwd", _p(_contig(dy), F32), _p(_contig(x), F32), _p(gamma, F32), _p(mean), _p(rstd), B, S, E, dy.shape[1],
-          pad, _p(_contig(dx), F32), _p(add, F32), _p(dgamma, F32), _p(dbeta, F32))
+    """dy: [B,n_out,E] f32; x, dx: [B,X,E] f32, S = mean.shape[1] <= X rows per slide took part in the forward;
+    dx = (add or 0) + LN gradient (rows >= S: just add / 0); dgamma/dbeta accumulate."""
+    B, X, E = x.shape
+    _call("mirror_layernorm_bwd", _p(_contig(dy), F32), _p(_contig(x), F32), _p(gamma, F32), _p(mean), _p(rstd), B, mean.shape[1], X, E,
+          dy.shape[1], pad, _p(_contig(dx), F32), _p(add, F32), _p(dgamma, F32), _p(dbeta, F32))
 
 
 @_op

@@ -198,8 +198,9 @@ class FeatureTransMIL(nn.Module):
         self.layer2 = TransLayer(dim=embed_dim)
         self.norm = nn.LayerNorm(embed_dim)
 
-    def _tokens(self, h):
-        """fc1+ReLU, wrap pad, cls, layer1, PPEG, layer2, final norm -> ([B,S,E] f32, bf16 copy, add_length)."""
+    def _tokens(self, h, drop_wrap=False):
+        """fc1+ReLU, wrap pad, cls, layer1, PPEG, layer2, final norm -> ([B,S,E] f32, bf16 copy, add_length).
+        ``drop_wrap``: the final norm returns only the N+1 real tokens (contiguous [B,N+1,E]); add_length is then 0."""
         N = h.shape[1]
         Hs = int(np.ceil(np.sqrt(N)))
         add = Hs * Hs - N
@@ -207,6 +208,9 @@ class FeatureTransMIL(nn.Module):
         x = self.layer1(x)
         x = self.pos_layer(x)
         x = self.layer2(x)
+        if drop_wrap:
+            y, y16 = ops.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps, keep=N + 1)
+            return y, y16, 0
         y, y16 = ops.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
         return y, y16, add
 
@@ -313,14 +317,14 @@ class FeatureTransMILHybrid(FeatureTransMIL):
             nn.init.constant_(m.weight, 1.0)
 
     def forward_encoder(self, h):
-        y, y16, add = self._tokens(h)
-        S = y.shape[1]
-        self._emb16 = y16[:, : S - add, :]  # bf16 copy for the decoders of THIS forward (not a parameter/buffer)
-        return y[:, : S - add, :]
+        y, y16, _ = self._tokens(h, drop_wrap=True)  # LayerNorm + `h[:, :-add_length]` (models/mirror.py:372) in one pass
+        self._emb16 = y16  # bf16 copy for the decoders of THIS forward (not a parameter/buffer)
+        return y
 
-    def forward_alignment_head(self, h):
+    def forward_alignment_head(self, h, cls=None):
         eps = 1e-6 if h.dtype == torch.float16 else 1e-12
-        return ops.linear(ops.l2_normalize(h[:, 0, :], eps), self.alignment_head.weight, self.alignment_head.bias)
+        cls = h[:, 0, :] if cls is None else cls
+        return ops.linear(ops.l2_normalize(cls, eps), self.alignment_head.weight, self.alignment_head.bias)
 
     def forward_retention_head(self, h, mask_ratio, noise=None):
         B, T, E = h.shape  # T = N + 1
@@ -338,10 +342,10 @@ class FeatureTransMILHybrid(FeatureTransMIL):
             r = blk(r)
         r, r16 = ops.layer_norm(r, self.retention_norm.weight, self.retention_norm.bias, self.retention_norm.eps)
         r = ops.linear(r, self.retention_head.weight, self.retention_head.bias, x16=r16)
-        return r[:, 1:, :], mask
+        return ops.drop_first_token(r), mask
 
-    def forward_decoders(self, h, mask_ratio, noise=None):
-        a = self.forward_alignment_head(h)
+    def forward_decoders(self, h, mask_ratio, noise=None, cls=None):
+        a = self.forward_alignment_head(h, cls)
         r, mask = self.forward_retention_head(h, mask_ratio, noise)
         self._emb16 = None
         return a, r, mask
@@ -428,13 +432,13 @@ class MIRROR(nn.Module):
 
     def forward(self, wsi_emb, rna_emb, wsi_mask_ratio: float = 0.75, rna_mask_ratio: float = 0.75, noise=None) -> Tuple[torch.Tensor, ...]:
         noise = noise or {}
-        wsi_emb = self.wsi_encoder.forward_encoder(wsi_emb)
-        wa, wr, wm = self.wsi_encoder.forward_decoders(wsi_emb, wsi_mask_ratio, noise.get("wsi_mask"))
-        wsi_retention_target = wsi_emb[:, 1:, :]
+        # the encoder output is read whole (retention decoder), as its cls row (alignment head, style encoder) and as its
+        # patch rows (retention target): one fan-out node, so that the backward merges the three gradients in one pass
+        wsi_cls, wsi_emb, wsi_retention_target = ops.token_fanout(self.wsi_encoder.forward_encoder(wsi_emb))
+        wa, wr, wm = self.wsi_encoder.forward_decoders(wsi_emb, wsi_mask_ratio, noise.get("wsi_mask"), cls=wsi_cls)
         rna_emb = self.rna_encoder.forward_encoder(rna_emb)
         ra, rr, rm = self.rna_encoder.forward_decoders(rna_emb, rna_mask_ratio, noise.get("rna_mask"))
-        ws, wmu, wls, rs, rmu, rls = self.forward_style_clustering(wsi_emb[:, 0, :], rna_emb, noise.get("wsi_eps"),
-                                                                   noise.get("rna_eps"))
+        ws, wmu, wls, rs, rmu, rls = self.forward_style_clustering(wsi_cls, rna_emb, noise.get("wsi_eps"), noise.get("rna_eps"))
         return (wa, wr, wsi_retention_target, wm, ws, wmu, wls, ra, rr, rna_emb, rm, rs, rmu, rls, self.logit_scale.exp())
 
 

@@ -191,19 +191,27 @@ def stack_rows(a, b):
 
 # ----------------------------------------------------------------------------------------------
 class LayerNormFn(Function):
-    """nn.LayerNorm over the last dim; returns (y f32, y bf16 copy [non-differentiable])."""
+    """nn.LayerNorm over the last dim; returns (y f32, y bf16 copy [non-differentiable]).  ``keep``: x is [B,X,E] and only
+    the first ``keep`` tokens of every slide are normalised and returned ([B,keep,E], contiguous) -- LayerNorm followed by
+    the reference's ``h[:, :-add_length]`` (models/mirror.py:372) without materialising the dropped rows."""
 
     @staticmethod
     @_cfwd
-    def forward(ctx, x, weight, bias, eps):
+    def forward(ctx, x, weight, bias, eps, keep=None):
         E = x.shape[-1]
-        x3 = x.contiguous().view(1, -1, E)
-        y16, y32, mean, rstd = K.layernorm_fwd(x3, weight, bias, eps, want_bf16=True, want_f32=True)
-        ctx.save_for_backward(x3, weight, mean, rstd)
         ctx.shape = tuple(x.shape)
-        y16 = y16.view(ctx.shape)
+        if keep is not None and keep < x.shape[1]:
+            x3 = x.contiguous()
+            out_shape = (x.shape[0], keep, E)
+        else:
+            keep = None
+            x3 = x.contiguous().view(1, -1, E)
+            out_shape = ctx.shape
+        y16, y32, mean, rstd = K.layernorm_fwd(x3, weight, bias, eps, want_bf16=True, want_f32=True, rows=keep)
+        ctx.save_for_backward(x3, weight, mean, rstd)
+        y16 = y16.view(out_shape)
         ctx.mark_non_differentiable(y16)
-        return y32.view(ctx.shape), y16
+        return y32.view(out_shape), y16
 
     @staticmethod
     @once_differentiable
@@ -214,12 +222,46 @@ class LayerNormFn(Function):
         dx = torch.empty_like(x3)
         dg = torch.zeros(E, device=dy.device, dtype=F32)
         db = torch.zeros(E, device=dy.device, dtype=F32)
-        K.layernorm_bwd(dy.contiguous().view(1, -1, E), x3, weight, mean, rstd, 0, dx, None, dg, db)
-        return dx.view(ctx.shape), dg, db, None
+        K.layernorm_bwd(dy.contiguous().view(x3.shape[0], -1, E), x3, weight, mean, rstd, 0, dx, None, dg, db)
+        return dx.view(ctx.shape), dg, db, None, None
 
 
-def layer_norm(x, weight, bias, eps):
-    return LayerNormFn.apply(x, weight, bias, eps)
+class TokenFanoutFn(Function):
+    """h [B,T,E] -> (cls = h[:,0,:] (copy), h, h[:,1:,:] (view)).  The three ways the model reads its encoder output
+    (models/mirror.py:889-905); the backward merges the three gradients in one pass instead of autograd's
+    zeros + slice-copy + add chain over the full token matrix."""
+
+    @staticmethod
+    @_cfwd
+    def forward(ctx, h):
+        h = h.contiguous()
+        ctx.shape = tuple(h.shape)
+        cls = torch.empty(h.shape[0], h.shape[2], device=h.device, dtype=F32)
+        K.copy_rows_(h[:, 0, :], cls)
+        return cls, h.view_as(h), h[:, 1:, :]
+
+    @staticmethod
+    @once_differentiable
+    @_cbwd
+    def backward(ctx, d_cls, d_full, d_tok):
+        B, T, E = ctx.shape
+        dev = next(t for t in (d_cls, d_full, d_tok) if t is not None).device
+        if d_tok is not None and d_tok.stride(2) != 1:
+            d_tok = d_tok.contiguous()
+        return K.token_fanout_bwd(d_full, d_cls, d_tok, B, T, E, dev)
+
+
+def token_fanout(h):
+    return TokenFanoutFn.apply(h)
+
+
+def drop_first_token(r):
+    """r[:, 1:, :] whose backward writes the padded gradient in one pass (no zeros + slice copy)."""
+    return TokenFanoutFn.apply(r)[2]
+
+
+def layer_norm(x, weight, bias, eps, keep=None):
+    return LayerNormFn.apply(x, weight, bias, eps, keep)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -176,6 +176,14 @@ class Emu:
         dst += alpha * src
         return dst
 
+    def token_fanout_bwd(self, d_full, d_cls, d_tok, B, T, E, device):
+        out = torch.zeros(B, T, E) if d_full is None else d_full.clone()
+        if d_cls is not None:
+            out[:, 0] += d_cls
+        if d_tok is not None:
+            out[:, 1:] += d_tok
+        return out
+
     def act_fwd(self, pre, act, drop_p=0.0, seed=0, want_bf16=True, want_f32=False):
         v = _act(pre, act)
         if drop_p > 0:
@@ -252,8 +260,10 @@ class Emu:
         dlogvar += dz * eps * 0.5 * torch.exp(0.5 * logvar)
 
     # ------------------------------------------------------- norms / softmax
-    def layernorm_fwd(self, x, gamma, beta, eps, n_out=None, pad=0, want_bf16=True, want_f32=False):
-        B, S, E = x.shape
+    def layernorm_fwd(self, x, gamma, beta, eps, n_out=None, pad=0, want_bf16=True, want_f32=False, rows=None):
+        B, X, E = x.shape
+        S = rows or X
+        x = x[:, :S]
         n_out = n_out or S
         mean = x.mean(-1)
         var = x.var(-1, unbiased=False)
@@ -264,11 +274,13 @@ class Emu:
         return (full.to(BF16) if want_bf16 else None), (full if want_f32 else None), mean, rstd
 
     def layernorm_bwd(self, dy, x, gamma, mean, rstd, pad, dx, add, dgamma, dbeta):
-        B, S, E = x.shape
+        B, X, E = x.shape
+        S = mean.shape[1]
         g = dy[:, pad:pad + S]
-        xh = (x - mean[..., None]) * rstd[..., None]
+        xh = (x[:, :S] - mean[..., None]) * rstd[..., None]
         gg = g * gamma
-        d = rstd[..., None] * (gg - gg.mean(-1, keepdim=True) - xh * (gg * xh).mean(-1, keepdim=True))
+        d = torch.zeros(B, X, E)
+        d[:, :S] = rstd[..., None] * (gg - gg.mean(-1, keepdim=True) - xh * (gg * xh).mean(-1, keepdim=True))
         dgamma += (g * xh).sum((0, 1))
         dbeta += g.sum((0, 1))
         dx.copy_(d + add if add is not None else d)

@@ -379,3 +379,28 @@ def test_gemm_bulk_store_epilogue(M, N, Kd, outs):
     if o16 is not None:
         close(o16, o16c, 8e-3, "bulk-store bf16")
         assert (o16s[:, M] == 7.0).all(), "rows past M must be clipped"
+
+
+@pytest.mark.parametrize("B,X,S,E", [(3, 40, 33, 768), (2, 19, 17, 192)])
+def test_layernorm_leading_rows_only(B, X, S, E):
+    # final norm of the WSI encoder: only the first S of X rows per slide are normalised / receive a gradient
+    x, g, b = rn(B, X, E, scale=2.0) + 0.5, 1 + 0.1 * rn(E, seed=1), 0.1 * rn(E, seed=2)
+    both("layernorm_fwd", (x, g, b, 1e-5), {"want_bf16": True, "want_f32": True, "rows": S}, tol=3e-6)
+    xs = x[:, :S]
+    mean, rstd = xs.mean(-1), torch.rsqrt(xs.var(-1, unbiased=False) + 1e-5)
+    dy = rn(B, S, E, seed=3)
+    for add in (None, rn(B, X, E, seed=4)):
+        both("layernorm_bwd", (dy, x, g, mean, rstd, 0, torch.full((B, X, E), 9.0), add, torch.zeros(E), torch.zeros(E)), tol=2e-5,
+             check_args=(6, 8, 9))
+
+
+def test_token_fanout_bwd():
+    B, T, E = 3, 21, 192
+    full, cls = rn(B, T, E, seed=1), rn(B, E, seed=2)
+    tok_store = rn(B, T + 3, E, seed=3)
+    for f, c, t in ((full, cls, tok_store[:, 4:, :]), (None, None, tok_store[:, 4:, :]), (full, None, None), (None, cls, None)):
+        want = EMU.token_fanout_bwd(f, c, t, B, T, E, "cpu")
+        dev = lambda v: None if v is None else v.cuda()
+        td = tok_store.cuda()[:, 4:, :] if t is not None else None  # strided view on the device too
+        got = K.token_fanout_bwd(dev(f), dev(c), td, B, T, E, "cuda")
+        close(got, want, 1e-6, "token_fanout_bwd")
