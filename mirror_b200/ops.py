@@ -200,6 +200,7 @@ class LayerNormFn(Function):
     def forward(ctx, x, weight, bias, eps, keep=None):
         E = x.shape[-1]
         ctx.shape = tuple(x.shape)
+        ctx.set_materialize_grads(False)  # the bf16 copy never has a gradient: no zero-filled stand-in for it
         if keep is not None and keep < x.shape[1]:
             x3 = x.contiguous()
             out_shape = (x.shape[0], keep, E)
@@ -217,6 +218,8 @@ class LayerNormFn(Function):
     @once_differentiable
     @_cbwd
     def backward(ctx, dy, _unused):
+        if dy is None:
+            return None, None, None, None, None
         x3, weight, mean, rstd = ctx.saved_tensors
         E = x3.shape[-1]
         dx = torch.empty_like(x3)
@@ -236,6 +239,7 @@ class TokenFanoutFn(Function):
     def forward(ctx, h):
         h = h.contiguous()
         ctx.shape = tuple(h.shape)
+        ctx.set_materialize_grads(False)  # unused outputs must not cost a zero-filled token matrix
         cls = torch.empty(h.shape[0], h.shape[2], device=h.device, dtype=F32)
         K.copy_rows_(h[:, 0, :], cls)
         return cls, h.view_as(h), h[:, 1:, :]
@@ -245,6 +249,8 @@ class TokenFanoutFn(Function):
     @_cbwd
     def backward(ctx, d_cls, d_full, d_tok):
         B, T, E = ctx.shape
+        if d_cls is None and d_full is None and d_tok is None:
+            return None
         dev = next(t for t in (d_cls, d_full, d_tok) if t is not None).device
         if d_tok is not None and d_tok.stride(2) != 1:
             d_tok = d_tok.contiguous()
@@ -471,7 +477,9 @@ class NystromLayerFn(Function):
         mm = (B, hd, m, m)
 
         # ---- to_out: y = h + drop(o16[pad:] @ Wout^T + b)
-        dyd = torch.zeros(B, n, E, device=dev, dtype=BF16) if pad else torch.empty(B, n, E, device=dev, dtype=BF16)
+        dyd = torch.empty(B, n, E, device=dev, dtype=BF16)
+        if pad:
+            dyd[:, :pad, :].zero_()  # the zero rows the sequence was front-padded with
         K.act_bwd(dy, None, K.ACT_NONE, drop_p, seed, out16=dyd[:, pad:, :])
         do16 = torch.empty(B, n, E, device=dev, dtype=BF16)
         K.gemm(dyd.view(B * n, E), _T(wout16), out_bf16=do16.view(B * n, E))

@@ -39,7 +39,8 @@ def timed(name, f, bytes_=0):
     print(f"{name:42s} {ms:8.3f} ms   {bytes_ / ms / 1e9 if bytes_ else 0:7.2f} TB/s", flush=True)
 
 
-for tag, (a, b) in ({"strided": (q, kl)} if ONCE else {"strided": (q, kl), "contig": (qc, klc)}).items():
+ONLY = os.environ.get("PROBE_ONLY", "")
+for tag, (a, b) in ({} if ONLY == "pinv" else {"strided": (q, kl)} if ONCE else {"strided": (q, kl), "contig": (qc, klc)}).items():
     o32 = torch.empty(B, hd, n, m, device="cuda")
     o16 = torch.empty(B, hd, n, m, device="cuda", dtype=torch.bfloat16)
     st = K.softmax_stats((B, hd), n, m, "cuda")
@@ -56,6 +57,9 @@ z = torch.randn(B, hd, m, m, device="cuda", generator=g).to(torch.bfloat16)
 zo = torch.empty_like(z)
 timed("pinv 384^3 NN bf16 + res", lambda: K.gemm(z, z.transpose(-1, -2), out_bf16=zo, res=z), 2 * B * hd * m * m * 2)
 timed("pinv 384^3 NT bf16", lambda: K.gemm(z, z, out_bf16=zo, alpha=0.25), B * hd * m * m * 2)
+if ONLY == "pinv":
+    timed("pinv 384^3 multi3", lambda: K.gemm(z, z, more=[(z, z), (z.transpose(-1, -2), z.transpose(-1, -2))], out_bf16=zo, res=z, res2=z))
+    sys.exit(0)
 # s3: [m, n] rows = landmarks, columns = tokens
 ql, k = heads(lm, 0), heads(qkv, E)
 o16 = torch.empty(B, hd, m, n, device="cuda", dtype=torch.bfloat16)

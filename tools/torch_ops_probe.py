@@ -29,7 +29,8 @@ def step():
 for _ in range(2):
     step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True,
+             experimental_config=torch._C._profiler._ExperimentalConfig(verbose=True)) as prof:
     step()
     torch.cuda.synchronize()
 rows = []
@@ -37,7 +38,7 @@ for e in prof.key_averages(group_by_input_shape=True, group_by_stack_n=6):
     t = getattr(e, "device_time_total", 0) or getattr(e, "cuda_time_total", 0)
     self_t = getattr(e, "self_device_time_total", 0) or getattr(e, "self_cuda_time_total", 0)
     if e.key.startswith("aten::") and self_t > 20:
-        stack = [s for s in e.stack if "mirror_b200" in s or "bench" in s or "losses" in s]
+        stack = [s for s in e.stack if "mirror_b200" in s or "bench" in s or "losses" in s] or list(e.stack)[:4]
         rows.append((self_t, e.count, e.key, str(e.input_shapes)[:90], " <- ".join(s.split("/")[-1][:60] for s in stack[:3])))
 rows.sort(reverse=True)
 print(f"{'self us':>9s} {'n':>4s}  op / shapes / python site")
