@@ -27,17 +27,17 @@ struct KParams {
   int a_b1, a_b2, b_b1, b_b2;  // 0 where an operand is broadcast along that batch dim (batch stride 0), else 1
 };
 
-constexpr int kSinkBytes = 6144;  // per epilogue warp: one 32x32 f32 box (4 KB, 128B swizzle) + one bf16 box (2 KB, 64B swizzle)
+constexpr int kSinkBytes = 4096;  // per epilogue warp: one 32x32 f32 box (4 KB, 128B swizzle) or two bf16 boxes (2 KB, 64B swizzle)
 
 // TMAS: the epilogue hands finished 32x32 chunks to TMA (bulk tensor stores out of a per-warp staging box) instead of
-// storing from registers; one pipeline stage is traded for the staging boxes.
+// storing from registers.  The 32 KB of boxes fit beside the full pipeline for BN = 128 / 256; BN = 192 gives up a stage.
 template <int BN, bool TMAS = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = TMAS ? kEpiWarps * kSinkBytes : 0;
-  static constexpr int STAGES = ((BN == 256) ? 4 : (BN == 192 ? 5 : 6)) - (TMAS ? 1 : 0);
+  static constexpr int STAGES = ((BN == 256) ? 4 : (BN == 192 ? 5 : 6)) - ((TMAS && BN == 192) ? 1 : 0);
   static constexpr int TMEM_COLS = (kAccStages * BN <= 256) ? 256 : 512;  // power of two >= 2 accumulator stages
   static constexpr int BAR_BYTES = (2 * STAGES + 2 * kAccStages) * 8 + 16;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
@@ -101,10 +101,8 @@ struct Sink {
 
 // f32 chunk: lane = row, 8 pieces of 16 B.  128B swizzle: piece j of row r lives at r*128 + ((j ^ (r & 7)) * 16).
 __device__ __forceinline__ void sink_tma_f32(Sink& s, const uint4 (&pc)[8], bool both, int b1, int b2, int row0, int col0, int lane) {
-  if (lane == 0) {
-    if (both) bulk_wait_read<1>();  // the bf16 box of the previous chunk may still be in flight
-    else bulk_wait_read<0>();
-  }
+  (void)both;
+  if (lane == 0) bulk_wait_read<0>();  // the box (shared with the bf16 boxes) must have been read out
   __syncwarp();
   const uint32_t base = s.buf + lane * 128;
 #pragma unroll
@@ -119,9 +117,12 @@ __device__ __forceinline__ void sink_tma_f32(Sink& s, const uint4 (&pc)[8], bool
 
 // bf16 chunk: 4 pieces of 16 B per row.  64B swizzle: piece j of row r lives at r*64 + ((j ^ ((r >> 1) & 3)) * 16).
 __device__ __forceinline__ void sink_tma_bf16(Sink& s, const uint4 (&pc)[4], bool both, int b1, int b2, int row0, int col0, int lane) {
-  if (lane == 0) bulk_wait_read<1>();  // two boxes in rotation (or the f32 box of this chunk): one group may stay in flight
+  if (lane == 0) {
+    if (both) bulk_wait_read<0>();  // the f32 box of this chunk occupies the same bytes
+    else bulk_wait_read<1>();       // two boxes in rotation: one group may stay in flight
+  }
   __syncwarp();
-  const uint32_t box = s.buf + (both ? 4096 : (s.flip ? 2048 : 0));
+  const uint32_t box = s.buf + (s.flip ? 2048 : 0);
   s.flip ^= 1;
   const uint32_t base = box + lane * 64;
 #pragma unroll

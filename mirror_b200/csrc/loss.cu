@@ -104,6 +104,75 @@ __global__ void masked_mse_fwd_kernel(const float* __restrict__ a, long long a_b
     atomicAdd(scratch + 1, den);
   }
 }
+// The same two kernels for E % 4 == 0 (the WSI retention term: 2048 x 768 tokens per slide): one warp per token row,
+// float4 lanes, the (slide, token) split and the mask test once per row -- the scalar versions spend their time in
+// 64-bit div/mod per element (2.8 TB/s); unmasked rows (25 %) are never read.
+__global__ void __launch_bounds__(256)
+masked_mse_fwd_rows_kernel(const float* __restrict__ a, long long a_bs, const float* __restrict__ b, long long b_bs,
+                           const float* __restrict__ mask, int B, int T, int E, float* __restrict__ scratch) {
+  __shared__ float sh[32];
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const long long rows = (long long)B * T;
+  float num = 0.f, den = 0.f;
+  for (long long row = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+    const float m = mask[row];
+    if (lane == 0) den += m;
+    if (m == 0.f) continue;
+    const long long bb = row / T;
+    const int t = (int)(row - bb * T);
+    const float* ar = a + bb * a_bs + (long long)t * E;
+    const float* br = b + bb * b_bs + (long long)t * E;
+    float acc = 0.f;
+    for (int c = lane * 4; c < E; c += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(ar + c);
+      const float4 y = *reinterpret_cast<const float4*>(br + c);
+      const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+      acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    num += m * acc;
+  }
+  num = block_sum(num, sh);
+  den = block_sum(den, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(scratch, num / E);
+    atomicAdd(scratch + 1, den);
+  }
+}
+__global__ void __launch_bounds__(256)
+masked_mse_bwd_rows_kernel(const float* __restrict__ a, long long a_bs, const float* __restrict__ b, long long b_bs,
+                           const float* __restrict__ mask, int B, int T, int E, const float* __restrict__ scratch,
+                           const float* __restrict__ gout, float gw, float* __restrict__ da, long long da_bs, int acc_a,
+                           float* __restrict__ db, long long db_bs, int acc_b) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const long long rows = (long long)B * T;
+  const float k = *gout * gw * 2.f / (E * scratch[1]);
+  for (long long row = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+    const float m = mask[row];
+    if (m == 0.f && (!da || acc_a) && (!db || acc_b)) continue;  // nothing to add
+    const long long bb = row / T;
+    const int t = (int)(row - bb * T);
+    const long long ro = (long long)t * E;
+    const float km = k * m;
+    for (int c = lane * 4; c < E; c += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m != 0.f) {
+        const float4 x = *reinterpret_cast<const float4*>(a + bb * a_bs + ro + c);
+        const float4 y = *reinterpret_cast<const float4*>(b + bb * b_bs + ro + c);
+        v = make_float4(km * (x.x - y.x), km * (x.y - y.y), km * (x.z - y.z), km * (x.w - y.w));
+      }
+      if (da) {
+        float4* p = reinterpret_cast<float4*>(da + bb * da_bs + ro + c);
+        if (acc_a) { const float4 o = *p; *p = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w); }
+        else *p = v;
+      }
+      if (db) {
+        float4* p = reinterpret_cast<float4*>(db + bb * db_bs + ro + c);
+        if (acc_b) { const float4 o = *p; *p = make_float4(o.x - v.x, o.y - v.y, o.z - v.z, o.w - v.w); }
+        else *p = make_float4(-v.x, -v.y, -v.z, -v.w);
+      }
+    }
+  }
+}
 __global__ void ratio_kernel(const float* __restrict__ scratch, float* __restrict__ out) { *out = scratch[0] / scratch[1]; }
 // da (+)= g * mask * 2 (a-b) / (E * den) ; db (+)= -that
 __global__ void masked_mse_bwd_kernel(const float* __restrict__ a, long long a_bs, const float* __restrict__ b, long long b_bs,
@@ -243,11 +312,22 @@ extern "C" int mirror_clip_loss_bwd(const float* raw, int32_t B, const float* sc
 }
 
 /* scratch: 2 floats, zeroed here */
+// float4 rows: E and every batch stride a multiple of 4 elements, bases 16-byte aligned, rows wide enough for a warp
+static bool mse_rows_ok(int E, const float* a, long long a_bs, const float* b, long long b_bs, const float* da, long long da_bs,
+                        const float* db, long long db_bs) {
+  auto al = [](const float* p, long long bs) { return !p || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && bs % 4 == 0); };
+  return E % 4 == 0 && E >= 128 && al(a, a_bs) && al(b, b_bs) && al(da, da_bs) && al(db, db_bs);
+}
+
 extern "C" int mirror_masked_mse_fwd(const float* a, int64_t a_bs, const float* b, int64_t b_bs, const float* mask, int32_t B,
                                      int32_t T, int32_t E, float* scratch, float* out, mirror_stream_t stream) {
   MB_CHECK_ARG(a && b && mask && scratch && out && B > 0 && T > 0 && E > 0, "masked_mse_fwd: bad args");
   MB_CUDA(cudaMemsetAsync(scratch, 0, 8, STREAM));
-  masked_mse_fwd_kernel<<<ew_grid((long long)B * T * E, 256 * 4), 256, 0, STREAM>>>(a, a_bs, b, b_bs, mask, B, T, E, scratch);
+  if (mse_rows_ok(E, a, a_bs, b, b_bs, nullptr, 0, nullptr, 0)) {
+    masked_mse_fwd_rows_kernel<<<ew_grid((long long)B * T, 8), 256, 0, STREAM>>>(a, a_bs, b, b_bs, mask, B, T, E, scratch);
+  } else {
+    masked_mse_fwd_kernel<<<ew_grid((long long)B * T * E, 256 * 4), 256, 0, STREAM>>>(a, a_bs, b, b_bs, mask, B, T, E, scratch);
+  }
   MB_LAUNCH_CHECK();
   ratio_kernel<<<1, 1, 0, STREAM>>>(scratch, out);
   MB_LAUNCH_CHECK();
@@ -257,8 +337,13 @@ extern "C" int mirror_masked_mse_bwd(const float* a, int64_t a_bs, const float* 
                                      int32_t T, int32_t E, const float* scratch, const float* gout, float gw, float* da,
                                      int64_t da_bs, int32_t acc_a, float* db, int64_t db_bs, int32_t acc_b, mirror_stream_t stream) {
   MB_CHECK_ARG(a && b && mask && scratch && gout && (da || db) && B > 0 && T > 0 && E > 0, "masked_mse_bwd: bad args");
-  masked_mse_bwd_kernel<<<ew_grid((long long)B * T * E, 256 * 2), 256, 0, STREAM>>>(a, a_bs, b, b_bs, mask, B, T, E, scratch, gout,
-                                                                                  gw, da, da_bs, acc_a, db, db_bs, acc_b);
+  if (mse_rows_ok(E, a, a_bs, b, b_bs, da, da_bs, db, db_bs)) {
+    masked_mse_bwd_rows_kernel<<<ew_grid((long long)B * T, 8), 256, 0, STREAM>>>(a, a_bs, b, b_bs, mask, B, T, E, scratch, gout, gw, da,
+                                                                             da_bs, acc_a, db, db_bs, acc_b);
+  } else {
+    masked_mse_bwd_kernel<<<ew_grid((long long)B * T * E, 256 * 2), 256, 0, STREAM>>>(a, a_bs, b, b_bs, mask, B, T, E, scratch, gout,
+                                                                                    gw, da, da_bs, acc_a, db, db_bs, acc_b);
+  }
   MB_LAUNCH_CHECK();
   return 0;
 }

@@ -134,8 +134,10 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
 // Same contract, E == ITERS*128: the per-column partial sums of dgamma / dbeta stay in registers (lane owns columns
 // lane*4 + 128*i), are combined across the 8 warps through shared memory once per CTA and leave as one global atomic
 // per column and CTA -- no shared-memory atomics in the row loop.
+// 4-warp CTAs, three per SM (166 registers per thread): 12 rows in flight per SM instead of the 8 of one 8-warp CTA.
+constexpr int kRegWarps = 4;
 template <int ITERS>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kRegWarps * 32, 3)
 ln_bwd_reg_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                   const float* __restrict__ mean, const float* __restrict__ rstd, int B, int S, int X, int n_out, int pad,
                   float* dx, const float* add, float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -152,7 +154,7 @@ ln_bwd_reg_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
     ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const long long rows = (long long)B * X;
-  for (long long ri = blockIdx.x * (long long)kWarps + (threadIdx.x >> 5); ri < rows; ri += (long long)gridDim.x * kWarps) {
+  for (long long ri = blockIdx.x * (long long)kRegWarps + (threadIdx.x >> 5); ri < rows; ri += (long long)gridDim.x * kRegWarps) {
     const int b = (int)(ri / X), s = (int)(ri % X);
     if (s >= S) {
 #pragma unroll
@@ -331,7 +333,10 @@ extern "C" int mirror_layernorm_bwd(const float* dy, const float* x, const float
   if (grid > (long long)num_sms() * 2) grid = (long long)num_sms() * 2;
   if (grid < 1) grid = 1;
   if (E == 768) {
-    ln_bwd_reg_kernel<6><<<(int)grid, kWarps * 32, 0, STREAM>>>(dy, x, gamma, mean, rstd, B, S, x_rows, n_out, pad, dx, add, dgamma,
+    long long rgrid = (rows + kRegWarps * 4 - 1) / (kRegWarps * 4);
+    if (rgrid > (long long)num_sms() * 3) rgrid = (long long)num_sms() * 3;
+    if (rgrid < 1) rgrid = 1;
+    ln_bwd_reg_kernel<6><<<(int)rgrid, kRegWarps * 32, 0, STREAM>>>(dy, x, gamma, mean, rstd, B, S, x_rows, n_out, pad, dx, add, dgamma,
                                                                 dbeta);
   } else {
     ln_bwd_kernel<<<(int)grid, kWarps * 32, 2 * E * sizeof(float), STREAM>>>(dy, x, gamma, mean, rstd, B, S, x_rows, E, n_out, pad, dx,

@@ -252,8 +252,9 @@ def test_clip_loss_kernels(B, wr, wc):
              check_args=(7,))
 
 
-def test_masked_mse_strided():
-    B, T, E = 3, 20, 32
+@pytest.mark.parametrize("E", [32, 192, 768, 1])  # 192 / 768: warp-per-row float4 kernels; 32 / 1: scalar kernels
+def test_masked_mse_strided(E):
+    B, T = 3, 20
     big = rn(B, T + 1, E)
     a, b = rn(B, T + 1, E, seed=1)[:, 1:, :], big[:, 1:, :]
     mask = (torch.rand(B, T, generator=torch.Generator().manual_seed(2)) > 0.25).float()
