@@ -44,3 +44,18 @@ rows.sort(reverse=True)
 print(f"{'self us':>9s} {'n':>4s}  op / shapes / python site")
 for r in rows[:45]:
     print(f"{r[0]:9.0f} {r[1]:4d}  {r[2]:28s} {r[3]}\n{'':16s}{r[4]}")
+
+# ---- device-side view of the same step: time per kernel name (CUDA-event free, from the profiler's kernel records)
+from collections import defaultdict  # noqa: E402
+
+agg = defaultdict(lambda: [0, 0.0])
+for ev in prof.events():
+    if getattr(ev, "device_type", None) is not None and str(ev.device_type).endswith("CUDA") and ev.name and not ev.name.startswith("aten::"):
+        dt = getattr(ev, "device_time", 0) or getattr(ev, "cuda_time", 0)
+        name = ev.name.split("(")[0].replace("void ", "").replace("mb::(anonymous namespace)::", "")
+        agg[name][0] += 1
+        agg[name][1] += dt
+tot = sum(v[1] for v in agg.values())
+print(f"\n{len(agg)} kernel names, {tot / 1e3:.2f} ms of device time in the step")
+for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:48]:
+    print(f"{t / 1e3:8.3f} ms {c:5d}  {name[:110]}")
