@@ -93,8 +93,11 @@ typedef struct {
  *   SOFTMAX       out = exp(alpha*acc - max) / sum          (bf16 and/or f32)
  *   ROWDOT        stats[part].x = sum_j acc_j * P_j over the part's columns, P = `res` (bf16 probabilities)
  *   SOFTMAX_BWD   out = alpha * P * (acc - sum of partial dots)   (bf16): d logits-before-alpha
+ *   SOFTMAX_BWD_DOT  the same with the row dots given directly: stats = [batch2,batch1,M] f32.  When the probabilities
+ *                 fed a product O = P V, sum_j G_ij P_ij = dO_i . O_i (mirror_rowdot_bf16), so the ROWDOT pass is not needed.
  * Needs N % 32 == 0; alpha is the only other epilogue term honoured. */
-enum { MIRROR_GEMM_NORMAL = 0, MIRROR_GEMM_ROWSTATS = 1, MIRROR_GEMM_SOFTMAX = 2, MIRROR_GEMM_ROWDOT = 3, MIRROR_GEMM_SOFTMAX_BWD = 4 };
+enum { MIRROR_GEMM_NORMAL = 0, MIRROR_GEMM_ROWSTATS = 1, MIRROR_GEMM_SOFTMAX = 2, MIRROR_GEMM_ROWDOT = 3, MIRROR_GEMM_SOFTMAX_BWD = 4,
+       MIRROR_GEMM_SOFTMAX_BWD_DOT = 5 };
 int mirror_gemm_nparts(int32_t N);
 
 int mirror_gemm_bf16(const mirror_gemm_args* args, mirror_stream_t stream);
@@ -124,6 +127,8 @@ int mirror_cast_split3(const float* src, int64_t rows, int32_t cols, int64_t lds
                        int32_t stack_rows, int32_t order, mirror_stream_t stream);
 /* dst[r,0:cols] = src[r,0:cols] with row strides: gathers `wsi_emb[:, 0, :]` (models/mirror.py:896) into a dense block */
 int mirror_copy_rows_f32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd, mirror_stream_t stream);
+/* out[r] = sum_c a[r,c]*b[r,c] over contiguous bf16 rows (cols % 8 == 0): the row dots dO.O of a softmax backward */
+int mirror_rowdot_bf16(const void* a, const void* b, int64_t rows, int32_t cols, float* out, mirror_stream_t stream);
 /* dst += alpha*src  (gradient accumulation of the autograd graph) */
 int mirror_axpy_f32(float* dst, const float* src, int64_t n, float alpha, mirror_stream_t stream);
 /* Gradient of the encoder output h:[B,T,E] that the model reads three ways (models/mirror.py:889-905: the whole matrix for the

@@ -283,6 +283,8 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
     invS = 1.f / ssum;
   } else if (row_ok && e.mode == MIRROR_GEMM_SOFTMAX_BWD) {
     for (int i = 0; i < e.nparts; ++i) dot += stats[i].x;
+  } else if (row_ok && e.mode == MIRROR_GEMM_SOFTMAX_BWD_DOT) {
+    dot = e.stats[(long long)(b2 * e.batch1 + b1) * e.M + row];
   }
   mbar_wait(tfull_bar, aphase);
   tc_fence_after();
@@ -1077,9 +1079,9 @@ int fill_epi(const mirror_gemm_args* g, Epi* e) {
   e->res_row_div = g->res_row_div > 1 ? g->res_row_div : 1;
   e->mode = g->mode; e->stats = g->stats; e->nparts = 0;
   if (g->mode != MIRROR_GEMM_NORMAL) {
-    MB_CHECK_ARG(g->mode >= 1 && g->mode <= 4 && g->stats && g->N % 32 == 0 && g->split_k <= 1 && g->res_row_div <= 1,
+    MB_CHECK_ARG(g->mode >= 1 && g->mode <= 5 && g->stats && g->N % 32 == 0 && g->split_k <= 1 && g->res_row_div <= 1,
                  "gemm: softmax modes need stats, N %% 32 == 0 and no split-K");
-    MB_CHECK_ARG((g->mode != MIRROR_GEMM_ROWDOT && g->mode != MIRROR_GEMM_SOFTMAX_BWD) || (g->res && g->res_is_bf16),
+    MB_CHECK_ARG(g->mode < MIRROR_GEMM_ROWDOT || (g->res && g->res_is_bf16),
                  "gemm: ROWDOT / SOFTMAX_BWD read the bf16 probabilities through `res`");
     MB_CHECK_ARG(g->mode == MIRROR_GEMM_ROWSTATS || g->mode == MIRROR_GEMM_ROWDOT || g->out_f32 || g->out_bf16, "gemm: no output");
   }

@@ -66,7 +66,7 @@ def _operands(g, a, b):
     return B2, B1, M, N
 
 
-GEMM_NORMAL, GEMM_ROWSTATS, GEMM_SOFTMAX, GEMM_ROWDOT, GEMM_SOFTMAX_BWD = range(5)
+GEMM_NORMAL, GEMM_ROWSTATS, GEMM_SOFTMAX, GEMM_ROWDOT, GEMM_SOFTMAX_BWD, GEMM_SOFTMAX_BWD_DOT = range(6)
 
 
 def gemm_nparts(n):
@@ -125,8 +125,9 @@ def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NON
     g.gamma, g.beta, g.split_k, g.diag = gamma, beta, split_k, diag
     if mode != GEMM_NORMAL:
         _cuda(stats, torch.float32)
-        if tuple(stats.shape) != (*a.shape[:-2], M, gemm_nparts(N), 2) or not stats.is_contiguous():
-            raise ValueError("gemm: stats must come from softmax_stats() for this product")
+        want = (*a.shape[:-2], M) if mode == GEMM_SOFTMAX_BWD_DOT else (*a.shape[:-2], M, gemm_nparts(N), 2)
+        if tuple(stats.shape) != want or not stats.is_contiguous():
+            raise ValueError("gemm: stats must come from softmax_stats() / rowdot() for this product")
         g.mode, g.stats = mode, stats.data_ptr()
     for o, dt, name in ((out_f32, torch.float32, "32"), (out_bf16, torch.bfloat16, "16")):
         if o is None:
@@ -228,6 +229,16 @@ def axpy_(dst, src, alpha=1.0):
     assert dst.numel() == src.numel()
     _call("mirror_axpy_f32", _p(dst, F32), _p(src, F32), dst.numel(), alpha)
     return dst
+
+
+@_op
+def rowdot(a16, b16):
+    """[..., R, C] bf16 x2 (contiguous) -> [..., R] f32 row dots."""
+    _contig(a16), _contig(b16)
+    assert a16.shape == b16.shape
+    out = torch.empty(a16.shape[:-1], device=a16.device, dtype=F32)
+    _call("mirror_rowdot_bf16", _p(a16, BF16), _p(b16, BF16), a16.numel() // a16.shape[-1], a16.shape[-1], _p(out))
+    return out
 
 
 @_op

@@ -7,6 +7,7 @@ accumulation, fp32 residual stream / LayerNorm / softmax statistics / head
 outputs / losses.
 """
 import math
+import os
 
 import torch
 from torch.autograd import Function
@@ -365,6 +366,9 @@ def _heads(t, col0, E, h=WSI_HEADS):
     return t[:, :, col0:col0 + E].unflatten(-1, (h, E // h)).permute(0, 2, 1, 3)
 
 
+_AB_NO_DOTS = os.environ.get("MIRROR_B200_AB_NO_DOTS") == "1"  # A/B switch (measurement only): two-pass softmax backward everywhere
+
+
 def _softmax_gemm(a, b, rows, cols, alpha, want_f32=False):
     """softmax_rows(alpha * a @ b^T) -> (bf16, f32 | None) without the logits touching HBM: two GEMM passes over the
     (K = head_dim) product, row statistics then normalised probabilities (MIRROR_GEMM_ROWSTATS / SOFTMAX)."""
@@ -381,17 +385,21 @@ def _softmax_gemm(a, b, rows, cols, alpha, want_f32=False):
     return p16, p32
 
 
-def _softmax_bwd_gemm(a, b, p16, alpha):
-    """d logits = alpha * P * (G - rowsum(G * P)) with G = a @ b^T never materialised (MIRROR_GEMM_ROWDOT / SOFTMAX_BWD)."""
+def _softmax_bwd_gemm(a, b, p16, alpha, dots=None):
+    """d logits = alpha * P * (G - rowsum(G * P)) with G = a @ b^T never materialised (MIRROR_GEMM_ROWDOT / SOFTMAX_BWD).
+    ``dots``: rowsum(G * P) when the caller has it cheaper (P fed O = P V, so rowsum(G * P) = dO . O row by row)."""
     batch, dev = a.shape[:-2], a.device
     rows, cols = p16.shape[-2:]
     if cols % 32:
         g = torch.empty(*batch, rows, cols, device=dev, dtype=F32)
         K.gemm(a, b, out_f32=g)
         return K.softmax_bwd(p16, g, alpha)[0]
+    ds = torch.empty_like(p16)
+    if dots is not None:
+        K.gemm(a, b, alpha=alpha, mode=K.GEMM_SOFTMAX_BWD_DOT, stats=dots, res=p16, out_bf16=ds)
+        return ds
     st = K.softmax_stats(batch, rows, cols, dev)
     K.gemm(a, b, mode=K.GEMM_ROWDOT, stats=st, res=p16)
-    ds = torch.empty_like(p16)
     K.gemm(a, b, alpha=alpha, mode=K.GEMM_SOFTMAX_BWD, stats=st, res=p16, out_bf16=ds)
     return ds
 
@@ -498,7 +506,8 @@ class NystromLayerFn(Function):
         K.gemm(dw16, kv, out_bf16=gz16)
         dkv16 = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
         K.gemm(_T(zf16), _T(dw16), out_bf16=dkv16)
-        ds3 = _softmax_bwd_gemm(dkv16, v, a3, scale)                                   # da3 = dkv v^T
+        # da3 = dkv v^T; its row dots with a3 are dkv . kv (kv = a3 v), so one pass suffices
+        ds3 = _softmax_bwd_gemm(dkv16, v, a3, scale, dots=None if _AB_NO_DOTS else K.rowdot(dkv16, kv))
         d_conv = torch.zeros(hd, conv_w.numel() // hd, device=dev, dtype=F32)
         dvc = K.res_conv_bwd(do16, qkv, conv_w.reshape(hd, -1), d_conv)              # conv^T(dO), bf16 [B,n,E]
         del do16

@@ -118,6 +118,11 @@ class Emu:
     def _gemm_softmax(self, acc, mode, stats, alpha, res, out_f32, out_bf16):
         """Fused row-softmax epilogue modes: the partials go through `stats` split per half tile as the kernel does."""
         n = acc.shape[-1]
+        if mode == 5:
+            assert n % 32 == 0 and stats.shape == acc.shape[:-1] and res.dtype == BF16
+            v = alpha * res.float() * (acc - stats[..., None])
+            out_bf16.copy_(v.to(BF16))
+            return
         assert n % 32 == 0 and stats.shape == (*acc.shape[:-1], self.gemm_nparts(n), 2)
         bn = 256 if (n % 256 == 0 or n >= 1024) else (192 if n % 192 == 0 else 128)
         hw = bn // 2
@@ -175,6 +180,9 @@ class Emu:
     def axpy_(self, dst, src, alpha=1.0):
         dst += alpha * src
         return dst
+
+    def rowdot(self, a16, b16):
+        return (a16.float() * b16.float()).sum(-1)
 
     def token_fanout_bwd(self, d_full, d_cls, d_tok, B, T, E, device):
         out = torch.zeros(B, T, E) if d_full is None else d_full.clone()

@@ -350,6 +350,10 @@ def test_gemm_fused_softmax_fwd_bwd(rows, cols, kd):
     ds = torch.zeros(Bt, hd, rows, cols, device="cuda", dtype=BF16)
     K.gemm(ga.cuda(), gb.cuda(), alpha=alpha, mode=K.GEMM_SOFTMAX_BWD, stats=st2, res=p16, out_bf16=ds)
     close(ds, ds_ref, 6e-3, "softmax bwd")
+    # one-pass form: the row dots are handed over (here computed on the host), MIRROR_GEMM_SOFTMAX_BWD_DOT
+    ds1 = torch.zeros_like(ds)
+    K.gemm(ga.cuda(), gb.cuda(), alpha=alpha, mode=K.GEMM_SOFTMAX_BWD_DOT, stats=(G * P).sum(-1).cuda().contiguous(), res=p16, out_bf16=ds1)
+    close(ds1, ds_ref, 6e-3, "softmax bwd (dots given)")
     # and the emulation used by the CPU suite follows the same contract
     st_c = torch.zeros(Bt, hd, rows, K.gemm_nparts(cols), 2)
     EMU.gemm(a, b, alpha=alpha, mode=1, stats=st_c)
@@ -405,3 +409,8 @@ def test_token_fanout_bwd():
         td = tok_store.cuda()[:, 4:, :] if t is not None else None  # strided view on the device too
         got = K.token_fanout_bwd(dev(f), dev(c), td, B, T, E, "cuda")
         close(got, want, 1e-6, "token_fanout_bwd")
+
+
+def test_rowdot():
+    a, b = rn(3, 5, 77, 96, seed=1).to(BF16), rn(3, 5, 77, 96, seed=2).to(BF16)
+    both("rowdot", (a, b), tol=2e-6)
