@@ -780,6 +780,9 @@ class SymKlFn(Function):
         return K.sym_kl_bwd(scores, ctx.B, g.contiguous(), 1.0), None
 
 
+_WEIGHT_VECTORS = {}
+
+
 class CombineFn(Function):
     """total = sum_i w_i * term_i (losses/mirror_loss.py:121-127)."""
 
@@ -793,8 +796,14 @@ class CombineFn(Function):
     @once_differentiable
     @_cbwd
     def backward(ctx, g):
-        # five scalars: host-side list -> one tiny tensor op (bookkeeping, not arithmetic of the hot path)
-        return g.reshape(1) * torch.tensor(ctx.weights, device=g.device, dtype=F32), None
+        # five scalars (bookkeeping, not arithmetic of the hot path).  The weight vector is uploaded ONCE per (weights,
+        # device): torch.tensor(list, device=cuda) is a blocking copy -- as the first node of every backward it made the
+        # host wait for the whole forward (26 ms per step) and the GPU then idle while the backward was being enqueued.
+        key = (tuple(float(w) for w in ctx.weights), g.device)
+        w = _WEIGHT_VECTORS.get(key)
+        if w is None:
+            w = _WEIGHT_VECTORS[key] = torch.tensor(key[0], device=g.device, dtype=F32)
+        return g.reshape(1) * w, None
 
 
 class StackScalarsFn(Function):

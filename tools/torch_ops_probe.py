@@ -52,10 +52,22 @@ agg = defaultdict(lambda: [0, 0.0])
 for ev in prof.events():
     if getattr(ev, "device_type", None) is not None and str(ev.device_type).endswith("CUDA") and ev.name and not ev.name.startswith("aten::"):
         dt = getattr(ev, "device_time", 0) or getattr(ev, "cuda_time", 0)
-        name = ev.name.split("(")[0].replace("void ", "").replace("mb::(anonymous namespace)::", "")
+        name = ev.name.replace("void ", "").replace("mb::(anonymous namespace)::", "").split("(")[0]
         agg[name][0] += 1
         agg[name][1] += dt
 tot = sum(v[1] for v in agg.values())
 print(f"\n{len(agg)} kernel names, {tot / 1e3:.2f} ms of device time in the step")
 for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:48]:
     print(f"{t / 1e3:8.3f} ms {c:5d}  {name[:110]}")
+
+# ---- host side: how long does the CPU need to enqueue one step (no synchronisation inside the loop)?
+import time  # noqa: E402
+
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(5):
+    step()
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+t2 = time.perf_counter()
+print(f"\nhost enqueue time per step: {(t1 - t0) / 5 * 1e3:.1f} ms; device drained {(t2 - t1) * 1e3:.1f} ms after the last enqueue; wall per step {(t2 - t0) / 5 * 1e3:.1f} ms")
