@@ -380,11 +380,13 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
 
 // One epilogue warp's share of a finished tile: the 32 rows of its TMEM lane quarter (first row row0) x BN/2 columns
 // starting at cbase.
-template <int BN>
+// SM: the kernel instantiation serves the fused row-softmax modes ONLY (and the others never): each kernel carries one of the
+// two epilogues -- with both inlined the epilogue warps lost a quarter of their issue slots to instruction-cache misses.
+template <int BN, bool SM>
 __device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t taddr, Sink& sink, int b1, int b2, int row0,
                                               int cbase, int lane, uint64_t* tfull_bar, uint32_t aphase, int part) {
   constexpr int NCH = BN / 64;  // 32-column chunks per thread
-  if (e.mode != MIRROR_GEMM_NORMAL) {
+  if constexpr (SM) {
     epilogue_tile_softmax<BN>(e, sink, taddr, b1, b2, row0, cbase, lane, tfull_bar, aphase, part);
     return;
   }
@@ -397,8 +399,10 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t 
   mbar_wait(tfull_bar, aphase);
   tc_fence_after();
   if (!rows_ok) return;
-  // chunks go in pairs (static register names for the two prefetch buffers); fully unrolled: NCH <= 4
-#pragma unroll
+  // chunks go in pairs (static register names for the two prefetch buffers).  The pair loop is NOT unrolled: the vector
+  // chunk body is ~1000 instructions and four copies of it (BN = 256) overflow the instruction cache of the SM -- the
+  // epilogue warps were losing ~a quarter of their issue slots to instruction fetch (ncu: stall_no_inst).
+#pragma unroll 1
   for (int c = 0; c < NCH; c += 2) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -412,7 +416,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t 
   }
 }
 
-template <int BN, int A_MN, int B_MN, bool TMAS>
+template <int BN, int A_MN, int B_MN, bool TMAS, bool SM>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC32, const __grid_constant__ CUtensorMap tmC16,
@@ -552,7 +556,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row0 = mb_ * BM + q * 32;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
+      epilogue_tile<BN, SM>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
                         &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
@@ -730,7 +734,7 @@ gemm_tcgen05_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int row0 = (mg * CL + rank) * BM + q * 32;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
+      epilogue_tile<BN, false>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
                         &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
@@ -900,7 +904,7 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
       const int row0 = mb_ * BM + q * 32;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      epilogue_tile<BN>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
+      epilogue_tile<BN, false>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
                         &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
@@ -962,11 +966,11 @@ int make_operand_map(CUtensorMap* map, const void* ptr, int mn_major, long long 
   return 0;
 }
 
-template <int BN, int A_MN, int B_MN, bool TMAS>
+template <int BN, int A_MN, int B_MN, bool TMAS, bool SM = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC32, const CUtensorMap& tmC16, const KParams& p,
            int vec_ok, cudaStream_t stream) {
   using C = Cfg<BN, TMAS>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TMAS>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TMAS, SM>;
   static bool configured = false;  // benign race: attribute set is idempotent
   if (!configured) {
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -1136,7 +1140,10 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restr
 
 using namespace mb;
 
-static int tile_n_for(int N) { return (N % 256 == 0 || N >= 1024) ? 256 : (N % 192 == 0 ? 192 : 128); }
+static int tile_n_for(int N) {
+  static const int no192 = [] { const char* v = getenv("MIRROR_B200_AB_NO_BN192"); return v && *v == '1'; }();  // A/B switch
+  return (N % 256 == 0 || N >= 1024) ? 256 : ((N % 192 == 0 && !no192) ? 192 : 128);
+}
 
 extern "C" int mirror_gemm_nparts(int32_t N) {
   const int bn = tile_n_for(N);
@@ -1224,6 +1231,15 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
     rc = make_output_maps(g, &tmC32, &tmC16);
     if (rc) return rc;
   }
+  if (g->mode != MIRROR_GEMM_NORMAL) {  // the fused softmax epilogues exist for K-major operands (q k^T-shaped products) only
+    MB_CHECK_ARG(key == 0, "gemm: softmax modes need K-major A and B");
+    if (BN == 256) return tmas ? launch<256, 0, 0, true, true>(tmA, tmB, tmC32, tmC16, p, vec, stream)
+                               : launch<256, 0, 0, false, true>(tmA, tmB, tmC32, tmC16, p, vec, stream);
+    if (BN == 192) return tmas ? launch<192, 0, 0, true, true>(tmA, tmB, tmC32, tmC16, p, vec, stream)
+                               : launch<192, 0, 0, false, true>(tmA, tmB, tmC32, tmC16, p, vec, stream);
+    return tmas ? launch<128, 0, 0, true, true>(tmA, tmB, tmC32, tmC16, p, vec, stream)
+                : launch<128, 0, 0, false, true>(tmA, tmB, tmC32, tmC16, p, vec, stream);
+  }
 #define MB_DISPATCH(BNV, TM)                                                        \
   switch (key) {                                                                    \
     case 0: return launch<BNV, 0, 0, TM>(tmA, tmB, tmC32, tmC16, p, vec, stream);   \
@@ -1247,7 +1263,7 @@ extern "C" int mirror_gemm_bf16_multi(const mirror_gemm_args* terms, int32_t nte
   int rc = fill_epi(g, &p.e);
   if (rc) return rc;
   MB_CHECK_ARG(g->split_k <= 1 && g->mode == MIRROR_GEMM_NORMAL, "gemm_multi: split_k / softmax modes are not supported");
-  const int BN = (g->N % 256 == 0 || g->N >= 1024) ? 256 : (g->N % 192 == 0 ? 192 : 128);
+  const int BN = tile_n_for(g->N);
   p.K = g->K;
   p.batch1 = g->batch1;
   p.batch2 = g->batch2;
