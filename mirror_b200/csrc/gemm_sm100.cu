@@ -301,6 +301,10 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
     tmem_ld_32x32(taddr + c * 32, acc);
     tmem_ld_wait();
     float v[32];
+    if (e.mode == 6) {  // measurement only (tools/softmax_gemm_probe.py): the cost of draining TMEM and of the tile hand-shake alone
+      run_dot += __uint_as_float(acc[0]) + __uint_as_float(acc[31]);
+      continue;
+    }
     if (e.mode == MIRROR_GEMM_ROWSTATS) {
       float cm = -INFINITY;
 #pragma unroll
@@ -374,7 +378,7 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
   }
   if (row_ok) {
     if (e.mode == MIRROR_GEMM_ROWSTATS) stats[part] = make_float2(run_m, run_s);
-    else if (e.mode == MIRROR_GEMM_ROWDOT) stats[part] = make_float2(run_dot, 0.f);
+    else if (e.mode == MIRROR_GEMM_ROWDOT || e.mode == 6) stats[part] = make_float2(run_dot, 0.f);
   }
 }
 
@@ -1070,7 +1074,7 @@ int fill_epi(const mirror_gemm_args* g, Epi* e) {
   MB_CHECK_ARG(g && g->a && g->b, "gemm: null operand");
   MB_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0 && g->batch1 > 0 && g->batch2 > 0, "gemm: bad shape M=%d N=%d K=%d", g->M,
                g->N, g->K);
-  MB_CHECK_ARG(g->out_f32 || g->out_bf16 || g->mode == MIRROR_GEMM_ROWSTATS || g->mode == MIRROR_GEMM_ROWDOT, "gemm: no output");
+  MB_CHECK_ARG(g->out_f32 || g->out_bf16 || g->mode == MIRROR_GEMM_ROWSTATS || g->mode == MIRROR_GEMM_ROWDOT || g->mode == 6, "gemm: no output");
   MB_CHECK_ARG(g->beta == 0.f || g->out_f32, "gemm: beta needs out_f32");
   MB_CHECK_ARG(g->drop_p >= 0.f && g->drop_p < 1.f, "gemm: drop_p out of range");
   MB_CHECK_ARG(g->split_k <= 1 || (g->out_f32 && !g->out_bf16 && !g->bias && !g->res && !g->res2 && g->act == 0 && g->drop_p == 0.f && g->diag == 0.f),
@@ -1083,11 +1087,11 @@ int fill_epi(const mirror_gemm_args* g, Epi* e) {
   e->res_row_div = g->res_row_div > 1 ? g->res_row_div : 1;
   e->mode = g->mode; e->stats = g->stats; e->nparts = 0;
   if (g->mode != MIRROR_GEMM_NORMAL) {
-    MB_CHECK_ARG(g->mode >= 1 && g->mode <= 5 && g->stats && g->N % 32 == 0 && g->split_k <= 1 && g->res_row_div <= 1,
+    MB_CHECK_ARG(g->mode >= 1 && g->mode <= 6 && g->stats && g->N % 32 == 0 && g->split_k <= 1 && g->res_row_div <= 1,
                  "gemm: softmax modes need stats, N %% 32 == 0 and no split-K");
-    MB_CHECK_ARG(g->mode < MIRROR_GEMM_ROWDOT || (g->res && g->res_is_bf16),
+    MB_CHECK_ARG(g->mode < MIRROR_GEMM_ROWDOT || g->mode == 6 || (g->res && g->res_is_bf16),
                  "gemm: ROWDOT / SOFTMAX_BWD read the bf16 probabilities through `res`");
-    MB_CHECK_ARG(g->mode == MIRROR_GEMM_ROWSTATS || g->mode == MIRROR_GEMM_ROWDOT || g->out_f32 || g->out_bf16, "gemm: no output");
+    MB_CHECK_ARG(g->mode == MIRROR_GEMM_ROWSTATS || g->mode == MIRROR_GEMM_ROWDOT || g->mode == 6 || g->out_f32 || g->out_bf16, "gemm: no output");
   }
   MB_CHECK_ARG(!g->res2 || g->res, "gemm: res2 needs res (it shares its strides)");
   e->ldr = g->ldr; e->r_bs1 = g->r_bs1; e->r_bs2 = g->r_bs2;

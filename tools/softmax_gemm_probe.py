@@ -47,6 +47,7 @@ for tag, (a, b) in ({} if ONLY == "pinv" else {"strided": (q, kl)} if ONCE else 
     nel = B * hd * n * m
     timed(f"s1 {tag} normal f32", lambda: K.gemm(a, b, out_f32=o32, alpha=0.1), nel * 4)
     timed(f"s1 {tag} normal bf16", lambda: K.gemm(a, b, out_bf16=o16, alpha=0.1), nel * 2)
+    timed(f"s1 {tag} NULL epilogue (mode 6)", lambda: K.gemm(a, b, alpha=0.1, mode=6, stats=st))
     timed(f"s1 {tag} ROWSTATS", lambda: K.gemm(a, b, alpha=0.1, mode=K.GEMM_ROWSTATS, stats=st))
     timed(f"s1 {tag} SOFTMAX bf16", lambda: K.gemm(a, b, alpha=0.1, mode=K.GEMM_SOFTMAX, stats=st, out_bf16=o16), nel * 2)
     timed(f"s1 {tag} ROWDOT", lambda: K.gemm(a, b, mode=K.GEMM_ROWDOT, stats=st, res=o16), nel * 2)
