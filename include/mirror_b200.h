@@ -127,8 +127,9 @@ int mirror_cast_split3(const float* src, int64_t rows, int32_t cols, int64_t lds
                        int32_t stack_rows, int32_t order, mirror_stream_t stream);
 /* dst[r,0:cols] = src[r,0:cols] with row strides: gathers `wsi_emb[:, 0, :]` (models/mirror.py:896) into a dense block */
 int mirror_copy_rows_f32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd, mirror_stream_t stream);
-/* out[r] = sum_c a[r,c]*b[r,c] over contiguous bf16 rows (cols % 8 == 0): the row dots dO.O of a softmax backward */
-int mirror_rowdot_bf16(const void* a, const void* b, int64_t rows, int32_t cols, float* out, mirror_stream_t stream);
+/* out[r] = sum_c a[r,c]*(b[r,c] - sub[r,c]) over contiguous bf16 rows (cols % 8 == 0, sub may be NULL): the row dots dO.O of a
+ * softmax backward; `sub` removes a residual that was added to O after the attention product */
+int mirror_rowdot_bf16(const void* a, const void* b, const void* sub, int64_t rows, int32_t cols, float* out, mirror_stream_t stream);
 /* dst += alpha*src  (gradient accumulation of the autograd graph) */
 int mirror_axpy_f32(float* dst, const float* src, int64_t n, float alpha, mirror_stream_t stream);
 /* Gradient of the encoder output h:[B,T,E] that the model reads three ways (models/mirror.py:889-905: the whole matrix for the

@@ -82,7 +82,7 @@ SIGNATURES = {
     "mirror_colsum": [_P, _I32, _I64, _I32, _I64, _P, _P],
     "mirror_reparam_fwd": [_P, _P, _P, _I64, _P, _P, _P],
     "mirror_reparam_bwd": [_P, _P, _P, _I64, _P, _P, _P],
-    "mirror_rowdot_bf16": [_P, _P, _I64, _I32, _P, _P],
+    "mirror_rowdot_bf16": [_P, _P, _P, _I64, _I32, _P, _P],
     "mirror_token_fanout_bwd": [_P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, _P],
     "mirror_layernorm_fwd": [_P, _P, _P, _F, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "mirror_layernorm_bwd": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],

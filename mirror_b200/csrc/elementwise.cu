@@ -286,9 +286,9 @@ __global__ void token_fanout_bwd_kernel(const float* __restrict__ full, const fl
   }
 }
 
-// out[r] = <a[r,:], b[r,:]> for contiguous bf16 rows; 8 lanes per row, 8 elements per lane and step
-__global__ void rowdot_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long rows, int cols,
-                                   float* __restrict__ out) {
+// out[r] = <a[r,:], b[r,:] - sub[r,:]> (sub optional) for contiguous bf16 rows; 8 lanes per row, 8 elements per lane and step
+__global__ void rowdot_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ minus, long long rows,
+                                   int cols, float* __restrict__ out) {
   const int sub = threadIdx.x & 7;
   const unsigned gmask = 0xFFu << (threadIdx.x & 24);  // the 8 lanes that share a row leave the loop together
   for (long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3; r < rows; r += ((long long)gridDim.x * blockDim.x) >> 3) {
@@ -296,12 +296,14 @@ __global__ void rowdot_bf16_kernel(const bf16* __restrict__ a, const bf16* __res
     for (int c = sub * 8; c < cols; c += 64) {
       const uint4 x = *reinterpret_cast<const uint4*>(a + r * cols + c);
       const uint4 y = *reinterpret_cast<const uint4*>(b + r * cols + c);
+      const uint4 z = minus ? *reinterpret_cast<const uint4*>(minus + r * cols + c) : make_uint4(0u, 0u, 0u, 0u);
       const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&x);
       const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&y);
+      const __nv_bfloat162* zh = reinterpret_cast<const __nv_bfloat162*>(&z);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float2 p = __bfloat1622float2(xh[t]), q = __bfloat1622float2(yh[t]);
-        acc += p.x * q.x + p.y * q.y;
+        const float2 p = __bfloat1622float2(xh[t]), q = __bfloat1622float2(yh[t]), s = __bfloat1622float2(zh[t]);
+        acc += p.x * (q.x - s.x) + p.y * (q.y - s.y);
       }
     }
     acc += __shfl_xor_sync(gmask, acc, 1);
@@ -351,10 +353,11 @@ extern "C" int mirror_copy_rows_f32(const float* src, int64_t lds, int64_t rows,
   return 0;
 }
 
-extern "C" int mirror_rowdot_bf16(const void* a, const void* b, int64_t rows, int32_t cols, float* out, mirror_stream_t stream) {
+extern "C" int mirror_rowdot_bf16(const void* a, const void* b, const void* sub, int64_t rows, int32_t cols, float* out,
+                                  mirror_stream_t stream) {
   MB_CHECK_ARG(a && b && out && rows > 0 && cols > 0 && cols % 8 == 0, "rowdot_bf16: bad args (cols must be a multiple of 8)");
   const long long threads = ((rows * 8 + 255) / 256) * 256;  // whole 8-lane groups: the shuffles need every lane of a warp alive
-  rowdot_bf16_kernel<<<grid_for(threads, 256), 256, 0, STREAM>>>(reinterpret_cast<const bf16*>(a), reinterpret_cast<const bf16*>(b), rows, cols, out);
+  rowdot_bf16_kernel<<<grid_for(threads, 256), 256, 0, STREAM>>>(reinterpret_cast<const bf16*>(a), reinterpret_cast<const bf16*>(b), reinterpret_cast<const bf16*>(sub), rows, cols, out);
   MB_LAUNCH_CHECK();
   return 0;
 }

@@ -237,12 +237,12 @@ def axpy_(dst, src, alpha=1.0):
 
 
 @_op
-def rowdot(a16, b16):
-    """[..., R, C] bf16 x2 (contiguous) -> [..., R] f32 row dots."""
+def rowdot(a16, b16, sub16=None):
+    """[..., R, C] bf16 (contiguous) -> [..., R] f32 row dots <a, b - sub>."""
     _contig(a16), _contig(b16)
-    assert a16.shape == b16.shape
+    assert a16.shape == b16.shape and (sub16 is None or (sub16.shape == a16.shape and sub16.is_contiguous()))
     out = torch.empty(a16.shape[:-1], device=a16.device, dtype=F32)
-    _call("mirror_rowdot_bf16", _p(a16, BF16), _p(b16, BF16), a16.numel() // a16.shape[-1], a16.shape[-1], _p(out))
+    _call("mirror_rowdot_bf16", _p(a16, BF16), _p(b16, BF16), _p(sub16, BF16), a16.numel() // a16.shape[-1], a16.shape[-1], _p(out))
     return out
 
 

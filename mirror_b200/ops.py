@@ -460,12 +460,11 @@ class NystromLayerFn(Function):
         rc = K.res_conv_fwd(qkv, conv_w.reshape(hd, -1))
         o16 = torch.empty(B, n, E, device=dev, dtype=BF16)
         K.gemm(a1, _T(w_), out_bf16=_heads(o16, 0, E), res=_heads(rc, 0, E))
-        del rc
         wout16 = K.cast_bf16(out_w)
         y = torch.empty(B, S, E, device=dev, dtype=F32)
         K.gemm(o16[:, pad:, :], wout16.unsqueeze(0).expand(B, E, E), out_f32=y, bias=out_b, drop_p=drop_p, drop_seed=seed, res=h)
         ctx.save_for_backward(h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, a1, a2_16, a3, z0_32, scratch, z16, kv, w_, o16,
-                              wout16, conv_w, *iters)
+                              wout16, conv_w, rc, *iters)
         ctx.meta = (B, S, E, pad, n, seg, scale, drop_p, seed)
         return y
 
@@ -474,7 +473,7 @@ class NystromLayerFn(Function):
     @_cbwd
     def backward(ctx, dy):
         (h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, a1, a2_16, a3, z0_32, scratch, zf16, kv, w_, o16, wout16,
-         conv_w, *iters) = ctx.saved_tensors
+         conv_w, rc, *iters) = ctx.saved_tensors
         B, S, E, pad, n, seg, scale, drop_p, seed = ctx.meta
         hd = WSI_HEADS
         d, m = E // hd, E // 2
@@ -497,7 +496,12 @@ class NystromLayerFn(Function):
         do_h = _heads(do16, 0, E)
 
         # ---- out = a1 @ w + res_conv(v)
-        ds1 = _softmax_bwd_gemm(do_h, w_, a1, scale)                                   # da1 = dO w^T stays in TMEM
+        # da1 = dO w^T stays in TMEM; its row dots with a1 are dO . (a1 w) = dO . (out - res_conv(v)), per token and head,
+        # so the ROWDOT pass over the n x m product is not needed (the 226 MB value residual is kept for this)
+        dots1 = None
+        if not _AB_NO_DOTS:
+            dots1 = K.rowdot(do16.view(B, n, hd, d), o16.view(B, n, hd, d), rc.view(B, n, hd, d)).permute(0, 2, 1).contiguous()
+        ds1 = _softmax_bwd_gemm(do_h, w_, a1, scale, dots=dots1)
         dw16 = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
         K.gemm(_T(a1), _T(do_h), out_bf16=dw16)
 

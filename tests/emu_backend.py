@@ -181,8 +181,9 @@ class Emu:
         dst += alpha * src
         return dst
 
-    def rowdot(self, a16, b16):
-        return (a16.float() * b16.float()).sum(-1)
+    def rowdot(self, a16, b16, sub16=None):
+        b = b16.float() - (sub16.float() if sub16 is not None else 0.0)
+        return (a16.float() * b).sum(-1)
 
     def token_fanout_bwd(self, d_full, d_cls, d_tok, B, T, E, device):
         out = torch.zeros(B, T, E) if d_full is None else d_full.clone()

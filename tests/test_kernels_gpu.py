@@ -414,3 +414,4 @@ def test_token_fanout_bwd():
 def test_rowdot():
     a, b = rn(3, 5, 77, 96, seed=1).to(BF16), rn(3, 5, 77, 96, seed=2).to(BF16)
     both("rowdot", (a, b), tol=2e-6)
+    both("rowdot", (a, b, rn(3, 5, 77, 96, seed=3).to(BF16)), tol=2e-6)
