@@ -157,8 +157,9 @@ int mirror_rank_mask(const float* noise, int32_t B, int32_t N, int32_t keep, flo
 /* r[b,t,e] = (t>=first && mask[b,t-first] ? tok[e*tok_stride] : r[b,t,e]) + pos[t,e]  (models/mirror.py:521-527,636-643,692-693,549) */
 int mirror_mask_pos_fwd(float* r, const float* mask, const float* tok, int32_t tok_stride, const float* pos, int32_t B, int32_t T,
                         int32_t E, int32_t first, mirror_stream_t stream);
-int mirror_mask_pos_bwd(float* dy, const float* mask, float* dtok, int32_t tok_stride, float* dpos, int32_t B, int32_t T, int32_t E,
-                        int32_t first, mirror_stream_t stream);
+/* dr = masked ? 0 : dy (dr must not alias dy); dpos[t,e] += sum_b dy; dtok[e*tok_stride] += sum of dy over the masked slots */
+int mirror_mask_pos_bwd(const float* dy, const float* mask, float* dr, float* dtok, int32_t tok_stride, float* dpos, int32_t B,
+                        int32_t T, int32_t E, int32_t first, mirror_stream_t stream);
 /* Nyström landmarks: lm[b,j,0:2E] = mean of `seg` consecutive rows of the q and k slots of qkv[B,n,3E] */
 int mirror_landmark_fwd(const void* qkv_bf16, void* lm_bf16, int32_t B, int32_t n, int32_t m, int32_t seg, int32_t E,
                         mirror_stream_t stream);
@@ -206,7 +207,7 @@ int mirror_res_conv_bwd(const void* dout_bf16, const void* qkv_bf16, const float
 /* z0 = a2^T / (max_rowsum * max_colsum), maxima over the WHOLE [BH,m,m] tensor (moore_penrose_iter_pinv init).
  * scratch32: 32 bytes of device memory kept by the caller until the backward call. */
 int mirror_pinv_init(const float* a2, int32_t BH, int32_t m, void* scratch32, float* z_f32, void* z_bf16, mirror_stream_t stream);
-int mirror_pinv_init_bwd(const float* gz0, const float* z0_f32, int32_t BH, int32_t m, void* scratch32, float* gx, int32_t accumulate,
+int mirror_pinv_init_bwd(const float* gz0, const void* z0_bf16, int32_t BH, int32_t m, void* scratch32, float* gx, int32_t accumulate,
                          mirror_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

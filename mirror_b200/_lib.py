@@ -77,7 +77,7 @@ SIGNATURES = {
     "mirror_wsi_embed_bwd": [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P],
     "mirror_rank_mask": [_P, _I32, _I32, _I32, _P, _P],
     "mirror_mask_pos_fwd": [_P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P],
-    "mirror_mask_pos_bwd": [_P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P],
+    "mirror_mask_pos_bwd": [_P, _P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P],
     "mirror_landmark_fwd": [_P, _P, _I32, _I32, _I32, _I32, _I32, _P],
     "mirror_colsum": [_P, _I32, _I64, _I32, _I64, _P, _P],
     "mirror_reparam_fwd": [_P, _P, _P, _I64, _P, _P, _P],

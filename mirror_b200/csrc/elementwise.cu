@@ -183,46 +183,56 @@ __global__ void mask_pos_fwd_kernel(float* __restrict__ r, const float* __restri
     r[i] = (m ? tok[(long long)e * tok_stride] : r[i]) + pos[(long long)t * E + e];
   }
 }
-// dr = masked ? 0 : dy (in place);  dpos[t,e] += sum_b dy;  dtok[e*tok_stride] += sum over masked slots
-__global__ void mask_pos_bwd_kernel(float* __restrict__ dy, const float* __restrict__ mask, float* __restrict__ dtok,
-                                    int tok_stride, float* __restrict__ dpos, int B, int T, int E, int first) {
+// dr = masked ? 0 : dy (out of place: with distinct restrict pointers the loads of the slide loop are batched; the in-place
+// version serialised every load behind the previous store);  dpos[t,e] += sum_b dy;  dtok[e*tok_stride] += sum over masked slots
+__global__ void mask_pos_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ mask, float* __restrict__ dr,
+                                    float* __restrict__ dtok, int tok_stride, float* __restrict__ dpos, int B, int T, int E, int first) {
   const long long total = (long long)T * E;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int e = (int)(i % E);
     const int t = (int)(i / E);
     float sp = 0.f, st = 0.f;
+#pragma unroll 8
     for (int b = 0; b < B; ++b) {
       const long long o = ((long long)b * T + t) * E + e;
       const float g = dy[o];
+      const bool masked = t >= first && mask[(long long)b * (T - first) + (t - first)] != 0.f;
       sp += g;
-      if (t >= first && mask[(long long)b * (T - first) + (t - first)] != 0.f) {
-        st += g;
-        dy[o] = 0.f;
-      }
+      st += masked ? g : 0.f;
+      dr[o] = masked ? 0.f : g;
     }
     dpos[i] += sp;
     if (st != 0.f) atomicAdd(dtok + (long long)e * tok_stride, st);
   }
 }
 
-// lm[b,j,c] = mean_{s<seg} qkv[b, j*seg+s, c]  for c < 2E (q and k slots)
+// lm[b,j,c] = mean_{s<seg} qkv[b, j*seg+s, c]  for c < 2E (q and k slots); 8 channels (16 bytes) per thread
 __global__ void landmark_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ lm, int B, int n, int m, int seg,
                                     int E) {
-  const int C2 = 2 * E;
-  const long long total = (long long)B * m * (C2 / 2);
+  const int C8 = 2 * E / 8;
+  const long long total = (long long)B * m * C8;
   const float inv = 1.f / seg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c2 = (int)(i % (C2 / 2));
-    const int j = (int)((i / (C2 / 2)) % m);
-    const int b = (int)(i / ((long long)(C2 / 2) * m));
-    const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(qkv + ((long long)b * n + (long long)j * seg) * 3 * E) + c2;
-    float sx = 0.f, sy = 0.f;
+    const int c8 = (int)(i % C8);
+    const int j = (int)((i / C8) % m);
+    const int b = (int)(i / ((long long)C8 * m));
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + ((long long)b * n + (long long)j * seg) * 3 * E) + c8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int s = 0; s < seg; ++s) {
-      const float2 f = __bfloat1622float2(src[(long long)s * 3 * E / 2]);
-      sx += f.x;
-      sy += f.y;
+      const uint4 u = src[(long long)s * 3 * E / 8];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __bfloat1622float2(h[t]);
+        acc[2 * t] += f.x;
+        acc[2 * t + 1] += f.y;
+      }
     }
-    reinterpret_cast<__nv_bfloat162*>(lm + ((long long)b * m + j) * C2)[c2] = __floats2bfloat162_rn(sx * inv, sy * inv);
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) oh[t] = __floats2bfloat162_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
+    reinterpret_cast<uint4*>(lm + ((long long)b * m + j) * 2 * E)[c8] = o;
   }
 }
 // out[c] += sum_r x[r, c]   (bias gradients).  Block = 32 x 8 threads over a [rows_chunk, 32-col] tile.
@@ -437,19 +447,20 @@ extern "C" int mirror_mask_pos_fwd(float* r, const float* mask, const float* tok
   MB_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int mirror_mask_pos_bwd(float* dy, const float* mask, float* dtok, int32_t tok_stride, float* dpos, int32_t B,
-                                   int32_t T, int32_t E, int32_t first, mirror_stream_t stream) {
-  MB_CHECK_ARG(dy && mask && dtok && dpos && B > 0 && T > first && E > 0 && first >= 0, "mask_pos_bwd: bad args");
-  mask_pos_bwd_kernel<<<grid_for((long long)T * E, 128), 128, 0, STREAM>>>(dy, mask, dtok, tok_stride, dpos, B, T, E, first);
+extern "C" int mirror_mask_pos_bwd(const float* dy, const float* mask, float* dr, float* dtok, int32_t tok_stride, float* dpos,
+                                   int32_t B, int32_t T, int32_t E, int32_t first, mirror_stream_t stream) {
+  MB_CHECK_ARG(dy && mask && dr && dr != dy && dtok && dpos && B > 0 && T > first && E > 0 && first >= 0,
+               "mask_pos_bwd: bad args (dr must not alias dy)");
+  mask_pos_bwd_kernel<<<grid_for((long long)T * E, 128), 128, 0, STREAM>>>(dy, mask, dr, dtok, tok_stride, dpos, B, T, E, first);
   MB_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int mirror_landmark_fwd(const void* qkv, void* lm, int32_t B, int32_t n, int32_t m, int32_t seg, int32_t E,
                                    mirror_stream_t stream) {
-  MB_CHECK_ARG(qkv && lm && B > 0 && m > 0 && seg > 0 && n == m * seg && E % 2 == 0, "landmark_fwd: bad args (n=%d m=%d seg=%d)",
+  MB_CHECK_ARG(qkv && lm && B > 0 && m > 0 && seg > 0 && n == m * seg && E % 8 == 0, "landmark_fwd: bad args (n=%d m=%d seg=%d)",
                n, m, seg);
-  landmark_fwd_kernel<<<grid_for((long long)B * m * E, 256), 256, 0, STREAM>>>(reinterpret_cast<const bf16*>(qkv),
+  landmark_fwd_kernel<<<grid_for((long long)B * m * (E / 4), 256), 256, 0, STREAM>>>(reinterpret_cast<const bf16*>(qkv),
                                                                              reinterpret_cast<bf16*>(lm), B, n, m, seg, E);
   MB_LAUNCH_CHECK();
   return 0;

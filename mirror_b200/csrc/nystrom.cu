@@ -219,10 +219,20 @@ __global__ void pinv_init_kernel(const float* __restrict__ a2, int m, const unsi
 // backward of z0 = x^T / D, D = c*r:
 //   s = <g_z0, z0>  (whole tensor)      dD = -s / D      dc = dD*r   dr = dD*c
 //   gx[bh,i,j] (+)= g_z0[bh,j,i]/D + [row (bh,i) is the arg-max row]*dc + [col (bh,j) is the arg-max col]*dr
-__global__ void dot_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float* __restrict__ out) {
+// <a, b> with a in f32 and b = the bf16 copy of z0 that the forward keeps anyway (an fp32 z0 was written only for this sum)
+__global__ void dot_kernel(const float* __restrict__ a, const bf16* __restrict__ b, long long n, float* __restrict__ out) {
   __shared__ float sh[32];
   float s = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += a[i] * b[i];
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = reinterpret_cast<const float4*>(a)[i];
+    const uint2 u = reinterpret_cast<const uint2*>(b)[i];
+    const float2 y0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 y1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    s += x.x * y0.x + x.y * y0.y + x.z * y1.x + x.w * y1.y;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) s += a[i] * __bfloat162float(b[i]);
   s = block_sum(s, sh);
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
@@ -317,13 +327,13 @@ extern "C" int mirror_pinv_init(const float* a2, int32_t BH, int32_t m, void* sc
   MB_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int mirror_pinv_init_bwd(const float* gz0, const float* z0_f32, int32_t BH, int32_t m, void* scratch32, float* gx,
+extern "C" int mirror_pinv_init_bwd(const float* gz0, const void* z0_bf16, int32_t BH, int32_t m, void* scratch32, float* gx,
                                     int32_t accumulate, mirror_stream_t stream) {
-  MB_CHECK_ARG(gz0 && z0_f32 && scratch32 && gx && BH > 0 && m > 0, "pinv_init_bwd: bad args");
+  MB_CHECK_ARG(gz0 && z0_bf16 && scratch32 && gx && BH > 0 && m > 0, "pinv_init_bwd: bad args");
   float* dotp = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch32) + 16);
   MB_CUDA(cudaMemsetAsync(dotp, 0, 4, STREAM));
   const long long n = (long long)BH * m * m;
-  dot_kernel<<<ew_grid(n, 256 * 4), 256, 0, STREAM>>>(gz0, z0_f32, n, dotp);
+  dot_kernel<<<ew_grid(n, 256 * 8), 256, 0, STREAM>>>(gz0, reinterpret_cast<const bf16*>(z0_bf16), n, dotp);
   MB_LAUNCH_CHECK();
   dim3 grid((m + 31) / 32, (m + 31) / 32, BH), block(32, 8);
   pinv_init_bwd_kernel<<<grid, block, 0, STREAM>>>(gz0, m, reinterpret_cast<const unsigned long long*>(scratch32), dotp, gx,

@@ -320,10 +320,13 @@ def mask_pos_fwd_(r, mask, tok, tok_stride, pos, first):
 
 
 @_op
-def mask_pos_bwd_(dy, mask, dtok, tok_stride, dpos, first):
+def mask_pos_bwd(dy, mask, dtok, tok_stride, dpos, first):
+    """-> dr [B,T,E] = dy with the masked slots zeroed (new tensor); dtok / dpos are ACCUMULATED."""
     B, T, E = dy.shape
-    _call("mirror_mask_pos_bwd", _p(_contig(dy), F32), _p(_contig(mask), F32), _p(dtok, F32), tok_stride, _p(_contig(dpos), F32), B, T, E, first)
-    return dy
+    dr = torch.empty_like(dy)
+    _call("mirror_mask_pos_bwd", _p(_contig(dy), F32), _p(_contig(mask), F32), _p(dr), _p(dtok, F32), tok_stride, _p(_contig(dpos), F32),
+          B, T, E, first)
+    return dr
 
 
 @_op
@@ -438,21 +441,20 @@ def res_conv_bwd(dout16, qkv, w, dw):
 
 @_op
 def pinv_init(a2):
-    """a2: [B,h,m,m] f32 -> (z32, z16, scratch) with z0 = a2^T / (max rowsum * max colsum)."""
+    """a2: [B,h,m,m] f32 -> (z16, scratch) with z0 = a2^T / (max rowsum * max colsum) in bf16."""
     m = a2.shape[-1]
     BH = a2.numel() // (m * m)
-    z32 = torch.empty_like(a2)
     z16 = torch.empty_like(a2, dtype=BF16)
     scratch = torch.empty(8, device=a2.device, dtype=F32)
-    _call("mirror_pinv_init", _p(_contig(a2), F32), BH, m, _p(scratch), _p(z32), _p(z16), launches=2)
-    return z32, z16, scratch
+    _call("mirror_pinv_init", _p(_contig(a2), F32), BH, m, _p(scratch), None, _p(z16), launches=2)
+    return z16, scratch
 
 
 @_op
-def pinv_init_bwd(gz0, z0_32, scratch, gx, accumulate):
+def pinv_init_bwd(gz0, z0_16, scratch, gx, accumulate):
     m = gz0.shape[-1]
     BH = gz0.numel() // (m * m)
-    _call("mirror_pinv_init_bwd", _p(_contig(gz0), F32), _p(_contig(z0_32), F32), BH, m, _p(scratch), _p(_contig(gx), F32),
+    _call("mirror_pinv_init_bwd", _p(_contig(gz0), F32), _p(_contig(z0_16), BF16), BH, m, _p(scratch), _p(_contig(gx), F32),
           int(accumulate), launches=2)
 
 

@@ -435,8 +435,7 @@ class NystromLayerFn(Function):
         a1, _ = _softmax_gemm(q, kl, n, m, scale)
         a2_16, a2_32 = _softmax_gemm(ql, kl, m, m, scale, want_f32=True)
         a3, _ = _softmax_gemm(ql, k, m, n, scale)
-        z32, z16, scratch = K.pinv_init(a2_32)
-        z0_32 = z32
+        z16, scratch = K.pinv_init(a2_32)
         iters = []
         mm = (B, hd, m, m)
         for _ in range(PINV_ITERS):
@@ -463,7 +462,7 @@ class NystromLayerFn(Function):
         wout16 = K.cast_bf16(out_w)
         y = torch.empty(B, S, E, device=dev, dtype=F32)
         K.gemm(o16[:, pad:, :], wout16.unsqueeze(0).expand(B, E, E), out_f32=y, bias=out_b, drop_p=drop_p, drop_seed=seed, res=h)
-        ctx.save_for_backward(h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, a1, a2_16, a3, z0_32, scratch, z16, kv, w_, o16,
+        ctx.save_for_backward(h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, a1, a2_16, a3, scratch, z16, kv, w_, o16,
                               wout16, conv_w, rc, *iters)
         ctx.meta = (B, S, E, pad, n, seg, scale, drop_p, seed)
         return y
@@ -472,7 +471,7 @@ class NystromLayerFn(Function):
     @once_differentiable
     @_cbwd
     def backward(ctx, dy):
-        (h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, a1, a2_16, a3, z0_32, scratch, zf16, kv, w_, o16, wout16,
+        (h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, a1, a2_16, a3, scratch, zf16, kv, w_, o16, wout16,
          conv_w, rc, *iters) = ctx.saved_tensors
         B, S, E, pad, n, seg, scale, drop_p, seed = ctx.meta
         hd = WSI_HEADS
@@ -541,7 +540,7 @@ class NystromLayerFn(Function):
         ga2 = torch.empty(mm, device=dev, dtype=F32)
         K.gemm(gens[0][0], gens[0][1], more=gens[1:], out_f32=ga2)
         del gens
-        K.pinv_init_bwd(gz32, z0_32, scratch, ga2, True)
+        K.pinv_init_bwd(gz32, iters[0], scratch, ga2, True)  # iters[0] = z0 (bf16)
         ds2, _ = K.softmax_bwd(a2_16, ga2, scale)
         del ga2, gz32, gz16
 
@@ -619,11 +618,10 @@ class MaskPosFn(Function):
         (mask,) = ctx.saved_tensors
         tok_stride, first, tshape, pshape = ctx.meta
         B, T, E = dy.shape
-        dy = dy.contiguous().clone() if not dy.is_contiguous() else dy.clone()
         dtok = torch.zeros(tshape, device=dy.device, dtype=F32)
         dpos = torch.zeros(T, E, device=dy.device, dtype=F32)
-        K.mask_pos_bwd_(dy, mask, dtok.view(-1), tok_stride, dpos, first)
-        return dy, None, dtok, dpos.view(pshape), None
+        dr = K.mask_pos_bwd(dy.contiguous(), mask, dtok.view(-1), tok_stride, dpos, first)
+        return dr, None, dtok, dpos.view(pshape), None
 
 
 # ----------------------------------------------------------------------------------------------

@@ -239,7 +239,7 @@ class Emu:
         r.copy_(torch.where(m, tokv.view(1, 1, E).expand(B, T, E), r) + pos.view(1, T, E))
         return r
 
-    def mask_pos_bwd_(self, dy, mask, dtok, tok_stride, dpos, first):
+    def mask_pos_bwd(self, dy, mask, dtok, tok_stride, dpos, first):
         B, T, E = dy.shape
         dpos += dy.sum(0)
         m = torch.zeros(B, T, 1, dtype=torch.bool)
@@ -249,8 +249,7 @@ class Emu:
             dtok[:E] += g
         else:
             dtok[:1] += g.sum()
-        dy.mul_(~m)
-        return dy
+        return dy * (~m)
 
     def landmark_fwd(self, qkv, m, seg):
         B, n, E3 = qkv.shape
@@ -341,12 +340,12 @@ class Emu:
         scratch[3], scratch[4] = float(rs.flatten().argmax()), float(cs.flatten().argmax())
         z = a2.transpose(-1, -2) / (scratch[0] * scratch[1])
         z = z.contiguous()
-        return z, z.to(BF16), scratch
+        return z.to(BF16), scratch
 
-    def pinv_init_bwd(self, gz0, z0_32, scratch, gx, accumulate):
+    def pinv_init_bwd(self, gz0, z0_16, scratch, gx, accumulate):
         c, r = scratch[0], scratch[1]
         D = c * r
-        dD = -(gz0 * z0_32).sum() / D
+        dD = -(gz0 * z0_16.float()).sum() / D
         m = gz0.shape[-1]
         v = gz0.transpose(-1, -2) / D
         v = v.contiguous()

@@ -48,7 +48,7 @@ def both(op, args, kwargs=None, tol=1e-5, check_args=()):
     rc = r_cpu if isinstance(r_cpu, (tuple, list)) else (r_cpu,)
     rg = r_gpu if isinstance(r_gpu, (tuple, list)) else (r_gpu,)
     for i, (c, g) in enumerate(zip(rc, rg)):
-        if torch.is_tensor(c) and c.numel() > 0 and op not in ("pinv_init",) or (op == "pinv_init" and i < 2):
+        if torch.is_tensor(c) and c.numel() > 0 and op not in ("pinv_init",) or (op == "pinv_init" and i < 1):
             close(g, c, tol if c.dtype != BF16 else max(tol, 8e-3), f"{op} ret{i}")
     for i in check_args:
         close(a_gpu[i], a_cpu[i], tol if a_cpu[i].dtype != BF16 else max(tol, 8e-3), f"{op} arg{i}")
@@ -136,7 +136,7 @@ def test_mask_pos(first, E, tok_stride):
     mask = (torch.rand(B, T - first, generator=torch.Generator().manual_seed(1)) > 0.3).float()
     tok = rn(E if tok_stride else 1, seed=7)
     both("mask_pos_fwd_", (rn(B, T, E), mask, tok, tok_stride, rn(T, E, seed=8), first), check_args=(0,))
-    both("mask_pos_bwd_", (rn(B, T, E, seed=9), mask, torch.zeros_like(tok), tok_stride, torch.zeros(T, E), first), tol=1e-5,
+    both("mask_pos_bwd", (rn(B, T, E, seed=9), mask, torch.zeros_like(tok), tok_stride, torch.zeros(T, E), first), tol=1e-5,
          check_args=(0, 2, 4))
 
 
@@ -211,13 +211,13 @@ def test_pinv_init_and_bwd():
     # rows of a real attn2 all sum to 1 (the arg-max row is then decided by round-off); scale the rows apart so that
     # the arg-max row / column are well defined and CPU and GPU must agree on them
     a2 = torch.softmax(rn(2, 8, 24, 24, scale=2.0), -1) * (1 + 0.2 * torch.rand(2, 8, 24, 1, generator=torch.Generator().manual_seed(3)))
-    (z32, z16, scratch), _ = both("pinv_init", (a2,), tol=2e-6)
-    z_cpu, _, s_cpu = EMU.pinv_init(a2)
+    (z16, scratch), _ = both("pinv_init", (a2,), tol=2e-6)
+    z_cpu, s_cpu = EMU.pinv_init(a2)
     g = rn(2, 8, 24, 24, seed=1)
     gx_cpu = torch.ones(2, 8, 24, 24)
     EMU.pinv_init_bwd(g, z_cpu, s_cpu, gx_cpu, True)
     gx = torch.ones(2, 8, 24, 24, device="cuda")
-    K.pinv_init_bwd(g.cuda(), z32, scratch, gx, True)
+    K.pinv_init_bwd(g.cuda(), z16, scratch, gx, True)
     close(gx, gx_cpu, 1e-5, "pinv_init_bwd")
 
 
