@@ -58,6 +58,9 @@ z = torch.randn(B, hd, m, m, device="cuda", generator=g).to(torch.bfloat16)
 zo = torch.empty_like(z)
 timed("pinv 384^3 NN bf16 + res", lambda: K.gemm(z, z.transpose(-1, -2), out_bf16=zo, res=z), 2 * B * hd * m * m * 2)
 timed("pinv 384^3 NT bf16", lambda: K.gemm(z, z, out_bf16=zo, alpha=0.25), B * hd * m * m * 2)
+timed("pinv 384^3 NN bf16 (no res)", lambda: K.gemm(z, z.transpose(-1, -2), out_bf16=zo), B * hd * m * m * 2)
+timed("pinv 384^3 NT bf16 + res", lambda: K.gemm(z, z, out_bf16=zo, res=z), 2 * B * hd * m * m * 2)
+timed("pinv 384^3 TN bf16", lambda: K.gemm(z.transpose(-1, -2), z.transpose(-1, -2), out_bf16=zo), B * hd * m * m * 2)
 if ONLY == "pinv":
     timed("pinv 384^3 multi3", lambda: K.gemm(z, z, more=[(z, z), (z.transpose(-1, -2), z.transpose(-1, -2))], out_bf16=zo, res=z, res2=z))
     sys.exit(0)
