@@ -384,14 +384,95 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
 
 // One epilogue warp's share of a finished tile: the 32 rows of its TMEM lane quarter (first row row0) x BN/2 columns
 // starting at cbase.
+// LEAN epilogue: out_bf16 = alpha*acc + diag*I + gamma*res16 + gamma2*res2_16 through the bulk-store sink, nothing else.
+// The generic chunk body executes ~230 instructions per 32x32 chunk of which 52 are the multiply / convert / store it is
+// there for (the rest tests features and rebuilds addresses); the Moore-Penrose, attention-value and similarity-gradient
+// products -- two thirds of all launches, all epilogue-bound -- need none of those features.  The host selects this
+// instantiation only when N % 32 == 0 (no ragged chunk), so there is no scalar path either.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_lean(const Epi& e, uint32_t taddr, Sink& sink, int b1, int b2, int row0, int cbase,
+                                                   int lane, uint64_t* tfull_bar, uint32_t aphase) {
+  constexpr int NCH = BN / 64;
+  const int row = row0 + lane;
+  const bool row_ok = row < e.M;
+  const long long roff = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)row * e.ldr;
+  const bf16* r1 = (e.res && row_ok) ? reinterpret_cast<const bf16*>(e.res) + roff : nullptr;
+  const bf16* r2 = (e.res2 && row_ok) ? e.res2 + roff : nullptr;
+  uint4 pa[4];  // residual of the chunk to come: requested before the accumulator is waited for / before the previous chunk's math
+  if (r1 && cbase < e.N) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pa[j] = reinterpret_cast<const uint4*>(r1 + cbase)[j];
+  }
+  mbar_wait(tfull_bar, aphase);
+  tc_fence_after();
+  if (row0 >= e.M) return;
+  const float alpha = e.alpha, gamma = e.gamma, gamma2 = e.gamma2, diag = e.diag;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col0 = cbase + c * 32;
+    if (col0 >= e.N) break;  // warp-uniform
+    uint32_t acc[32];
+    tmem_ld_32x32(taddr + c * 32, acc);
+    tmem_ld_wait();
+    float v[32];
+    if (r1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w[4] = {pa[j].x, pa[j].y, pa[j].z, pa[j].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // bf16 -> f32 is a shift / a mask
+          v[j * 8 + 2 * t] = fmaf(alpha, __uint_as_float(acc[j * 8 + 2 * t]), gamma * __uint_as_float(w[t] << 16));
+          v[j * 8 + 2 * t + 1] = fmaf(alpha, __uint_as_float(acc[j * 8 + 2 * t + 1]), gamma * __uint_as_float(w[t] & 0xffff0000u));
+        }
+      }
+      if (c + 1 < NCH && col0 + 32 < e.N) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pa[j] = reinterpret_cast<const uint4*>(r1 + col0 + 32)[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = alpha * __uint_as_float(acc[j]);
+    }
+    if (r2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = reinterpret_cast<const uint4*>(r2 + col0)[j];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          v[j * 8 + 2 * t] = fmaf(gamma2, __uint_as_float(w[t] << 16), v[j * 8 + 2 * t]);
+          v[j * 8 + 2 * t + 1] = fmaf(gamma2, __uint_as_float(w[t] & 0xffff0000u), v[j * 8 + 2 * t + 1]);
+        }
+      }
+    }
+    if (diag != 0.f && row >= col0 && row < col0 + 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += (col0 + j == row) ? diag : 0.f;
+    }
+    uint4 pc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pc[j]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j * 8 + 2 * t], v[j * 8 + 2 * t + 1]);
+    }
+    sink_tma_bf16(sink, pc, false, b1, b2, row0, col0, lane);
+  }
+}
+
 // SM: the kernel instantiation serves the fused row-softmax modes ONLY (and the others never): each kernel carries one of the
 // two epilogues -- with both inlined the epilogue warps lost a quarter of their issue slots to instruction-cache misses.
-template <int BN, bool SM>
+// EK: which ONE epilogue the instantiation carries: 0 generic, 1 the fused row-softmax modes, 2 lean (above)
+template <int BN, int EK>
 __device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t taddr, Sink& sink, int b1, int b2, int row0,
                                               int cbase, int lane, uint64_t* tfull_bar, uint32_t aphase, int part) {
   constexpr int NCH = BN / 64;  // 32-column chunks per thread
-  if constexpr (SM) {
+  if constexpr (EK == 1) {
     epilogue_tile_softmax<BN>(e, sink, taddr, b1, b2, row0, cbase, lane, tfull_bar, aphase, part);
+    return;
+  }
+  if constexpr (EK == 2) {
+    epilogue_tile_lean<BN>(e, taddr, sink, b1, b2, row0, cbase, lane, tfull_bar, aphase);
     return;
   }
   const bool rows_ok = row0 < e.M;  // warp-uniform
@@ -420,7 +501,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t 
   }
 }
 
-template <int BN, int A_MN, int B_MN, bool TMAS, bool SM>
+template <int BN, int A_MN, int B_MN, bool TMAS, int EK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC32, const __grid_constant__ CUtensorMap tmC16,
@@ -560,7 +641,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row0 = mb_ * BM + q * 32;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      epilogue_tile<BN, SM>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
+      epilogue_tile<BN, EK>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
                         &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
@@ -738,7 +819,7 @@ gemm_tcgen05_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int row0 = (mg * CL + rank) * BM + q * 32;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      epilogue_tile<BN, false>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
+      epilogue_tile<BN, 0>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
                         &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
@@ -773,7 +854,7 @@ struct MultiInfo {
   int b_mn[kMaxTerms];
 };
 
-template <int BN, bool TMAS>
+template <int BN, bool TMAS, int EK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_constant__ KParams p,
                           const __grid_constant__ MultiInfo mi, const int vec_ok) {
@@ -908,7 +989,7 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
       const int row0 = mb_ * BM + q * 32;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      epilogue_tile<BN, false>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
+      epilogue_tile<BN, EK>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
                         &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
       __syncwarp();
@@ -970,11 +1051,11 @@ int make_operand_map(CUtensorMap* map, const void* ptr, int mn_major, long long 
   return 0;
 }
 
-template <int BN, int A_MN, int B_MN, bool TMAS, bool SM = false>
+template <int BN, int A_MN, int B_MN, bool TMAS, int EK = 0>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC32, const CUtensorMap& tmC16, const KParams& p,
            int vec_ok, cudaStream_t stream) {
   using C = Cfg<BN, TMAS>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TMAS, SM>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TMAS, EK>;
   static bool configured = false;  // benign race: attribute set is idempotent
   if (!configured) {
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -1029,6 +1110,14 @@ bool use_tma_store(const mirror_gemm_args* g, const Epi* e, int vec, long long k
          g->N % 32 == 0 && tma_store_ok(g);
 }
 
+// the lean epilogue covers: bf16 output only, alpha, diag, bf16 residual(s) read row by row -- and nothing else
+// (MIRROR_B200_AB_NO_LEAN=1 keeps the generic epilogue: A/B switch)
+bool lean_epilogue_ok(const mirror_gemm_args* g) {
+  static const int off = [] { const char* v = getenv("MIRROR_B200_AB_NO_LEAN"); return v && *v == '1'; }();
+  return !off && g->out_bf16 && !g->out_f32 && !g->bias && g->act == MIRROR_ACT_NONE && g->drop_p == 0.f && g->beta == 0.f &&
+         (!g->res || g->res_is_bf16) && g->res_row_div <= 1 && g->mode == MIRROR_GEMM_NORMAL && g->split_k <= 1 && g->N % 32 == 0;
+}
+
 int make_output_maps(const mirror_gemm_args* g, CUtensorMap* c32, CUtensorMap* c16) {
   int rc = 0;
   if (g->out_f32) rc = make_output_map(c32, g->out_f32, true, g->M, g->N, g->ldc32, g->c32_bs1, g->batch1, g->c32_bs2, g->batch2);
@@ -1054,10 +1143,10 @@ int launch_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams
 }
 
 
-template <int BN, bool TMAS>
+template <int BN, bool TMAS, int EK = 0>
 int launch_multi(const MultiMaps& maps, const KParams& p, const MultiInfo& mi, int vec_ok, cudaStream_t stream) {
   using C = Cfg<BN, TMAS>;
-  auto kern = gemm_tcgen05_multi_kernel<BN, TMAS>;
+  auto kern = gemm_tcgen05_multi_kernel<BN, TMAS, EK>;
   static bool configured = false;
   if (!configured) {
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -1237,12 +1326,25 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
   }
   if (g->mode != MIRROR_GEMM_NORMAL) {  // the fused softmax epilogues exist for K-major operands (q k^T-shaped products) only
     MB_CHECK_ARG(key == 0, "gemm: softmax modes need K-major A and B");
-    if (BN == 256) return tmas ? launch<256, 0, 0, true, true>(tmA, tmB, tmC32, tmC16, p, vec, stream)
-                               : launch<256, 0, 0, false, true>(tmA, tmB, tmC32, tmC16, p, vec, stream);
-    if (BN == 192) return tmas ? launch<192, 0, 0, true, true>(tmA, tmB, tmC32, tmC16, p, vec, stream)
-                               : launch<192, 0, 0, false, true>(tmA, tmB, tmC32, tmC16, p, vec, stream);
-    return tmas ? launch<128, 0, 0, true, true>(tmA, tmB, tmC32, tmC16, p, vec, stream)
-                : launch<128, 0, 0, false, true>(tmA, tmB, tmC32, tmC16, p, vec, stream);
+    if (BN == 256) return tmas ? launch<256, 0, 0, true, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream)
+                               : launch<256, 0, 0, false, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream);
+    if (BN == 192) return tmas ? launch<192, 0, 0, true, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream)
+                               : launch<192, 0, 0, false, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream);
+    return tmas ? launch<128, 0, 0, true, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream)
+                : launch<128, 0, 0, false, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream);
+  }
+  if (tmas && lean_epilogue_ok(g)) {
+#define MB_DISPATCHL(BNV)                                                           \
+  switch (key) {                                                                    \
+    case 0: return launch<BNV, 0, 0, true, 2>(tmA, tmB, tmC32, tmC16, p, vec, stream);   \
+    case 1: return launch<BNV, 0, 1, true, 2>(tmA, tmB, tmC32, tmC16, p, vec, stream);   \
+    case 2: return launch<BNV, 1, 0, true, 2>(tmA, tmB, tmC32, tmC16, p, vec, stream);   \
+    default: return launch<BNV, 1, 1, true, 2>(tmA, tmB, tmC32, tmC16, p, vec, stream);  \
+  }
+    if (BN == 256) { MB_DISPATCHL(256) }
+    if (BN == 192) { MB_DISPATCHL(192) }
+    MB_DISPATCHL(128)
+#undef MB_DISPATCHL
   }
 #define MB_DISPATCH(BNV, TM)                                                        \
   switch (key) {                                                                    \
@@ -1306,6 +1408,11 @@ extern "C" int mirror_gemm_bf16_multi(const mirror_gemm_args* terms, int32_t nte
   if (tmas) {
     rc = make_output_maps(g, &maps.c32, &maps.c16);
     if (rc) return rc;
+  }
+  if (tmas && lean_epilogue_ok(g)) {
+    if (BN == 256) return launch_multi<256, true, 2>(maps, p, mi, vec, stream);
+    if (BN == 192) return launch_multi<192, true, 2>(maps, p, mi, vec, stream);
+    return launch_multi<128, true, 2>(maps, p, mi, vec, stream);
   }
   if (BN == 256) return tmas ? launch_multi<256, true>(maps, p, mi, vec, stream) : launch_multi<256, false>(maps, p, mi, vec, stream);
   if (BN == 192) return tmas ? launch_multi<192, true>(maps, p, mi, vec, stream) : launch_multi<192, false>(maps, p, mi, vec, stream);
