@@ -1106,7 +1106,8 @@ bool tma_store_ok(const mirror_gemm_args* g) {
 bool use_tma_store(const mirror_gemm_args* g, const Epi* e, int vec, long long ktot) {
   static const int env = [] { const char* v = getenv("MIRROR_B200_TMA_STORE"); return v && *v ? atoi(v) : -1; }();
   if (env == 0) return false;
-  return (g->out_f32 || g->out_bf16) && vec && !e->atomic && e->act != MIRROR_ACT_GELU && g->split_k <= 1 && ktot <= 1024 &&
+  static const long long kmax = [] { const char* v = getenv("MIRROR_B200_AB_TMAS_KMAX"); return v && *v ? atoll(v) : 3072LL; }();
+  return (g->out_f32 || g->out_bf16) && vec && !e->atomic && e->act != MIRROR_ACT_GELU && g->split_k <= 1 && ktot <= kmax &&
          g->N % 32 == 0 && tma_store_ok(g);
 }
 
