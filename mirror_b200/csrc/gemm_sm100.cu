@@ -262,16 +262,18 @@ __device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, uint32_t taddr,
 
 // Fused row-softmax epilogues (MIRROR_GEMM_ROWSTATS / SOFTMAX / ROWDOT / SOFTMAX_BWD): thread = row, this warp's BN/2
 // columns are one "part" of the row.  Logits live in the base-2 domain (x2 = alpha*log2(e)*acc) so exp is one MUFU.EX2.
-template <int BN>
+// MODE != 0: the mode is a compile-time constant of the instantiation (all mode tests fold away); 0: read it from e.mode
+template <int BN, int MODE = 0>
 __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, uint32_t taddr, int b1, int b2, int row0, int cbase,
                                                       int lane, uint64_t* tfull_bar, uint32_t aphase, int part) {
   constexpr int NCH = BN / 64;
+  const int mode = MODE ? MODE : e.mode;
   const int row = row0 + lane;
   const bool row_ok = row < e.M;
   float2* stats = reinterpret_cast<float2*>(e.stats) + ((long long)(b2 * e.batch1 + b1) * e.M + (row_ok ? row : 0)) * e.nparts;
   const float a2 = e.alpha * 1.4426950408889634f;
   float M2 = 0.f, invS = 0.f, dot = 0.f;
-  if (row_ok && e.mode == MIRROR_GEMM_SOFTMAX) {  // combine the partials of pass 1 (these loads overlap the tile's MMAs)
+  if (row_ok && mode == MIRROR_GEMM_SOFTMAX) {  // combine the partials of pass 1 (these loads overlap the tile's MMAs)
     float m = -INFINITY;
     for (int i = 0; i < e.nparts; ++i) m = fmaxf(m, stats[i].x);
     float ssum = 0.f;
@@ -281,9 +283,9 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
     }
     M2 = m;
     invS = 1.f / ssum;
-  } else if (row_ok && e.mode == MIRROR_GEMM_SOFTMAX_BWD) {
+  } else if (row_ok && mode == MIRROR_GEMM_SOFTMAX_BWD) {
     for (int i = 0; i < e.nparts; ++i) dot += stats[i].x;
-  } else if (row_ok && e.mode == MIRROR_GEMM_SOFTMAX_BWD_DOT) {
+  } else if (row_ok && mode == MIRROR_GEMM_SOFTMAX_BWD_DOT) {
     dot = e.stats[(long long)(b2 * e.batch1 + b1) * e.M + row];
   }
   mbar_wait(tfull_bar, aphase);
@@ -301,11 +303,11 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
     tmem_ld_32x32(taddr + c * 32, acc);
     tmem_ld_wait();
     float v[32];
-    if (e.mode == 6) {  // measurement only (tools/softmax_gemm_probe.py): the cost of draining TMEM and of the tile hand-shake alone
+    if (mode == 6) {  // measurement only (tools/softmax_gemm_probe.py): the cost of draining TMEM and of the tile hand-shake alone
       run_dot += __uint_as_float(acc[0]) + __uint_as_float(acc[31]);
       continue;
     }
-    if (e.mode == MIRROR_GEMM_ROWSTATS) {
+    if (mode == MIRROR_GEMM_ROWSTATS) {
       float cm = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -322,7 +324,7 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
       run_s += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       continue;
     }
-    if (e.mode == MIRROR_GEMM_SOFTMAX) {
+    if (mode == MIRROR_GEMM_SOFTMAX) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fast_exp2(a2 * __uint_as_float(acc[j]) - M2) * invS;
     } else {  // ROWDOT / SOFTMAX_BWD read the probabilities
@@ -344,7 +346,7 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
           v[j * 8 + 2 * t + 1] = f.y;
         }
       }
-      if (e.mode == MIRROR_GEMM_ROWDOT) {
+      if (mode == MIRROR_GEMM_ROWDOT) {
         float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 32; ++j) d4[j & 3] += v[j] * __uint_as_float(acc[j]);
@@ -377,8 +379,8 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
     }
   }
   if (row_ok) {
-    if (e.mode == MIRROR_GEMM_ROWSTATS) stats[part] = make_float2(run_m, run_s);
-    else if (e.mode == MIRROR_GEMM_ROWDOT || e.mode == 6) stats[part] = make_float2(run_dot, 0.f);
+    if (mode == MIRROR_GEMM_ROWSTATS) stats[part] = make_float2(run_m, run_s);
+    else if (mode == MIRROR_GEMM_ROWDOT || mode == 6) stats[part] = make_float2(run_dot, 0.f);
   }
 }
 
@@ -395,7 +397,8 @@ __device__ __forceinline__ void epilogue_tile_lean(const Epi& e, uint32_t taddr,
   constexpr int NCH = BN / 64;
   const int row = row0 + lane;
   const bool row_ok = row < e.M;
-  const long long roff = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)row * e.ldr;
+  const int rrow = e.res_row_div > 1 ? row / e.res_row_div : row;  // row-broadcast residual (landmark-mean backward)
+  const long long roff = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)rrow * e.ldr;
   const bf16* r1 = (e.res && row_ok) ? reinterpret_cast<const bf16*>(e.res) + roff : nullptr;
   const bf16* r2 = (e.res2 && row_ok) ? e.res2 + roff : nullptr;
   uint4 pa[4];  // residual of the chunk to come: requested before the accumulator is waited for / before the previous chunk's math
@@ -469,6 +472,10 @@ __device__ __forceinline__ void epilogue_tile(const Epi& e, bool fast, uint32_t 
   constexpr int NCH = BN / 64;  // 32-column chunks per thread
   if constexpr (EK == 1) {
     epilogue_tile_softmax<BN>(e, sink, taddr, b1, b2, row0, cbase, lane, tfull_bar, aphase, part);
+    return;
+  }
+  if constexpr (EK >= 11) {  // one softmax mode, fixed at compile time
+    epilogue_tile_softmax<BN, EK - 10>(e, sink, taddr, b1, b2, row0, cbase, lane, tfull_bar, aphase, part);
     return;
   }
   if constexpr (EK == 2) {
@@ -1116,7 +1123,7 @@ bool use_tma_store(const mirror_gemm_args* g, const Epi* e, int vec, long long k
 bool lean_epilogue_ok(const mirror_gemm_args* g) {
   static const int off = [] { const char* v = getenv("MIRROR_B200_AB_NO_LEAN"); return v && *v == '1'; }();
   return !off && g->out_bf16 && !g->out_f32 && !g->bias && g->act == MIRROR_ACT_NONE && g->drop_p == 0.f && g->beta == 0.f &&
-         (!g->res || g->res_is_bf16) && g->res_row_div <= 1 && g->mode == MIRROR_GEMM_NORMAL && g->split_k <= 1 && g->N % 32 == 0;
+         (!g->res || g->res_is_bf16) && g->mode == MIRROR_GEMM_NORMAL && g->split_k <= 1 && g->N % 32 == 0;
 }
 
 int make_output_maps(const mirror_gemm_args* g, CUtensorMap* c32, CUtensorMap* c16) {
@@ -1327,12 +1334,23 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
   }
   if (g->mode != MIRROR_GEMM_NORMAL) {  // the fused softmax epilogues exist for K-major operands (q k^T-shaped products) only
     MB_CHECK_ARG(key == 0, "gemm: softmax modes need K-major A and B");
-    if (BN == 256) return tmas ? launch<256, 0, 0, true, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream)
-                               : launch<256, 0, 0, false, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream);
-    if (BN == 192) return tmas ? launch<192, 0, 0, true, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream)
-                               : launch<192, 0, 0, false, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream);
-    return tmas ? launch<128, 0, 0, true, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream)
-                : launch<128, 0, 0, false, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream);
+    // one instantiation per mode (the mode tests fold away); writers go through the bulk-store sink, the two statistics
+    // passes have no output.  Anything else (unaligned outputs) falls back to the instantiation that reads e.mode.
+#define MB_SOFTMAX(BNV)                                                                                            \
+  switch (g->mode) {                                                                                                \
+    case MIRROR_GEMM_ROWSTATS: return launch<BNV, 0, 0, false, 11>(tmA, tmB, tmC32, tmC16, p, vec, stream);          \
+    case MIRROR_GEMM_ROWDOT: return launch<BNV, 0, 0, false, 13>(tmA, tmB, tmC32, tmC16, p, vec, stream);            \
+    case MIRROR_GEMM_SOFTMAX: if (tmas) return launch<BNV, 0, 0, true, 12>(tmA, tmB, tmC32, tmC16, p, vec, stream); break;          \
+    case MIRROR_GEMM_SOFTMAX_BWD: if (tmas) return launch<BNV, 0, 0, true, 14>(tmA, tmB, tmC32, tmC16, p, vec, stream); break;      \
+    case MIRROR_GEMM_SOFTMAX_BWD_DOT: if (tmas) return launch<BNV, 0, 0, true, 15>(tmA, tmB, tmC32, tmC16, p, vec, stream); break;  \
+    default: break;                                                                                                 \
+  }                                                                                                                 \
+  return tmas ? launch<BNV, 0, 0, true, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream)                                   \
+              : launch<BNV, 0, 0, false, 1>(tmA, tmB, tmC32, tmC16, p, vec, stream);
+    if (BN == 256) { MB_SOFTMAX(256) }
+    if (BN == 192) { MB_SOFTMAX(192) }
+    MB_SOFTMAX(128)
+#undef MB_SOFTMAX
   }
   if (tmas && lean_epilogue_ok(g)) {
 #define MB_DISPATCHL(BNV)                                                           \

@@ -546,12 +546,12 @@ class NystromLayerFn(Function):
 
         # ---- similarities (1/sqrt(d) already folded into ds*).  Landmark gradients first (each a two-term GEMM), then dq / dk
         # with the landmark-mean backward fused as a row-broadcast residual: row t of q receives dql[t // seg] / seg.
-        dlm32 = torch.empty(B, m, 2 * E, device=dev, dtype=F32)
-        K.gemm(ds2, _T(kl), more=[(ds3, _T(k))], out_f32=_heads(dlm32, 0, E))             # dql = ds2 kl + ds3 k
-        K.gemm(_T(ds1), _T(q), more=[(_T(ds2), _T(ql))], out_f32=_heads(dlm32, E, E))     # dkl = ds1^T q + ds2^T ql
-        K.gemm(ds1, _T(kl), out_bf16=_heads(dqkv16, 0, E), res=_heads(dlm32, 0, E), gamma=1.0 / seg, res_row_div=seg)      # dq
-        K.gemm(_T(ds3), _T(ql), out_bf16=_heads(dqkv16, E, E), res=_heads(dlm32, E, E), gamma=1.0 / seg, res_row_div=seg)  # dk
-        del ds1, ds2, ds3, dlm32
+        dlm16 = torch.empty(B, m, 2 * E, device=dev, dtype=BF16)  # bf16 like dq / dk themselves: the lean epilogue reads it
+        K.gemm(ds2, _T(kl), more=[(ds3, _T(k))], out_bf16=_heads(dlm16, 0, E))             # dql = ds2 kl + ds3 k
+        K.gemm(_T(ds1), _T(q), more=[(_T(ds2), _T(ql))], out_bf16=_heads(dlm16, E, E))     # dkl = ds1^T q + ds2^T ql
+        K.gemm(ds1, _T(kl), out_bf16=_heads(dqkv16, 0, E), res=_heads(dlm16, 0, E), gamma=1.0 / seg, res_row_div=seg)      # dq
+        K.gemm(_T(ds3), _T(ql), out_bf16=_heads(dqkv16, E, E), res=_heads(dlm16, E, E), gamma=1.0 / seg, res_row_div=seg)  # dk
+        del ds1, ds2, ds3, dlm16
 
         # ---- to_qkv and LayerNorm
         dxn = torch.empty(B, n, E, device=dev, dtype=F32)
