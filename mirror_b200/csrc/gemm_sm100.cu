@@ -295,6 +295,7 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
   const int rowA = row0 + (lane & ~1);
   const bool okA = rowA < e.M, okB = rowA + 1 < e.M;
   float run_m = -INFINITY, run_s = 0.f, run_dot = 0.f;
+  const float nad = -e.alpha * dot;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int col0 = cbase + c * 32;
@@ -354,7 +355,7 @@ __device__ __forceinline__ void epilogue_tile_softmax(const Epi& e, Sink& sink, 
         continue;
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = e.alpha * v[j] * (__uint_as_float(acc[j]) - dot);
+      for (int j = 0; j < 32; ++j) v[j] *= fmaf(e.alpha, __uint_as_float(acc[j]), nad);  // P * (alpha*G - alpha*dot): two ops per element
     }
     if (e.o32) {
       uint4 pc[8];
