@@ -112,6 +112,47 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, long long bs_dy, lo
   }
 }
 
+// The same for C % 4 == 0 and 16-byte aligned rows: one warp per (b,t) row, float4 lanes -- no 64-bit div/mod per element
+// (the scalar kernel moved 0.6 GB in 0.4 ms on the dropout backward of a token matrix).
+__global__ void __launch_bounds__(256)
+act_bwd_rows_kernel(const float* __restrict__ dy, long long bs_dy, long long ld_dy, const float* __restrict__ pre, long long bs_pre,
+                    long long ld_pre, int B, int T, int C, int act, float drop_p, float drop_scale, uint64_t seed,
+                    bf16* __restrict__ o16, long long bs16, long long ld16, float* __restrict__ o32, long long bs32, long long ld32) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const long long rows = (long long)B * T;
+  for (long long r = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
+    const long long b = r / T;
+    const int t = (int)(r - b * T);
+    const float* gy = dy + b * bs_dy + t * ld_dy;
+    const float* px = pre ? pre + b * bs_pre + t * ld_pre : nullptr;
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 g = *reinterpret_cast<const float4*>(gy + c);
+      if (drop_p > 0.f) {
+        const uint64_t i = (uint64_t)r * C + c;  // dense (b,t,c) index, as in the forward
+        g.x = hash_u01(seed, i) >= drop_p ? g.x * drop_scale : 0.f;
+        g.y = hash_u01(seed, i + 1) >= drop_p ? g.y * drop_scale : 0.f;
+        g.z = hash_u01(seed, i + 2) >= drop_p ? g.z * drop_scale : 0.f;
+        g.w = hash_u01(seed, i + 3) >= drop_p ? g.w * drop_scale : 0.f;
+      }
+      if (act != MIRROR_ACT_NONE) {
+        const float4 x = *reinterpret_cast<const float4*>(px + c);
+        if (act == MIRROR_ACT_RELU) {
+          g.x = x.x > 0.f ? g.x : 0.f; g.y = x.y > 0.f ? g.y : 0.f; g.z = x.z > 0.f ? g.z : 0.f; g.w = x.w > 0.f ? g.w : 0.f;
+        } else {
+          g.x *= gelu_erf_grad(x.x); g.y *= gelu_erf_grad(x.y); g.z *= gelu_erf_grad(x.z); g.w *= gelu_erf_grad(x.w);
+        }
+      }
+      if (o16) {
+        uint2 u;
+        *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(g.x, g.y);
+        *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(g.z, g.w);
+        *reinterpret_cast<uint2*>(o16 + b * bs16 + t * ld16 + c) = u;
+      }
+      if (o32) *reinterpret_cast<float4*>(o32 + b * bs32 + t * ld32 + c) = g;
+    }
+  }
+}
+
 // h[b,0,:] = cls ; h[b,1+N+j,:] = h[b,1+j,:] for j < add      (models/mirror.py:656-665)
 __global__ void assemble_fwd_kernel(float* __restrict__ h, const float* __restrict__ cls, int B, int N, int add, int E) {
   const int S = 1 + N + add;
@@ -403,9 +444,19 @@ extern "C" int mirror_act_bwd(const float* dy, int64_t bs_dy, int64_t ld_dy, con
                               int64_t bs16, int64_t ld16, float* out_f32, int64_t bs32, int64_t ld32, mirror_stream_t stream) {
   MB_CHECK_ARG(dy && B > 0 && T > 0 && C > 0 && (out_bf16 || out_f32) && (act == 0 || pre) && drop_p >= 0.f && drop_p < 1.f,
                "act_bwd: bad args");
-  act_bwd_kernel<<<grid_for((long long)B * T * C, 256), 256, 0, STREAM>>>(
-      dy, bs_dy, ld_dy, pre, bs_pre, ld_pre, B, T, C, act, drop_p, 1.f / (1.f - drop_p), seed, reinterpret_cast<bf16*>(out_bf16),
-      bs16, ld16, out_f32, bs32, ld32);
+  auto al = [](const void* ptr, long long bs, long long ld, int bytes) {
+    return !ptr || (((reinterpret_cast<uintptr_t>(ptr) * 1ULL) % (4 * bytes)) == 0 && bs % 4 == 0 && ld % 4 == 0);
+  };
+  if (C % 4 == 0 && C >= 128 && al(dy, bs_dy, ld_dy, 4) && al(pre, bs_pre, ld_pre, 4) && al(out_bf16, bs16, ld16, 2) &&
+      al(out_f32, bs32, ld32, 4)) {
+    act_bwd_rows_kernel<<<grid_for((long long)B * T, 8), 256, 0, STREAM>>>(
+        dy, bs_dy, ld_dy, pre, bs_pre, ld_pre, B, T, C, act, drop_p, 1.f / (1.f - drop_p), seed, reinterpret_cast<bf16*>(out_bf16),
+        bs16, ld16, out_f32, bs32, ld32);
+  } else {
+    act_bwd_kernel<<<grid_for((long long)B * T * C, 256), 256, 0, STREAM>>>(
+        dy, bs_dy, ld_dy, pre, bs_pre, ld_pre, B, T, C, act, drop_p, 1.f / (1.f - drop_p), seed, reinterpret_cast<bf16*>(out_bf16),
+        bs16, ld16, out_f32, bs32, ld32);
+  }
   MB_LAUNCH_CHECK();
   return 0;
 }

@@ -94,12 +94,13 @@ def test_copy_rows_axpy():
 
 @pytest.mark.parametrize("act", [0, 1, 2])
 @pytest.mark.parametrize("p", [0.0, 0.1])
-def test_act_fwd_bwd(act, p):
-    pre = rn(7, 33, 40)
+@pytest.mark.parametrize("C", [40, 768])  # 768: the float4 warp-per-row kernel
+def test_act_fwd_bwd(act, p, C):
+    pre = rn(7, 33, C)
     both("act_fwd", (pre, act, p, 99), {"want_bf16": True, "want_f32": True}, tol=2e-6)
-    dy = rn(7, 33, 40, seed=5)
-    out32 = torch.zeros(7, 40, 40)[:, :33, :]  # padded destination view
-    out16 = torch.zeros(7, 33, 40, dtype=BF16)
+    dy = rn(7, 33, C, seed=5)
+    out32 = torch.zeros(7, 40, C)[:, :33, :]  # padded destination view
+    out16 = torch.zeros(7, 33, C, dtype=BF16)
     a_gpu = to_dev((dy, pre, out16, out32))
     K.act_bwd(a_gpu[0], a_gpu[1], act, p, 99, out16=a_gpu[2], out32=a_gpu[3])
     c16, c32 = out16.clone(), out32.clone()
