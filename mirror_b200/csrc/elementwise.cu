@@ -61,6 +61,40 @@ __global__ void cast_split3_kernel(const float* __restrict__ src, long long rows
   }
 }
 
+// 8 columns per thread (cols, cols_out, lds multiples of 8, 16-byte aligned bases): two float4 loads, three 16-byte stores
+__global__ void cast_split3_vec_kernel(const float* __restrict__ src, long long rows, int cols, long long lds,
+                                       bf16* __restrict__ dst, long long rows_out, int cols_out, int stack_rows, int order) {
+  const int c8n = cols_out / 8;
+  const long long total = rows_out * c8n;
+  const long long ldd = stack_rows ? cols_out : 3LL * cols_out;
+  const long long blk = stack_rows ? rows_out * (long long)cols_out : cols_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c8n;
+    const int c = (int)(i - r * c8n) * 8;
+    float x[8];
+    if (r < rows && c < cols) {  // cols % 8 == 0: a group of 8 is inside or outside as a whole
+      const float4 a = *reinterpret_cast<const float4*>(src + r * lds + c), b = *reinterpret_cast<const float4*>(src + r * lds + c + 4);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = 0.f;
+    }
+    uint4 hi, lo;
+    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&hi);
+    __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&lo);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      hh[k] = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
+      const float2 hf = __bfloat1622float2(hh[k]);
+      ll[k] = __floats2bfloat162_rn(x[2 * k] - hf.x, x[2 * k + 1] - hf.y);
+    }
+    bf16* d = dst + r * ldd + c;
+    *reinterpret_cast<uint4*>(d) = hi;
+    *reinterpret_cast<uint4*>(d + blk) = order == 0 ? lo : hi;
+    *reinterpret_cast<uint4*>(d + 2 * blk) = order == 0 ? hi : lo;
+  }
+}
+
 // strided 2-D copy (gathers e.g. the cls rows of [B,N+1,E] into a dense [B,E] block)
 __global__ void copy_rows_kernel(const float* __restrict__ src, long long lds, long long rows, int cols, float* __restrict__ dst,
                                  long long ldd) {
@@ -222,6 +256,25 @@ __global__ void mask_pos_fwd_kernel(float* __restrict__ r, const float* __restri
     const int b = (int)(i / ((long long)E * T));
     const bool m = t >= first && mask[(long long)b * (T - first) + (t - first)] != 0.f;
     r[i] = (m ? tok[(long long)e * tok_stride] : r[i]) + pos[(long long)t * E + e];
+  }
+}
+// E % 4 == 0, tok_stride == 1: one warp per token row, float4 lanes (masked rows never read r)
+__global__ void __launch_bounds__(256)
+mask_pos_fwd_rows_kernel(float* __restrict__ r, const float* __restrict__ mask, const float* __restrict__ tok,
+                         const float* __restrict__ pos, int B, int T, int E, int first) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const long long rows = (long long)B * T;
+  for (long long row = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+    const long long b = row / T;
+    const int t = (int)(row - b * T);
+    const bool m = t >= first && mask[b * (T - first) + (t - first)] != 0.f;
+    float* rr = r + row * E;
+    const float* pp = pos + (long long)t * E;
+    for (int c = lane * 4; c < E; c += 128) {
+      const float4 a = m ? *reinterpret_cast<const float4*>(tok + c) : *reinterpret_cast<const float4*>(rr + c);
+      const float4 q = *reinterpret_cast<const float4*>(pp + c);
+      *reinterpret_cast<float4*>(rr + c) = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+    }
   }
 }
 // dr = masked ? 0 : dy (out of place: with distinct restrict pointers the loads of the slide loop are batched; the in-place
@@ -390,8 +443,14 @@ extern "C" int mirror_cast_split3(const float* src, int64_t rows, int32_t cols, 
                                   int32_t cols_out, int32_t stack_rows, int32_t order, mirror_stream_t stream) {
   MB_CHECK_ARG(src && dst && rows > 0 && cols > 0 && cols_out >= cols && rows_out >= rows && lds >= cols && (order == 0 || order == 1),
                "cast_split3: bad args");
-  cast_split3_kernel<<<grid_for(rows_out * (long long)cols_out, 256), 256, 0, STREAM>>>(
-      src, rows, cols, lds, reinterpret_cast<bf16*>(dst), rows_out, cols_out, stack_rows, order);
+  const bool al = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  if (cols % 8 == 0 && cols_out % 8 == 0 && lds % 8 == 0 && al) {
+    cast_split3_vec_kernel<<<grid_for(rows_out * (long long)(cols_out / 8), 256), 256, 0, STREAM>>>(
+        src, rows, cols, lds, reinterpret_cast<bf16*>(dst), rows_out, cols_out, stack_rows, order);
+  } else {
+    cast_split3_kernel<<<grid_for(rows_out * (long long)cols_out, 256), 256, 0, STREAM>>>(
+        src, rows, cols, lds, reinterpret_cast<bf16*>(dst), rows_out, cols_out, stack_rows, order);
+  }
   MB_LAUNCH_CHECK();
   return 0;
 }
@@ -494,7 +553,12 @@ extern "C" int mirror_rank_mask(const float* noise, int32_t B, int32_t N, int32_
 extern "C" int mirror_mask_pos_fwd(float* r, const float* mask, const float* tok, int32_t tok_stride, const float* pos,
                                    int32_t B, int32_t T, int32_t E, int32_t first, mirror_stream_t stream) {
   MB_CHECK_ARG(r && mask && tok && pos && B > 0 && T > first && E > 0 && first >= 0, "mask_pos_fwd: bad args");
-  mask_pos_fwd_kernel<<<grid_for((long long)B * T * E, 256), 256, 0, STREAM>>>(r, mask, tok, tok_stride, pos, B, T, E, first);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(tok) | reinterpret_cast<uintptr_t>(pos)) & 15) == 0;
+  if (E % 4 == 0 && E >= 128 && tok_stride == 1 && al16) {
+    mask_pos_fwd_rows_kernel<<<grid_for((long long)B * T, 8), 256, 0, STREAM>>>(r, mask, tok, pos, B, T, E, first);
+  } else {
+    mask_pos_fwd_kernel<<<grid_for((long long)B * T * E, 256), 256, 0, STREAM>>>(r, mask, tok, tok_stride, pos, B, T, E, first);
+  }
   MB_LAUNCH_CHECK();
   return 0;
 }

@@ -73,6 +73,7 @@ def test_cast_strided_rows():
 @pytest.mark.parametrize("stack,order", [(False, 0), (False, 1), (True, 0), (True, 1)])
 def test_cast_split3(stack, order):
     both("cast_split3", (rn(13, 77), 16, 80, stack, order), tol=1e-6)
+    both("cast_split3", (rn(13, 72), 16, 80, stack, order), tol=1e-6)  # multiples of 8: the 16-byte vector kernel
 
 
 def test_split3_product_is_fp32_grade():
@@ -131,7 +132,7 @@ def test_rank_mask_ties_are_stable():
     assert torch.equal(m.cpu()[0], (torch.arange(64) >= 16).float())
 
 
-@pytest.mark.parametrize("first,E,tok_stride", [(1, 48, 1), (0, 1, 0)])
+@pytest.mark.parametrize("first,E,tok_stride", [(1, 48, 1), (0, 1, 0), (1, 192, 1)])  # 192: float4 warp-per-row kernel
 def test_mask_pos(first, E, tok_stride):
     B, T = 3, 41
     mask = (torch.rand(B, T - first, generator=torch.Generator().manual_seed(1)) > 0.3).float()
