@@ -194,22 +194,27 @@ pinv_scale_kernel(const float* __restrict__ a2, int m, unsigned long long* __res
 __device__ __forceinline__ float key_val(unsigned long long k) { return __uint_as_float((unsigned)(k >> 32)); }
 __device__ __forceinline__ unsigned key_idx(unsigned long long k) { return 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFu); }
 
-// z0[bh,i,j] = a2[bh,j,i] / (c*r)  via a 32x32 shared tile
-__global__ void pinv_init_kernel(const float* __restrict__ a2, int m, const unsigned long long* __restrict__ keys,
-                                 float* __restrict__ z32, bf16* __restrict__ z16) {
-  __shared__ float tile[32][33];
+// z0[bh,i,j] = a2[bh,j,i] / (c*r)  via a 64x64 shared tile (256 threads = 64 columns x 4 row phases, 16 elements each)
+constexpr int TP = 64;
+__global__ void __launch_bounds__(256)
+pinv_init_kernel(const float* __restrict__ a2, int m, const unsigned long long* __restrict__ keys, float* __restrict__ z32,
+                 bf16* __restrict__ z16) {
+  __shared__ float tile[TP][TP + 1];
   const float inv = 1.f / (key_val(keys[0]) * key_val(keys[1]));
   const long long base = (long long)blockIdx.z * m * m;
-  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int i = i0 + r, j = j0 + threadIdx.x;
-    tile[r][threadIdx.x] = (i < m && j < m) ? a2[base + (long long)i * m + j] : 0.f;
+  const int i0 = blockIdx.y * TP, j0 = blockIdx.x * TP;
+  const int tx = threadIdx.x & (TP - 1), ty = threadIdx.x / TP;
+#pragma unroll 4
+  for (int r = ty; r < TP; r += 4) {
+    const int i = i0 + r, j = j0 + tx;
+    tile[r][tx] = (i < m && j < m) ? a2[base + (long long)i * m + j] : 0.f;
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int j = j0 + r, i = i0 + threadIdx.x;  // output row j, column i
+#pragma unroll 4
+  for (int r = ty; r < TP; r += 4) {
+    const int j = j0 + r, i = i0 + tx;  // output row j, column i
     if (i < m && j < m) {
-      const float v = tile[threadIdx.x][r] * inv;
+      const float v = tile[tx][r] * inv;
       if (z32) z32[base + (long long)j * m + i] = v;
       if (z16) z16[base + (long long)j * m + i] = __float2bfloat16(v);
     }
@@ -236,9 +241,10 @@ __global__ void dot_kernel(const float* __restrict__ a, const bf16* __restrict__
   s = block_sum(s, sh);
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
-__global__ void pinv_init_bwd_kernel(const float* __restrict__ gz0, int m, const unsigned long long* __restrict__ keys,
-                                     const float* __restrict__ dotp, float* __restrict__ gx, int accumulate) {
-  __shared__ float tile[32][33];
+__global__ void __launch_bounds__(256)
+pinv_init_bwd_kernel(const float* __restrict__ gz0, int m, const unsigned long long* __restrict__ keys,
+                     const float* __restrict__ dotp, float* __restrict__ gx, int accumulate) {
+  __shared__ float tile[TP][TP + 1];
   const float c = key_val(keys[0]), r = key_val(keys[1]);
   const float D = c * r, inv = 1.f / D;
   const float dD = -dotp[0] * inv;
@@ -246,16 +252,19 @@ __global__ void pinv_init_bwd_kernel(const float* __restrict__ gz0, int m, const
   const unsigned arg_row = key_idx(keys[0]), arg_col = key_idx(keys[1]);
   const int bh = blockIdx.z;
   const long long base = (long long)bh * m * m;
-  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;  // output tile rows i0.., cols j0..
-  for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
-    const int j = j0 + rr, i = i0 + threadIdx.x;  // read g_z0[j, i]
-    tile[rr][threadIdx.x] = (i < m && j < m) ? gz0[base + (long long)j * m + i] : 0.f;
+  const int i0 = blockIdx.y * TP, j0 = blockIdx.x * TP;  // output tile rows i0.., cols j0..
+  const int tx = threadIdx.x & (TP - 1), ty = threadIdx.x / TP;
+#pragma unroll 4
+  for (int rr = ty; rr < TP; rr += 4) {
+    const int j = j0 + rr, i = i0 + tx;  // read g_z0[j, i]
+    tile[rr][tx] = (i < m && j < m) ? gz0[base + (long long)j * m + i] : 0.f;
   }
   __syncthreads();
-  for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
-    const int i = i0 + rr, j = j0 + threadIdx.x;
+#pragma unroll 4
+  for (int rr = ty; rr < TP; rr += 4) {
+    const int i = i0 + rr, j = j0 + tx;
     if (i < m && j < m) {
-      float v = tile[threadIdx.x][rr] * inv;
+      float v = tile[tx][rr] * inv;
       if ((unsigned)(bh * m + i) == arg_row) v += dc;
       if ((unsigned)(bh * m + j) == arg_col) v += dr;
       float* p = gx + base + (long long)i * m + j;
@@ -321,8 +330,8 @@ extern "C" int mirror_pinv_init(const float* a2, int32_t BH, int32_t m, void* sc
   MB_CUDA(cudaMemsetAsync(scratch32, 0, 32, STREAM));
   pinv_scale_kernel<<<BH, 512, 0, STREAM>>>(a2, m, reinterpret_cast<unsigned long long*>(scratch32));
   MB_LAUNCH_CHECK();
-  dim3 grid((m + 31) / 32, (m + 31) / 32, BH), block(32, 8);
-  pinv_init_kernel<<<grid, block, 0, STREAM>>>(a2, m, reinterpret_cast<const unsigned long long*>(scratch32), z_f32,
+  dim3 grid((m + TP - 1) / TP, (m + TP - 1) / TP, BH);
+  pinv_init_kernel<<<grid, 256, 0, STREAM>>>(a2, m, reinterpret_cast<const unsigned long long*>(scratch32), z_f32,
                                                reinterpret_cast<bf16*>(z_bf16));
   MB_LAUNCH_CHECK();
   return 0;
@@ -335,8 +344,8 @@ extern "C" int mirror_pinv_init_bwd(const float* gz0, const void* z0_bf16, int32
   const long long n = (long long)BH * m * m;
   dot_kernel<<<ew_grid(n, 256 * 8), 256, 0, STREAM>>>(gz0, reinterpret_cast<const bf16*>(z0_bf16), n, dotp);
   MB_LAUNCH_CHECK();
-  dim3 grid((m + 31) / 32, (m + 31) / 32, BH), block(32, 8);
-  pinv_init_bwd_kernel<<<grid, block, 0, STREAM>>>(gz0, m, reinterpret_cast<const unsigned long long*>(scratch32), dotp, gx,
+  dim3 grid((m + TP - 1) / TP, (m + TP - 1) / TP, BH);
+  pinv_init_bwd_kernel<<<grid, 256, 0, STREAM>>>(gz0, m, reinterpret_cast<const unsigned long long*>(scratch32), dotp, gx,
                                                    accumulate);
   MB_LAUNCH_CHECK();
   return 0;
