@@ -1305,7 +1305,14 @@ extern "C" int mirror_gemm_bf16(const mirror_gemm_args* g, mirror_stream_t strea
     }
   }
   // N tile: 256 when it divides N (or N is large), 192 for N = 384-like sizes (the Nystrom landmark matrices), else 128.
-  const int BN = tile_n_for(g->N);
+  int BN = tile_n_for(g->N);
+  {  // a batch-sized product (M = 64 rows) has only N / BN tiles and streams its weight through that many SMs: narrower tiles
+     // double the SMs that pull on the weight (MIRROR_B200_AB_NO_NARROW=1: A/B switch)
+    static const int off = [] { const char* v = getenv("MIRROR_B200_AB_NO_NARROW"); return v && *v == '1'; }();
+    const long long tiles256 = (long long)((g->M + BM - 1) / BM) * ((g->N + 255) / 256) * g->batch1 * g->batch2 *
+                               (g->split_k > 1 ? g->split_k : 1);
+    if (!off && BN == 256 && g->mode == MIRROR_GEMM_NORMAL && g->N % 128 == 0 && tiles256 * 2 <= num_sms()) BN = 128;
+  }
   p.K = g->K;
   p.batch1 = g->batch1;
   p.batch2 = g->batch2;
