@@ -20,6 +20,7 @@ constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kAccStages = 2;
+constexpr int kMaxAccStages = 4;  // barrier slots reserved; 128-wide tiles use all four (4 x 128 = the 512 TMEM columns)
 
 struct KParams {
   Epi e;
@@ -38,8 +39,10 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = TMAS ? kEpiWarps * kSinkBytes : 0;
   static constexpr int STAGES = ((BN == 256) ? 4 : (BN == 192 ? 5 : 6)) - ((TMAS && BN == 192) ? 1 : 0);
-  static constexpr int TMEM_COLS = (kAccStages * BN <= 256) ? 256 : 512;  // power of two >= 2 accumulator stages
-  static constexpr int BAR_BYTES = (2 * STAGES + 2 * kAccStages) * 8 + 16;
+  // accumulator stages in TMEM: the epilogue of tile i overlaps the MMAs of the following tiles; 4 for the 128-wide tile
+  static constexpr int ACC_STAGES = (BN == 128) ? 4 : kAccStages;
+  static constexpr int TMEM_COLS = (ACC_STAGES * BN <= 256) ? 256 : 512;
+  static constexpr int BAR_BYTES = (2 * STAGES + 2 * kMaxAccStages) * 8 + 16;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
 };
 
@@ -523,8 +526,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
-  uint64_t* tempty = tfull + kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
+  uint64_t* tempty = tfull + kMaxAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -538,7 +541,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], 1);
       }
-      for (int s = 0; s < kAccStages; ++s) {
+      for (int s = 0; s < C::ACC_STAGES; ++s) {
         mbar_init(&tfull[s], 1);
         mbar_init(&tempty[s], kEpiWarps);  // one arrive per epilogue warp
       }
@@ -607,8 +610,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int tile = w / p.split_k, ks = w - tile * p.split_k;
         const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
         if (kb0 >= kb1) continue;
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = it % C::ACC_STAGES;
+        const uint32_t aphase = (it / C::ACC_STAGES) & 1;
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -647,8 +650,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int b1 = t % p.batch1, b2 = t / p.batch1;
       const int cbase = nb * BN + half * (BN / 2);
       const int row0 = mb_ * BM + q * 32;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = it % C::ACC_STAGES;
+      const uint32_t aphase = (it / C::ACC_STAGES) & 1;
       epilogue_tile<BN, EK>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
                         &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();
@@ -693,8 +696,8 @@ gemm_tcgen05_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
-  uint64_t* tempty = tfull + kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
+  uint64_t* tempty = tfull + kMaxAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -875,8 +878,8 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
-  uint64_t* tempty = tfull + kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
+  uint64_t* tempty = tfull + kMaxAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && elect_one()) {
@@ -891,7 +894,7 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], 1);
       }
-      for (int s = 0; s < kAccStages; ++s) {
+      for (int s = 0; s < C::ACC_STAGES; ++s) {
         mbar_init(&tfull[s], 1);
         mbar_init(&tempty[s], kEpiWarps);
       }
@@ -949,8 +952,8 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
       uint32_t phase = 0;
       int it = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = it % C::ACC_STAGES;
+        const uint32_t aphase = (it / C::ACC_STAGES) & 1;
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -995,8 +998,8 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
       const int b1 = t % p.batch1, b2 = t / p.batch1;
       const int cbase = nb * BN + half * (BN / 2);
       const int row0 = mb_ * BM + q * 32;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = it % C::ACC_STAGES;
+      const uint32_t aphase = (it / C::ACC_STAGES) & 1;
       epilogue_tile<BN, EK>(p.e, fast, tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * (BN / 2), sink, b1, b2, row0, cbase, lane,
                         &tfull[as], aphase, nb * 2 + half);
       tc_fence_before();

@@ -62,6 +62,8 @@ timed("pinv 384^3 NN bf16 (no res)", lambda: K.gemm(z, z.transpose(-1, -2), out_
 timed("pinv 384^3 NT bf16 + res", lambda: K.gemm(z, z, out_bf16=zo, res=z), 2 * B * hd * m * m * 2)
 timed("pinv 384^3 TN bf16", lambda: K.gemm(z.transpose(-1, -2), z.transpose(-1, -2), out_bf16=zo), B * hd * m * m * 2)
 if ONLY == "pinv":
+    stz = K.softmax_stats((B, hd), m, m, "cuda")
+    timed("pinv 384^3 NT NULL epilogue (mode 6)", lambda: K.gemm(z, z, mode=6, stats=stz))
     timed("pinv 384^3 multi3", lambda: K.gemm(z, z, more=[(z, z), (z.transpose(-1, -2), z.transpose(-1, -2))], out_bf16=zo, res=z, res2=z))
     sys.exit(0)
 # s3: [m, n] rows = landmarks, columns = tokens
