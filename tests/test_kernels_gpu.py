@@ -158,6 +158,11 @@ def test_gemm_row_broadcast_residual():
     o = torch.zeros(Bt, n, d, device="cuda", dtype=BF16)
     K.gemm(a.cuda(), b.cuda(), out_bf16=o, res=r.cuda(), gamma=1.0 / seg, res_row_div=seg)
     close(o, o_cpu, 8e-3, "row-broadcast residual")
+    # bf16 residual: the lean epilogue instantiation (bulk stores) takes the same product
+    r16 = r.to(BF16)
+    EMU.gemm(a, b, out_bf16=o_cpu, res=r16, gamma=1.0 / seg, res_row_div=seg)
+    K.gemm(a.cuda(), b.cuda(), out_bf16=o, res=r16.cuda(), gamma=1.0 / seg, res_row_div=seg)
+    close(o, o_cpu, 8e-3, "row-broadcast bf16 residual (lean epilogue)")
 
 
 def test_colsum():
