@@ -61,6 +61,22 @@ timed("pinv 384^3 NT bf16", lambda: K.gemm(z, z, out_bf16=zo, alpha=0.25), B * h
 timed("pinv 384^3 NN bf16 (no res)", lambda: K.gemm(z, z.transpose(-1, -2), out_bf16=zo), B * hd * m * m * 2)
 timed("pinv 384^3 NT bf16 + res", lambda: K.gemm(z, z, out_bf16=zo, res=z), 2 * B * hd * m * m * 2)
 timed("pinv 384^3 TN bf16", lambda: K.gemm(z.transpose(-1, -2), z.transpose(-1, -2), out_bf16=zo), B * hd * m * m * 2)
+if ONLY == "av":
+    # attention-value products: the n x m probabilities (906 MB) stream through once
+    a1 = torch.randn(B, hd, n, m, device="cuda", generator=g).to(torch.bfloat16)
+    w_ = torch.randn(B, hd, m, d, device="cuda", generator=g).to(torch.bfloat16)
+    do = torch.randn(B, n, E, device="cuda", generator=g).to(torch.bfloat16)
+    o16 = torch.empty(B, n, E, device="cuda", dtype=torch.bfloat16)
+    doh, oh = heads(do.repeat(1, 1, 3), 0), heads(o16.repeat(1, 1, 3), 0)
+    oh = o16.unflatten(-1, (hd, d)).permute(0, 2, 1, 3)
+    doh = do.unflatten(-1, (hd, d)).permute(0, 2, 1, 3)
+    timed("out = a1 w   [2304x96, K=384] NN", lambda: K.gemm(a1, w_.transpose(-1, -2), out_bf16=oh), B * hd * n * m * 2)
+    dw = torch.empty(B, hd, m, d, device="cuda", dtype=torch.bfloat16)
+    timed("dw = a1^T dO [384x96, K=2304] TN", lambda: K.gemm(a1.transpose(-1, -2), doh.transpose(-1, -2), out_bf16=dw), B * hd * n * m * 2)
+    w96 = torch.randn(B, hd, d, m, device="cuda", generator=g).to(torch.bfloat16)
+    stn = K.softmax_stats((B, hd), n, d, "cuda")
+    timed("out = a1 w   NT NULL epilogue", lambda: K.gemm(a1, w96, mode=6, stats=stn), B * hd * n * m * 2)
+    sys.exit(0)
 if ONLY == "pinv":
     stz = K.softmax_stats((B, hd), m, m, "cuda")
     timed("pinv 384^3 NT NULL epilogue (mode 6)", lambda: K.gemm(z, z, mode=6, stats=stz))
