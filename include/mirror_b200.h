@@ -183,9 +183,9 @@ int mirror_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
                          mirror_stream_t stream);
 /* dx:[B,x_rows,E] = (add ? add : 0) + LN-gradient (rows >= S: no LN term); `add` may alias dx (the residual branch of
  * models/mirror.py:312) */
-int mirror_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int32_t B,
-                         int32_t S, int32_t x_rows, int32_t E, int32_t n_out, int32_t pad, float* dx, const float* add,
-                         float* dgamma, float* dbeta, mirror_stream_t stream);
+int mirror_layernorm_bwd(const void* dy /* f32, or bf16 when dy_is_bf16 */, int32_t dy_is_bf16, const float* x, const float* gamma,
+                         const float* mean, const float* rstd, int32_t B, int32_t S, int32_t x_rows, int32_t E, int32_t n_out,
+                         int32_t pad, float* dx, const float* add, float* dgamma, float* dbeta, mirror_stream_t stream);
 /* row softmax of the three Nyström similarity matrices */
 int mirror_softmax_fwd(const float* x, int64_t rows, int32_t cols, void* y_bf16, float* y_f32, mirror_stream_t stream);
 int mirror_softmax_bwd(const void* y_bf16, const float* dy, int64_t rows, int32_t cols, float scale, void* dx_bf16, float* dx_f32,
@@ -209,6 +209,10 @@ int mirror_res_conv_bwd(const void* dout_bf16, const void* qkv_bf16, const float
 int mirror_pinv_init(const float* a2, int32_t BH, int32_t m, void* scratch32, float* z_f32, void* z_bf16, mirror_stream_t stream);
 int mirror_pinv_init_bwd(const float* gz0, const void* z0_bf16, int32_t BH, int32_t m, void* scratch32, float* gx, int32_t accumulate,
                          mirror_stream_t stream);
+/* The same followed by the row-softmax backward of attn2, fused: ds = scale * P * (g - rowsum(P g)) with
+ * g = ga2 + (the pinv_init_bwd terms), P = a2_bf16; ga2 is left untouched.  m % 32 == 0, m <= 512. */
+int mirror_pinv_init_softmax_bwd(const float* ga2, const float* gz0, const void* z0_bf16, const void* a2_bf16, int32_t BH, int32_t m,
+                                 void* scratch32, float scale, void* ds_bf16, mirror_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PPEG (ppeg.cu): models/mirror.py:317-331.  wm[49*E], bm[E], dwm[49*E], dbm[E] are caller-owned scratch.

@@ -82,10 +82,11 @@ SIGNATURES = {
     "mirror_colsum": [_P, _I32, _I64, _I32, _I64, _P, _P],
     "mirror_reparam_fwd": [_P, _P, _P, _I64, _P, _P, _P],
     "mirror_reparam_bwd": [_P, _P, _P, _I64, _P, _P, _P],
+    "mirror_pinv_init_softmax_bwd": [_P, _P, _P, _P, _I32, _I32, _P, _F, _P, _P],
     "mirror_rowdot_bf16": [_P, _P, _P, _I64, _I32, _P, _P],
     "mirror_token_fanout_bwd": [_P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, _P],
     "mirror_layernorm_fwd": [_P, _P, _P, _F, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
-    "mirror_layernorm_bwd": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "mirror_layernorm_bwd": [_P, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "mirror_softmax_fwd": [_P, _I64, _I32, _P, _P, _P],
     "mirror_softmax_bwd": [_P, _P, _I64, _I32, _F, _P, _P, _P],
     "mirror_l2norm_fwd": [_P, _I64, _I32, _I32, _F, _P, _P, _I64, _P, _P],

@@ -7,6 +7,17 @@ namespace {
 
 constexpr int kWarps = 8;
 
+// four consecutive gradient elements, from an f32 row or (dy16) from a bf16 row: the token-sized backward GEMM that produces
+// d(LN output) writes bf16 through its lean epilogue, and this kernel reads 2 instead of 4 bytes per element
+__device__ __forceinline__ float4 load_g4(const float* f32row, const bf16* b16row, int c) {
+  if (b16row) {
+    const uint2 u = *reinterpret_cast<const uint2*>(b16row + c);
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+  }
+  return *reinterpret_cast<const float4*>(f32row + c);
+}
+
 // ------------------------------------------------------------------ LayerNorm
 // x: [B, X, E] f32, of which the first S rows per slide are normalised (X > S drops the wrap-padding tokens of the WSI
 // encoder without a copy).  Outputs are written in a padded row layout [B, n_out, E] at row offset `pad`
@@ -71,7 +82,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 // x, dx, add: [B, X, E]; rows S..X-1 of a slide did not take part in the forward and receive dx = add (or 0).
 // dgamma/dbeta accumulate through shared-memory partials and one atomicAdd per block and column.
 __global__ void __launch_bounds__(kWarps * 32)
-ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+ln_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ dy16, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, int B, int S, int X, int E, int n_out, int pad,
               float* dx, const float* add, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float sh[];  // [2][E]
@@ -89,12 +100,14 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
       continue;
     }
     const float* xr = x + ri * E;
-    const float* gr = dy + ((long long)b * n_out + pad + s) * E;
+    const long long goff = ((long long)b * n_out + pad + s) * E;
+    const float* gr = dy16 ? nullptr : dy + goff;
+    const bf16* gr16 = dy16 ? dy16 + goff : nullptr;
     const float mu = mean[(long long)b * S + s], rs = rstd[(long long)b * S + s];
     float s1 = 0.f, s2 = 0.f;
     for (int c = lane * 4; c < E; c += 128) {
       const float4 v = *reinterpret_cast<const float4*>(xr + c);
-      const float4 g = *reinterpret_cast<const float4*>(gr + c);
+      const float4 g = load_g4(gr, gr16, c);
       const float4 w = *reinterpret_cast<const float4*>(gamma + c);
       const float gx = g.x * w.x, gy = g.y * w.y, gz = g.z * w.z, gw = g.w * w.w;
       s1 += gx + gy + gz + gw;
@@ -104,7 +117,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
     s2 = warp_sum(s2) * rs / E;  // mean(g * xhat)
     for (int c = lane * 4; c < E; c += 128) {
       const float4 v = *reinterpret_cast<const float4*>(xr + c);
-      const float4 g = *reinterpret_cast<const float4*>(gr + c);
+      const float4 g = load_g4(gr, gr16, c);
       const float4 w = *reinterpret_cast<const float4*>(gamma + c);
       const float hx = (v.x - mu) * rs, hy = (v.y - mu) * rs, hz = (v.z - mu) * rs, hw = (v.w - mu) * rs;
       float4 d;
@@ -138,7 +151,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
 constexpr int kRegWarps = 4;
 template <int ITERS>
 __global__ void __launch_bounds__(kRegWarps * 32, 3)
-ln_bwd_reg_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+ln_bwd_reg_kernel(const float* __restrict__ dy, const bf16* __restrict__ dy16, const float* __restrict__ x, const float* __restrict__ gamma,
                   const float* __restrict__ mean, const float* __restrict__ rstd, int B, int S, int X, int n_out, int pad,
                   float* dx, const float* add, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   constexpr int E = ITERS * 128;
@@ -165,14 +178,16 @@ ln_bwd_reg_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
       continue;
     }
     const float* xr = x + ri * E;
-    const float* gr = dy + ((long long)b * n_out + pad + s) * E;
+    const long long goff = ((long long)b * n_out + pad + s) * E;
+    const float* gr = dy16 ? nullptr : dy + goff;
+    const bf16* gr16 = dy16 ? dy16 + goff : nullptr;
     const float mu = mean[(long long)b * S + s], rs = rstd[(long long)b * S + s];
     float4 xv[ITERS], gv[ITERS];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < ITERS; ++i) {
       xv[i] = *reinterpret_cast<const float4*>(xr + lane * 4 + 128 * i);
-      gv[i] = *reinterpret_cast<const float4*>(gr + lane * 4 + 128 * i);
+      gv[i] = load_g4(gr, gr16, lane * 4 + 128 * i);
       xv[i].x = (xv[i].x - mu) * rs; xv[i].y = (xv[i].y - mu) * rs; xv[i].z = (xv[i].z - mu) * rs; xv[i].w = (xv[i].w - mu) * rs;
       const float gx = gv[i].x * w[i].x, gy = gv[i].y * w[i].y, gz = gv[i].z * w[i].z, gw = gv[i].w * w[i].w;
       s1 += gx + gy + gz + gw;
@@ -323,10 +338,12 @@ extern "C" int mirror_layernorm_fwd(const float* x, const float* gamma, const fl
   return 0;
 }
 
-extern "C" int mirror_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+extern "C" int mirror_layernorm_bwd(const void* dy_, int32_t dy_is_bf16, const float* x, const float* gamma, const float* mean, const float* rstd,
                                     int32_t B, int32_t S, int32_t x_rows, int32_t E, int32_t n_out, int32_t pad, float* dx,
                                     const float* add, float* dgamma, float* dbeta, mirror_stream_t stream) {
-  MB_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
+  MB_CHECK_ARG(dy_ && x && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
+  const float* dy = dy_is_bf16 ? nullptr : reinterpret_cast<const float*>(dy_);
+  const bf16* dy16 = dy_is_bf16 ? reinterpret_cast<const bf16*>(dy_) : nullptr;
   MB_CHECK_ARG(B > 0 && S > 0 && x_rows >= S && E % 4 == 0 && pad >= 0 && n_out >= S + pad, "layernorm_bwd: bad shape");
   const long long rows = (long long)B * x_rows;
   long long grid = (rows + kWarps * 4 - 1) / (kWarps * 4);  // >= 4 rows per warp to amortise the column atomics
@@ -336,10 +353,10 @@ extern "C" int mirror_layernorm_bwd(const float* dy, const float* x, const float
     long long rgrid = (rows + kRegWarps * 4 - 1) / (kRegWarps * 4);
     if (rgrid > (long long)num_sms() * 3) rgrid = (long long)num_sms() * 3;
     if (rgrid < 1) rgrid = 1;
-    ln_bwd_reg_kernel<6><<<(int)rgrid, kRegWarps * 32, 0, STREAM>>>(dy, x, gamma, mean, rstd, B, S, x_rows, n_out, pad, dx, add, dgamma,
-                                                                dbeta);
+    ln_bwd_reg_kernel<6><<<(int)rgrid, kRegWarps * 32, 0, STREAM>>>(dy, dy16, x, gamma, mean, rstd, B, S, x_rows, n_out, pad, dx, add,
+                                                                      dgamma, dbeta);
   } else {
-    ln_bwd_kernel<<<(int)grid, kWarps * 32, 2 * E * sizeof(float), STREAM>>>(dy, x, gamma, mean, rstd, B, S, x_rows, E, n_out, pad, dx,
+    ln_bwd_kernel<<<(int)grid, kWarps * 32, 2 * E * sizeof(float), STREAM>>>(dy, dy16, x, gamma, mean, rstd, B, S, x_rows, E, n_out, pad, dx,
                                                                              add, dgamma, dbeta);
   }
   MB_LAUNCH_CHECK();

@@ -273,6 +273,52 @@ pinv_init_bwd_kernel(const float* __restrict__ gz0, int m, const unsigned long l
   }
 }
 
+// pinv_init_bwd followed by the row-softmax backward of attn2, in one pass:
+//   g[i,j] = ga2[i,j] + gz0[j,i]/D + [row i is the arg-max row]*dc + [col j is the arg-max col]*dr
+//   ds[i,j] = scale * p[i,j] * (g[i,j] - sum_j p[i,j] g[i,j])                       (p = bf16 attn2)
+// One CTA = 32 rows of one matrix: the m x 32 block of gz0 those rows need is staged (transposed use) in shared memory,
+// then each warp finishes 4 rows with the row kept in registers (m <= 512).  Saves the read-modify-write of ga2 and its
+// re-read by a separate softmax kernel (1.5 GB -> 0.9 GB per layer at the benchmark shape).
+constexpr int kFuseMaxChunks = 16;
+__global__ void __launch_bounds__(256)
+pinv_init_softmax_bwd_kernel(const float* __restrict__ ga2, const float* __restrict__ gz0, const bf16* __restrict__ p16, int m,
+                             const unsigned long long* __restrict__ keys, const float* __restrict__ dotp, float scale,
+                             bf16* __restrict__ ds16) {
+  extern __shared__ float tile[];  // [m][33]
+  const float c = key_val(keys[0]), r = key_val(keys[1]);
+  const float D = c * r, inv = 1.f / D;
+  const float dD = -dotp[0] * inv;
+  const float dc = dD * r, dr = dD * c;
+  const unsigned arg_row = key_idx(keys[0]), arg_col = key_idx(keys[1]);
+  const int bh = blockIdx.y, i0 = blockIdx.x * 32;
+  const long long base = (long long)bh * m * m;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < m; j += 8) tile[j * 33 + lane] = (i0 + lane < m) ? gz0[base + (long long)j * m + i0 + lane] : 0.f;
+  __syncthreads();
+  const int nch = m / 32;
+  for (int ii = warp * 4; ii < warp * 4 + 4; ++ii) {
+    const int i = i0 + ii;
+    if (i >= m) break;
+    const float rowadd = ((unsigned)(bh * m + i) == arg_row) ? dc : 0.f;
+    float g[kFuseMaxChunks], p[kFuseMaxChunks];
+    float dot = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < kFuseMaxChunks; ++cc) {
+      if (cc < nch) {
+        const int j = cc * 32 + lane;
+        g[cc] = ga2[base + (long long)i * m + j] + tile[j * 33 + ii] * inv + rowadd + (((unsigned)(bh * m + j) == arg_col) ? dr : 0.f);
+        p[cc] = __bfloat162float(p16[base + (long long)i * m + j]);
+        dot += p[cc] * g[cc];
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int cc = 0; cc < kFuseMaxChunks; ++cc) {
+      if (cc < nch) ds16[base + (long long)i * m + cc * 32 + lane] = __float2bfloat16(scale * p[cc] * (g[cc] - dot));
+    }
+  }
+}
+
 }  // namespace
 }  // namespace mb
 
@@ -319,6 +365,29 @@ extern "C" int mirror_res_conv_bwd(const void* dout_bf16, const void* qkv, const
   const int wspc = conv_strips_per_chunk(B, n, E, 24);
   res_conv_wgrad_kernel<<<dim3(grid.x, ((n + TT - 1) / TT + wspc - 1) / wspc, B), 128, 0, STREAM>>>(
       reinterpret_cast<const bf16*>(dout_bf16), reinterpret_cast<const bf16*>(qkv), n, E, E / 8, dw, wspc);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+/* ds_bf16 = softmax_bwd(attn2, ga2 + pinv_init_bwd terms) without touching ga2; needs m % 32 == 0 and m <= 512 */
+extern "C" int mirror_pinv_init_softmax_bwd(const float* ga2, const float* gz0, const void* z0_bf16, const void* a2_bf16, int32_t BH,
+                                            int32_t m, void* scratch32, float scale, void* ds_bf16, mirror_stream_t stream) {
+  MB_CHECK_ARG(ga2 && gz0 && z0_bf16 && a2_bf16 && scratch32 && ds_bf16 && BH > 0 && m > 0 && m % 32 == 0 && m <= 32 * kFuseMaxChunks,
+               "pinv_init_softmax_bwd: bad args (m must be a multiple of 32, at most 512)");
+  float* dotp = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch32) + 16);
+  MB_CUDA(cudaMemsetAsync(dotp, 0, 4, STREAM));
+  const long long n = (long long)BH * m * m;
+  dot_kernel<<<ew_grid(n, 256 * 8), 256, 0, STREAM>>>(gz0, reinterpret_cast<const bf16*>(z0_bf16), n, dotp);
+  MB_LAUNCH_CHECK();
+  const size_t smem = (size_t)m * 33 * sizeof(float);
+  static bool configured = false;  // benign race: idempotent
+  if (!configured) {
+    MB_CUDA(cudaFuncSetAttribute(pinv_init_softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kFuseMaxChunks * 33 * 4));
+    configured = true;
+  }
+  pinv_init_softmax_bwd_kernel<<<dim3(m / 32, BH), 256, smem, STREAM>>>(ga2, gz0, reinterpret_cast<const bf16*>(a2_bf16), m,
+                                                                       reinterpret_cast<const unsigned long long*>(scratch32), dotp,
+                                                                       scale, reinterpret_cast<bf16*>(ds_bf16));
   MB_LAUNCH_CHECK();
   return 0;
 }

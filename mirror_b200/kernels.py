@@ -375,10 +375,12 @@ def layernorm_fwd(x, gamma, beta, eps, n_out=None, pad=0, want_bf16=True, want_f
 
 @_op
 def layernorm_bwd(dy, x, gamma, mean, rstd, pad, dx, add, dgamma, dbeta):
-    """dy: [B,n_out,E] f32; x, dx: [B,X,E] f32, S = mean.shape[1] <= X rows per slide took part in the forward;
+    """dy: [B,n_out,E] f32 or bf16; x, dx: [B,X,E] f32, S = mean.shape[1] <= X rows per slide took part in the forward;
     dx = (add or 0) + LN gradient (rows >= S: just add / 0); dgamma/dbeta accumulate."""
     B, X, E = x.shape
-    _call("mirror_layernorm_bwd", _p(_contig(dy), F32), _p(_contig(x), F32), _p(gamma, F32), _p(mean), _p(rstd), B, mean.shape[1], X, E,
+    if dy.dtype not in (F32, BF16):
+        raise TypeError("layernorm_bwd: dy must be f32 or bf16")
+    _call("mirror_layernorm_bwd", _p(_contig(dy)), int(dy.dtype == BF16), _p(_contig(x), F32), _p(gamma, F32), _p(mean), _p(rstd), B, mean.shape[1], X, E,
           dy.shape[1], pad, _p(_contig(dx), F32), _p(add, F32), _p(dgamma, F32), _p(dbeta, F32))
 
 
@@ -456,6 +458,17 @@ def pinv_init_bwd(gz0, z0_16, scratch, gx, accumulate):
     BH = gz0.numel() // (m * m)
     _call("mirror_pinv_init_bwd", _p(_contig(gz0), F32), _p(_contig(z0_16), BF16), BH, m, _p(scratch), _p(_contig(gx), F32),
           int(accumulate), launches=2)
+
+
+@_op
+def pinv_init_softmax_bwd(ga2, gz0, z0_16, a2_16, scratch, scale):
+    """-> ds2 bf16 = softmax_bwd(a2, ga2 + pinv_init_bwd(gz0)) * scale in one pass (ga2 is not modified)."""
+    m = gz0.shape[-1]
+    BH = gz0.numel() // (m * m)
+    ds = torch.empty_like(a2_16)
+    _call("mirror_pinv_init_softmax_bwd", _p(_contig(ga2), F32), _p(_contig(gz0), F32), _p(_contig(z0_16), BF16), _p(_contig(a2_16), BF16),
+          BH, m, _p(scratch), scale, _p(ds), launches=2)
+    return ds
 
 
 @_op

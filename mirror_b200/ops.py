@@ -366,6 +366,8 @@ def _heads(t, col0, E, h=WSI_HEADS):
     return t[:, :, col0:col0 + E].unflatten(-1, (h, E // h)).permute(0, 2, 1, 3)
 
 
+_AB_F32_DXN = os.environ.get("MIRROR_B200_AB_F32_DXN") == "1"                    # A/B switches (measurement only)
+_AB_UNFUSED_PINV_BWD = os.environ.get("MIRROR_B200_AB_UNFUSED_PINV_BWD") == "1"
 _AB_NO_DOTS = os.environ.get("MIRROR_B200_AB_NO_DOTS") == "1"  # A/B switch (measurement only): two-pass softmax backward everywhere
 
 
@@ -540,8 +542,11 @@ class NystromLayerFn(Function):
         ga2 = torch.empty(mm, device=dev, dtype=F32)
         K.gemm(gens[0][0], gens[0][1], more=gens[1:], out_f32=ga2)
         del gens
-        K.pinv_init_bwd(gz32, iters[0], scratch, ga2, True)  # iters[0] = z0 (bf16)
-        ds2, _ = K.softmax_bwd(a2_16, ga2, scale)
+        if m % 32 == 0 and m <= 512 and not _AB_UNFUSED_PINV_BWD:  # iters[0] = z0 (bf16)
+            ds2 = K.pinv_init_softmax_bwd(ga2, gz32, iters[0], a2_16, scratch, scale)
+        else:
+            K.pinv_init_bwd(gz32, iters[0], scratch, ga2, True)
+            ds2, _ = K.softmax_bwd(a2_16, ga2, scale)
         del ga2, gz32, gz16
 
         # ---- similarities (1/sqrt(d) already folded into ds*).  Landmark gradients first (each a two-term GEMM), then dq / dk
@@ -554,8 +559,8 @@ class NystromLayerFn(Function):
         del ds1, ds2, ds3, dlm16
 
         # ---- to_qkv and LayerNorm
-        dxn = torch.empty(B, n, E, device=dev, dtype=F32)
-        K.gemm(dqkv16.view(B * n, 3 * E), _T(wqkv16), out_f32=dxn.view(B * n, E))
+        dxn = torch.empty(B, n, E, device=dev, dtype=F32 if _AB_F32_DXN else BF16)  # bf16 like dqkv itself: lean epilogue, half the LN-backward read
+        K.gemm(dqkv16.view(B * n, 3 * E), _T(wqkv16), **{"out_f32" if _AB_F32_DXN else "out_bf16": dxn.view(B * n, E)})
         d_qkv_w = wgrad(dqkv16.view(B * n, 3 * E), xn16.view(B * n, E), 3 * E, E)
         dg = torch.zeros(E, device=dev, dtype=F32)
         db = torch.zeros(E, device=dev, dtype=F32)

@@ -284,7 +284,7 @@ class Emu:
     def layernorm_bwd(self, dy, x, gamma, mean, rstd, pad, dx, add, dgamma, dbeta):
         B, X, E = x.shape
         S = mean.shape[1]
-        g = dy[:, pad:pad + S]
+        g = dy[:, pad:pad + S].float()
         xh = (x[:, :S] - mean[..., None]) * rstd[..., None]
         gg = g * gamma
         d = torch.zeros(B, X, E)
@@ -357,6 +357,11 @@ class Emu:
             gx += v
         else:
             gx.copy_(v)
+
+    def pinv_init_softmax_bwd(self, ga2, gz0, z0_16, a2_16, scratch, scale):
+        g = ga2.clone()
+        self.pinv_init_bwd(gz0, z0_16, scratch, g, True)
+        return self.softmax_bwd(a2_16, g, scale)[0]
 
     # ------------------------------------------------------------------ ppeg
     def ppeg_fwd(self, x, w7, w5, w3, b7, b5, b3, H):

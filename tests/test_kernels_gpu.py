@@ -187,6 +187,9 @@ def test_layernorm(B, S, E, pad):
     for add in (None, rn(B, S, E, seed=4)):
         both("layernorm_bwd", (dy, x, g, mean, rstd, pad, torch.zeros(B, S, E), add, torch.zeros(E), torch.zeros(E)), tol=2e-5,
              check_args=(6, 8, 9))
+    # bf16 upstream gradient (what the token-sized backward GEMM writes)
+    both("layernorm_bwd", (dy.to(BF16), x, g, mean, rstd, pad, torch.zeros(B, S, E), None, torch.zeros(E), torch.zeros(E)), tol=2e-5,
+         check_args=(6, 8, 9))
 
 
 @pytest.mark.parametrize("rows,cols", [(100, 384), (7, 2304), (33, 3000), (5, 16512), (64, 96)])
@@ -422,3 +425,16 @@ def test_rowdot():
     a, b = rn(3, 5, 77, 96, seed=1).to(BF16), rn(3, 5, 77, 96, seed=2).to(BF16)
     both("rowdot", (a, b), tol=2e-6)
     both("rowdot", (a, b, rn(3, 5, 77, 96, seed=3).to(BF16)), tol=2e-6)
+
+
+def test_pinv_init_softmax_bwd_fused():
+    # pinv_init_bwd + row-softmax backward of attn2 in one pass (m % 32 == 0), against the two-step emulation
+    m = 96
+    a2 = torch.softmax(rn(2, 3, m, m, scale=2.0), -1) * (1 + 0.2 * torch.rand(2, 3, m, 1, generator=torch.Generator().manual_seed(3)))
+    z16, scratch = K.pinv_init(a2.cuda())
+    z_cpu, s_cpu = EMU.pinv_init(a2)
+    ga2, gz0 = rn(2, 3, m, m, seed=1), rn(2, 3, m, m, seed=2)
+    p16 = torch.softmax(rn(2, 3, m, m, seed=4), -1).to(BF16)
+    want = EMU.pinv_init_softmax_bwd(ga2, gz0, z_cpu, p16, s_cpu, 0.3)
+    got = K.pinv_init_softmax_bwd(ga2.cuda(), gz0.cuda(), z16, p16.cuda(), scratch, 0.3)
+    close(got, want, 8e-3, "pinv_init_softmax_bwd")
