@@ -149,6 +149,157 @@ res_conv_wgrad_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ qk
     if (sacc[i] != 0.f) atomicAdd(dw + i, sacc[i]);
 }
 
+// The same weight gradient on the tensor cores (head_dim % 16 == 0).  For one (slide, head) and a block of 64 tokens,
+// P = D V_win^T (D = dO block [64 x d], V_win = the 96 value rows t0-16 .. t0+79) holds every product the 33 lags need:
+// dw[j] = sum_t P[t, t + j] (column index relative to the window).  Each warp owns 16 rows and only the 48-column band
+// of P around its diagonal: 6 x (d/16) mma.sync.m16n8k16 per 16 tokens instead of 16 x d x 33 FMAs.  An accumulator
+// fragment element always sits on the same lag (column - row is fixed per thread, n-block and element), so the sums over
+// all token blocks of the chunk stay in 24 registers per thread and are binned by lag once at the end.
+constexpr int WG_TB = 64, WG_WIN = WG_TB + 32, WG_MAXD = 128;
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(128)
+res_conv_wgrad_mma_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ qkv, int n, int E, int d, float* __restrict__ dw,
+                          int blocks_per_chunk) {
+  extern __shared__ __align__(16) unsigned char wg_smem[];
+  const int pitch = d + 8;  // bf16 elements per staged row: 16-byte aligned rows, conflict-free fragment loads for d = 96
+  bf16* Ds = reinterpret_cast<bf16*>(wg_smem);
+  bf16* Vs = Ds + WG_TB * pitch;
+  __shared__ float sacc[TAPS];
+  if (threadIdx.x < TAPS) sacc[threadIdx.x] = 0.f;
+  const int h = blockIdx.y;
+  const long long b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int nblocks = (n + WG_TB - 1) / WG_TB;
+  const int blk0 = blockIdx.x * blocks_per_chunk, blk1 = min(nblocks, blk0 + blocks_per_chunk);
+  const int c16 = d / 8;  // 16-byte pieces per row
+  const bf16* dbase = dout + b * n * (long long)E + h * d;
+  const bf16* vbase = qkv + b * n * 3LL * E + 2 * E + h * d;
+  float acc[6][4];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+  const int r0 = warp * 16;
+  for (int blk = blk0; blk < blk1; ++blk) {
+    const int t0 = blk * WG_TB;
+    __syncthreads();  // the previous block's fragments have been read
+    for (int i = threadIdx.x; i < WG_TB * c16; i += blockDim.x) {
+      const int r = i / c16, p8 = (i - r * c16) * 8;
+      const int t = t0 + r;
+      const uint4 v = t < n ? *reinterpret_cast<const uint4*>(dbase + (long long)t * E + p8) : make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(Ds + r * pitch + p8) = v;
+    }
+    for (int i = threadIdx.x; i < WG_WIN * c16; i += blockDim.x) {
+      const int r = i / c16, p8 = (i - r * c16) * 8;
+      const int t = t0 - 16 + r;
+      const uint4 v = (t >= 0 && t < n) ? *reinterpret_cast<const uint4*>(vbase + (long long)t * 3 * E + p8) : make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(Vs + r * pitch + p8) = v;
+    }
+    __syncthreads();
+    for (int ks = 0; ks < d / 16; ++ks) {
+      const bf16* ap = Ds + (r0 + g) * pitch + ks * 16 + 2 * tg;
+      const uint32_t a0 = *reinterpret_cast<const uint32_t*>(ap), a1 = *reinterpret_cast<const uint32_t*>(ap + 8 * pitch);
+      const uint32_t a2 = *reinterpret_cast<const uint32_t*>(ap + 8), a3 = *reinterpret_cast<const uint32_t*>(ap + 8 * pitch + 8);
+#pragma unroll
+      for (int nb = 0; nb < 6; ++nb) {  // window row of column (nb*8 + g) of this warp's band: r0 + nb*8 + g
+        const bf16* bp = Vs + (r0 + nb * 8 + g) * pitch + ks * 16 + 2 * tg;
+        mma_bf16_16816(acc[nb], a0, a1, a2, a3, *reinterpret_cast<const uint32_t*>(bp), *reinterpret_cast<const uint32_t*>(bp + 8));
+      }
+    }
+  }
+  __syncthreads();  // sacc zeroed by all before anyone adds
+#pragma unroll
+  for (int nb = 0; nb < 6; ++nb)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = nb * 8 + 2 * tg + (e & 1) - g - ((e & 2) ? 8 : 0);  // lag index = column - row inside the band
+      if (j >= 0 && j < TAPS) atomicAdd(&sacc[j], acc[nb][e]);
+    }
+  __syncthreads();
+  if (threadIdx.x < TAPS && sacc[threadIdx.x] != 0.f) atomicAdd(dw + h * TAPS + threadIdx.x, sacc[threadIdx.x]);
+}
+
+// The FIR itself on the tensor cores (head_dim % 16 == 0): out[t, c] = sum_k T[t, k] * x[t0-16+k, c] with the 16 x 48 band
+// Toeplitz matrix T[r, k] = w[k - r] (data gradient: flipped taps) as the A operand -- constant per head, so its
+// fragments (split into bf16 hi + lo to keep the fp32 taps) live in registers -- and the staged token window as B
+// (row-major tokens x channels, read with ldmatrix.trans).  6 mma.sync.m16n8k16 per 16 tokens x 8 channels.
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_addr));
+}
+template <bool BWD>
+__global__ void __launch_bounds__(128)
+res_conv_mma_kernel(const bf16* __restrict__ src, long long src_ld, int src_col0, const float* __restrict__ w, int n, int E, int d,
+                    bf16* __restrict__ dst16, int blocks_per_chunk) {
+  extern __shared__ __align__(16) unsigned char wg_smem[];
+  const int pitch = d + 8;
+  bf16* Xs = reinterpret_cast<bf16*>(wg_smem);  // [96][pitch]: tokens t0-16 .. t0+79
+  bf16* Os = Xs + WG_WIN * pitch;               // [64][pitch]: results of this block before the 16-byte stores
+  const int h = blockIdx.y;
+  const long long b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int c16 = d / 8;
+  const bf16* xbase = src + b * n * src_ld + src_col0 + h * d;
+  bf16* obase = dst16 + b * n * (long long)E + h * d;
+  // A fragments: a[ks][0] = (row g, k = 16 ks + 2tg, +1), [1] = (row g+8, same k), [2] = (row g, k+8, +9), [3] = (row g+8, k+8, +9)
+  uint32_t ahi[3][4], alo[3][4];
+  const float* wh = w + h * TAPS;
+#pragma unroll
+  for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = g + ((q & 1) ? 8 : 0), k = ks * 16 + 2 * tg + ((q & 2) ? 8 : 0);
+      float t[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = k + e - r;  // tap index of T[r, k + e]
+        t[e] = (j >= 0 && j < TAPS) ? wh[BWD ? TAPS - 1 - j : j] : 0.f;
+      }
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(t[0], t[1]);
+      const float2 hf = __bfloat1622float2(hi);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(t[0] - hf.x, t[1] - hf.y);
+      ahi[ks][q] = *reinterpret_cast<const uint32_t*>(&hi);
+      alo[ks][q] = *reinterpret_cast<const uint32_t*>(&lo);
+    }
+  const int nblocks = (n + WG_TB - 1) / WG_TB;
+  const int blk0 = blockIdx.x * blocks_per_chunk, blk1 = min(nblocks, blk0 + blocks_per_chunk);
+  const int r0 = warp * 16;
+  const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(Xs);
+  for (int blk = blk0; blk < blk1; ++blk) {
+    const int t0 = blk * WG_TB;
+    __syncthreads();  // previous block: fragments read, results stored
+    for (int i = threadIdx.x; i < WG_WIN * c16; i += blockDim.x) {
+      const int r = i / c16, p8 = (i - r * c16) * 8;
+      const int t = t0 - 16 + r;
+      const uint4 v = (t >= 0 && t < n) ? *reinterpret_cast<const uint4*>(xbase + (long long)t * src_ld + p8) : make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(Xs + r * pitch + p8) = v;
+    }
+    __syncthreads();
+    for (int nb = 0; nb < d / 8; ++nb) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks) {
+        // B fragment: tokens (window rows) r0 + 16 ks + 0..15, channels nb*8 .. +7; lanes 0-15 supply the row addresses
+        uint32_t b0, b1;
+        ldmatrix_x2_trans(b0, b1, xs_addr + (uint32_t)(((r0 + ks * 16 + (lane & 15)) * pitch + nb * 8) * 2));
+        mma_bf16_16816(acc, ahi[ks][0], ahi[ks][1], ahi[ks][2], ahi[ks][3], b0, b1);
+        mma_bf16_16816(acc, alo[ks][0], alo[ks][1], alo[ks][2], alo[ks][3], b0, b1);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(Os + (r0 + g) * pitch + nb * 8 + 2 * tg) = __floats2bfloat162_rn(acc[0], acc[1]);
+      *reinterpret_cast<__nv_bfloat162*>(Os + (r0 + g + 8) * pitch + nb * 8 + 2 * tg) = __floats2bfloat162_rn(acc[2], acc[3]);
+    }
+    __syncwarp();
+    for (int i = lane; i < 16 * c16; i += 32) {  // this warp's 16 rows, 16 bytes per lane and step
+      const int r = i / c16, p8 = (i - r * c16) * 8;
+      const int t = t0 + r0 + r;
+      if (t < n) *reinterpret_cast<uint4*>(obase + (long long)t * E + p8) = *reinterpret_cast<const uint4*>(Os + (r0 + r) * pitch + p8);
+    }
+  }
+}
+
 // ---- pinv set-up.  a2: [BH, m, m] f32 (row softmax).  scal: [0]=max row abs-sum, [1]=max col abs-sum (as ordered
 // uint64 keys: float bits << 32 | ~index so that atomicMax also yields the FIRST arg-max).
 __device__ __forceinline__ unsigned long long pack_key(float v, unsigned idx) {
@@ -344,9 +495,34 @@ static int conv_strips_per_chunk(int B, int n, int E, int max_spc) {
   return spc > strips ? strips : spc;
 }
 
+// tensor-core versions of the three FIR kernels: head_dim a multiple of 16.  OPT-IN (MIRROR_B200_CONV_MMA=1) until they have
+// been through the GPU parity tests; the register-window kernels above are the default.
+static bool conv_mma_ok(int E) {
+  static const int on = [] { const char* v = getenv("MIRROR_B200_CONV_MMA"); return v && *v == '1'; }();
+  const int d = E / 8;
+  return on && d % 16 == 0 && d <= WG_MAXD;
+}
+static size_t conv_mma_smem(int E) { return (size_t)(WG_TB + WG_WIN) * (E / 8 + 8) * sizeof(bf16); }
+static dim3 conv_mma_grid(int B, int n, int* blocks_per_chunk) {  // (token chunks, heads, slides): ~4 CTAs per SM in the grid
+  const int nblocks = (n + WG_TB - 1) / WG_TB;
+  long long chunks = (4LL * num_sms() + 8LL * B - 1) / (8LL * B);
+  if (chunks < 1) chunks = 1;
+  if (chunks > nblocks) chunks = nblocks;
+  *blocks_per_chunk = (int)((nblocks + chunks - 1) / chunks);
+  return dim3((unsigned)((nblocks + *blocks_per_chunk - 1) / *blocks_per_chunk), 8, (unsigned)B);
+}
+
 extern "C" int mirror_res_conv_fwd(const void* qkv, const float* w, int32_t B, int32_t n, int32_t E, void* out_bf16,
                                    mirror_stream_t stream) {
   MB_CHECK_ARG(qkv && w && out_bf16 && B > 0 && n > 0 && E % 16 == 0, "res_conv_fwd: bad args");
+  if (conv_mma_ok(E)) {
+    int bpc;
+    const dim3 mg = conv_mma_grid(B, n, &bpc);
+    res_conv_mma_kernel<false><<<mg, 128, conv_mma_smem(E), STREAM>>>(reinterpret_cast<const bf16*>(qkv), 3LL * E, 2 * E, w, n, E, E / 8,
+                                                                     reinterpret_cast<bf16*>(out_bf16), bpc);
+    MB_LAUNCH_CHECK();
+    return 0;
+  }
   const int spc = conv_strips_per_chunk(B, n, E, 16);
   dim3 grid((E / 2 + 127) / 128, ((n + TT - 1) / TT + spc - 1) / spc, B);
   res_conv_kernel<false><<<grid, 128, 0, STREAM>>>(reinterpret_cast<const bf16*>(qkv), 3LL * E, 2 * E, w, n, E, E / 8,
@@ -359,12 +535,27 @@ extern "C" int mirror_res_conv_bwd(const void* dout_bf16, const void* qkv, const
   MB_CHECK_ARG(dout_bf16 && qkv && w && dv_bf16 && dw && B > 0 && n > 0 && E % 16 == 0, "res_conv_bwd: bad args");
   const int spc = conv_strips_per_chunk(B, n, E, 16);
   dim3 grid((E / 2 + 127) / 128, ((n + TT - 1) / TT + spc - 1) / spc, B);
-  res_conv_kernel<true><<<grid, 128, 0, STREAM>>>(reinterpret_cast<const bf16*>(dout_bf16), E, 0, w, n, E, E / 8,
-                                                 reinterpret_cast<bf16*>(dv_bf16), E, 0, spc);
+  if (conv_mma_ok(E)) {
+    int bpc;
+    const dim3 mg = conv_mma_grid(B, n, &bpc);
+    res_conv_mma_kernel<true><<<mg, 128, conv_mma_smem(E), STREAM>>>(reinterpret_cast<const bf16*>(dout_bf16), E, 0, w, n, E, E / 8,
+                                                                    reinterpret_cast<bf16*>(dv_bf16), bpc);
+  } else {
+    res_conv_kernel<true><<<grid, 128, 0, STREAM>>>(reinterpret_cast<const bf16*>(dout_bf16), E, 0, w, n, E, E / 8,
+                                                   reinterpret_cast<bf16*>(dv_bf16), E, 0, spc);
+  }
   MB_LAUNCH_CHECK();
-  const int wspc = conv_strips_per_chunk(B, n, E, 24);
-  res_conv_wgrad_kernel<<<dim3(grid.x, ((n + TT - 1) / TT + wspc - 1) / wspc, B), 128, 0, STREAM>>>(
-      reinterpret_cast<const bf16*>(dout_bf16), reinterpret_cast<const bf16*>(qkv), n, E, E / 8, dw, wspc);
+  const int d = E / 8;
+  if (conv_mma_ok(E)) {  // tensor-core weight gradient
+    int bpc;
+    const dim3 mg = conv_mma_grid(B, n, &bpc);
+    res_conv_wgrad_mma_kernel<<<mg, 128, conv_mma_smem(E), STREAM>>>(reinterpret_cast<const bf16*>(dout_bf16),
+                                                                    reinterpret_cast<const bf16*>(qkv), n, E, d, dw, bpc);
+  } else {
+    const int wspc = conv_strips_per_chunk(B, n, E, 24);
+    res_conv_wgrad_kernel<<<dim3(grid.x, ((n + TT - 1) / TT + wspc - 1) / wspc, B), 128, 0, STREAM>>>(
+        reinterpret_cast<const bf16*>(dout_bf16), reinterpret_cast<const bf16*>(qkv), n, E, d, dw, wspc);
+  }
   MB_LAUNCH_CHECK();
   return 0;
 }

@@ -208,7 +208,7 @@ def test_l2norm_strided_rows():
     both("l2norm_bwd", (rn(5, 96, seed=1), x, norm), tol=3e-6)
 
 
-@pytest.mark.parametrize("B,n,E", [(2, 72, 48), (1, 300, 192)])
+@pytest.mark.parametrize("B,n,E", [(2, 72, 48), (1, 300, 192), (2, 200, 128), (1, 333, 768)])  # head_dim 16 / 96: mma.sync weight grad
 def test_res_conv(B, n, E):
     qkv = rn(B, n, 3 * E).to(BF16)
     w = rn(8, 33, scale=0.2)
