@@ -496,29 +496,25 @@ static int conv_strips_per_chunk(int B, int n, int E, int max_spc) {
 }
 
 // tensor-core versions of the three FIR kernels (head_dim a multiple of 16), verified by the GPU parity tests.  Measured at the
-// benchmark shape: weight gradient 0.52 -> 0.35 ms (default); the FIR / data gradient 0.254 -> 0.297 ms, i.e. slower than the
-// register-window kernels (single-buffered staging), so those stay opt-in (MIRROR_B200_CONV_MMA=1).
-// MIRROR_B200_AB_NO_CONV_MMA=1 switches the tensor-core weight gradient off (A/B).
-static bool conv_mma_shape_ok(int E) {
-  const int d = E / 8;
-  return d % 16 == 0 && d <= WG_MAXD;
-}
-static bool conv_mma_ok(int E) {  // FIR and data gradient
-  static const int on = [] { const char* v = getenv("MIRROR_B200_CONV_MMA"); return v && *v == '1'; }();
-  return on && conv_mma_shape_ok(E);
-}
-static bool conv_wgrad_mma_ok(int E) {
+// benchmark shape with 3 token blocks per CTA: FIR / data gradient 0.254 -> 0.197 ms, weight gradient 0.52 -> 0.26 ms.
+// MIRROR_B200_AB_NO_CONV_MMA=1 switches back to the register-window kernels (A/B).
+static bool conv_mma_ok(int E) {
   static const int off = [] { const char* v = getenv("MIRROR_B200_AB_NO_CONV_MMA"); return v && *v == '1'; }();
-  return !off && conv_mma_shape_ok(E);
+  const int d = E / 8;
+  return !off && d % 16 == 0 && d <= WG_MAXD;
 }
+static bool conv_wgrad_mma_ok(int E) { return conv_mma_ok(E); }
 static size_t conv_mma_smem(int E) { return (size_t)(WG_TB + WG_WIN) * (E / 8 + 8) * sizeof(bf16); }
-static dim3 conv_mma_grid(int B, int n, int* blocks_per_chunk) {  // (token chunks, heads, slides): ~4 CTAs per SM in the grid
+static dim3 conv_mma_grid(int B, int n, int* blocks_per_chunk) {  // (token chunks, heads, slides)
+  // 64-token blocks per CTA: few, so that the grid has many more CTAs than fit at once and they overlap each other's loads
+  // (18 per CTA: 0.294 ms, 6: 0.214, 3: 0.197, 2: 0.199 forward).  MIRROR_B200_CONV_MMA_BPC overrides (tuning).
+  static const int env = [] { const char* v = getenv("MIRROR_B200_CONV_MMA_BPC"); return v && *v ? atoi(v) : 0; }();
   const int nblocks = (n + WG_TB - 1) / WG_TB;
-  long long chunks = (4LL * num_sms() + 8LL * B - 1) / (8LL * B);
-  if (chunks < 1) chunks = 1;
-  if (chunks > nblocks) chunks = nblocks;
-  *blocks_per_chunk = (int)((nblocks + chunks - 1) / chunks);
-  return dim3((unsigned)((nblocks + *blocks_per_chunk - 1) / *blocks_per_chunk), 8, (unsigned)B);
+  int bpc = env > 0 ? env : 3;
+  if (bpc > nblocks) bpc = nblocks;
+  (void)B;
+  *blocks_per_chunk = bpc;
+  return dim3((unsigned)((nblocks + bpc - 1) / bpc), 8, (unsigned)B);
 }
 
 extern "C" int mirror_res_conv_fwd(const void* qkv, const float* w, int32_t B, int32_t n, int32_t E, void* out_bf16,
