@@ -429,7 +429,8 @@ pinv_init_bwd_kernel(const float* __restrict__ gz0, int m, const unsigned long l
 //   ds[i,j] = scale * p[i,j] * (g[i,j] - sum_j p[i,j] g[i,j])                       (p = bf16 attn2)
 // One CTA = 32 rows of one matrix: the m x 32 block of gz0 those rows need is staged (transposed use) in shared memory,
 // then each warp finishes 4 rows with the row kept in registers (m <= 512).  Saves the read-modify-write of ga2 and its
-// re-read by a separate softmax kernel (1.5 GB -> 0.9 GB per layer at the benchmark shape).
+// re-read by a separate softmax kernel (1.5 GB -> 0.9 GB per layer at the benchmark shape) -- but measured SLOWER than the
+// two kernels it replaces (0.43 vs 0.34 ms per layer: the 128-byte staging reads), so the caller uses it only on request.
 constexpr int kFuseMaxChunks = 16;
 __global__ void __launch_bounds__(256)
 pinv_init_softmax_bwd_kernel(const float* __restrict__ ga2, const float* __restrict__ gz0, const bf16* __restrict__ p16, int m,
@@ -444,7 +445,14 @@ pinv_init_softmax_bwd_kernel(const float* __restrict__ ga2, const float* __restr
   const int bh = blockIdx.y, i0 = blockIdx.x * 32;
   const long long base = (long long)bh * m * m;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < m; j += 8) tile[j * 33 + lane] = (i0 + lane < m) ? gz0[base + (long long)j * m + i0 + lane] : 0.f;
+  for (int j0 = warp * 8; j0 < m; j0 += 64) {  // eight independent 128-byte row segments in flight per warp
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (j0 + u < m && i0 + lane < m) ? gz0[base + (long long)(j0 + u) * m + i0 + lane] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (j0 + u < m) tile[(j0 + u) * 33 + lane] = v[u];
+  }
   __syncthreads();
   const int nch = m / 32;
   for (int ii = warp * 4; ii < warp * 4 + 4; ++ii) {

@@ -367,7 +367,7 @@ def _heads(t, col0, E, h=WSI_HEADS):
 
 
 _AB_F32_DXN = os.environ.get("MIRROR_B200_AB_F32_DXN") == "1"                    # A/B switches (measurement only)
-_AB_UNFUSED_PINV_BWD = os.environ.get("MIRROR_B200_AB_UNFUSED_PINV_BWD") == "1"
+_FUSED_PINV_BWD = os.environ.get("MIRROR_B200_FUSED_PINV_BWD") == "1"  # opt-in: measured 1.30 ms vs 1.01 ms for the two kernels
 _AB_NO_DOTS = os.environ.get("MIRROR_B200_AB_NO_DOTS") == "1"  # A/B switch (measurement only): two-pass softmax backward everywhere
 
 
@@ -542,7 +542,7 @@ class NystromLayerFn(Function):
         ga2 = torch.empty(mm, device=dev, dtype=F32)
         K.gemm(gens[0][0], gens[0][1], more=gens[1:], out_f32=ga2)
         del gens
-        if m % 32 == 0 and m <= 512 and not _AB_UNFUSED_PINV_BWD:  # iters[0] = z0 (bf16)
+        if _FUSED_PINV_BWD and m % 32 == 0 and m <= 512:  # iters[0] = z0 (bf16)
             ds2 = K.pinv_init_softmax_bwd(ga2, gz32, iters[0], a2_16, scratch, scale)
         else:
             K.pinv_init_bwd(gz32, iters[0], scratch, ga2, True)
