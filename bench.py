@@ -107,6 +107,52 @@ def cpu_reference_step(B, N, Dw, Dr, steps, warmup, threads):
     return B * len(times) / sum(times), sum(times) / len(times)
 
 
+def run_eager(args):
+    """The GPU bar (SURVEY.md §8d last row): the reference algorithm (oracle restatement, pinned against the reference
+    sources) as PyTorch eager on the same B200 -- cuBLAS / cuDNN / ATen kernels under torch.autocast(bf16), TF32 matmuls
+    enabled like train_mirror.py:650-652.  Dropout off (favours this arm).  Baseline only: none of this repo's kernels run."""
+    import torch
+    from oracle import mirror_oracle as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    B, N, Dw, Dr = args.batch, args.patches, args.wsi_dim, args.rna_dim
+    cfg = O.default_cfg(Dw=Dw, Dr=Dr, N=N)
+    sd = {k: v.to(dev).requires_grad_(True) for k, v in O.make_state_dict(cfg, 0).items()}
+    wsi, rna = (t.to(dev) for t in O.make_inputs(B, N, Dw, Dr, 1234))
+    noise = {k: v.to(dev) for k, v in O.make_noise(B, N, cfg["E"], cfg["latent"], 4321).items()}
+    adt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": None}[args.eager_dtype]
+
+    def step():
+        with torch.autocast("cuda", dtype=adt, enabled=adt is not None):
+            out = O.mirror_forward(sd, wsi, rna, noise)
+            total = O.mirror_loss(out)[0]
+        O.grads_of(total, sd)
+        return total
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    sustained = peaks()[0]
+    f_slide = algorithmic_gflop_per_slide(N, Dw)
+    val = B / (ms / 1e3)
+    print(json.dumps({"impl": "eager", "metric": "MIRROR pretrain slides/s fwd+bwd", "value": val, "unit": "slides/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": args.eager_dtype, "data": "synthetic", "config": workload_config(args, B) | {"mode": "dropout off, fwd+loss+bwd, PyTorch eager (cuBLAS/cuDNN/ATen), autocast " + args.eager_dtype},
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30, "last_loss": float(loss),
+                      "step_algorithmic_tflops": val * f_slide / 1e3, "step_algorithmic_frac": val * f_slide / 1e3 / sustained}), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -138,7 +184,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
+    ap.add_argument("--eager-dtype", default="bf16", choices=["bf16", "fp16", "fp32"], help="autocast dtype of --impl eager")
     ap.add_argument("--batch", type=int, default=64, help="slides per GPU")
     ap.add_argument("--patches", type=int, default=2048)
     ap.add_argument("--wsi-dim", type=int, default=768)
@@ -150,6 +197,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "eager":
+        return run_eager(args)
 
     import torch
     import torch.distributed as dist

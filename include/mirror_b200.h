@@ -233,13 +233,31 @@ int mirror_rna_attn_bwd(const float* qkv, const float* dout, int32_t B, int32_t 
 /* ------------------------------------------------------------------------------------------------
  * Losses (loss.cu).  Loss values, the temperature scale and upstream gradients are DEVICE scalars.
  * ---------------------------------------------------------------------------------------------- */
-/* ClipLoss (losses/mirror_loss.py:37-52; w_row=w_col=0.5) / InfoNCE (losses/info_nce.py:144-164; symmetric 0.5/0.5, else 1/0)
- * on raw = W.R^T (unscaled, from mirror_gemm_bf16); logits = (*scale) * raw. */
-int mirror_clip_loss_fwd(const float* raw, int32_t B, const float* scale, float w_row, float w_col, float* row_lse, float* col_lse,
-                         float* loss, mirror_stream_t stream);
-/* G = d loss / d raw (bf16 and/or f32; operand of dW = G.R and dR = G^T.W); dscale += d loss / d scale */
-int mirror_clip_loss_bwd(const float* raw, int32_t B, const float* scale, float w_row, float w_col, const float* row_lse,
-                         const float* col_lse, const float* gout, void* G_bf16, float* G_f32, float* dscale, mirror_stream_t stream);
+/* Fused contrastive loss (contrastive.cu): the B x B logits L = (*scale) X Y^T live only in TMEM.
+ * Replaces losses/mirror_loss.py:39-50 (two logits GEMMs + two cross entropies) and losses/info_nce.py:144-164, plus their
+ * autograd backward (softmax gradients + four GEMMs).  X: [Br,K], Y: [Bc,K] bf16 row-major (ld in elements, multiples of 8);
+ * the positive of row i is column i + diag0 (diag0 = rank * B_local when Y is the all-gathered global batch).
+ * stats: lse[i] = ln sum_j e^{L_ij}, diag[i] = L_{i,i+diag0}; `part` is scratch of mirror_contrastive_nsplit(Br,Bc) * Br * 2 floats.
+ * Column statistics are the row statistics of the swapped call (X <-> Y). */
+int mirror_contrastive_nsplit(int32_t Br, int32_t Bc);
+int mirror_contrastive_stats(const void* x, int64_t ldx, const void* y, int64_t ldy, int32_t Br, int32_t Bc, int32_t K,
+                             const float* scale, int32_t diag0, float* part, int32_t nsplit, float* lse, float* diag,
+                             mirror_stream_t stream);
+/* dX[Br,E] (f32, ld lddx) = G Y_value with G_ij = s (a_r[i] e^{L_ij - lse_r[i]} + a_c[j] e^{L_ij - lse_c[j]}
+ *                                                    - [j == i + diag0] (a_r[i] + a_c[j])), recomputed tile by tile;
+ * *dscale += sum_ij (a_r[i] e^{L_ij - lse_r[i]} - [diag] a_r[i]) (X Y^T)_ij  (may be NULL).  a_c == NULL: one-sided loss.
+ * precise = 0: K == D, Y_value = Y.  precise = 1: split-3 operands, K == 3 D, X = [hi|lo|hi], Y's hi block at column 0 and its
+ * lo block at column lo_off; G is split into hi + lo too.  D: multiple of 64 (zero padded), E <= D columns are stored. */
+int mirror_contrastive_grad(const void* x, int64_t ldx, const void* y, int64_t ldy, int32_t Br, int32_t Bc, int32_t K, int32_t D,
+                            int32_t E, int32_t precise, int32_t lo_off, const float* scale, int32_t diag0, const float* lse_r,
+                            const float* lse_c, const float* a_r, const float* a_c, float* dx, int64_t lddx, float* dscale,
+                            mirror_stream_t stream);
+/* per_sample[i] = w_r (lse_r[i] - diag[i]) + w_c (lse_c[i] - diag[i]) (may be NULL); *out = mult * sum_i (may be NULL) */
+int mirror_contrastive_loss(const float* lse_r, const float* lse_c, const float* diag, int32_t B, float w_r, float w_c, float mult,
+                            float* per_sample, float* out, mirror_stream_t stream);
+/* a_r[i] = g[i*g_stride] * mult * w_r, a_c[i] = ... * w_c (a_c may be NULL): upstream gradient -> coefficients of G */
+int mirror_contrastive_coef(const float* g, int32_t g_stride, int32_t B, float w_r, float w_c, float mult, float* a_r, float* a_c,
+                            mirror_stream_t stream);
 /* retention terms, losses/mirror_loss.py:98-103: out = sum_rows mask*mean_e (a-b)^2 / sum mask; batches strided by a_bs / b_bs */
 int mirror_masked_mse_fwd(const float* a, int64_t a_bs, const float* b, int64_t b_bs, const float* mask, int32_t B, int32_t T,
                           int32_t E, float* scratch2, float* out, mirror_stream_t stream);

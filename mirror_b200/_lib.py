@@ -45,11 +45,20 @@ class GemmArgs(ctypes.Structure):
 
 
 def lib():
+    """Load the library, (re)building it first when it is missing or older than its sources.  The digest check is cheap
+    (hash of csrc/ + the header) and runs under an exclusive file lock: the ranks of a DDP job start together and must not
+    compile into the same object directory at once, and an edited .cu must never run as a stale .so."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            from . import build as _build  # compile in-tree; raises if nvcc is missing
-            _build.build()
+        from . import build as _build  # compile in-tree; raises if nvcc is missing
+        import fcntl
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if os.environ.get("MIRROR_B200_NO_REBUILD") != "1" or not os.path.exists(LIB_PATH):
+                    _build.build()
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.mirror_last_error.restype = ctypes.c_char_p
     return _lib
@@ -99,8 +108,11 @@ SIGNATURES = {
     "mirror_ppeg_bwd": [_P, _P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "mirror_rna_attn_fwd": [_P, _I32, _I32, _P, _P, _P],
     "mirror_rna_attn_bwd": [_P, _P, _I32, _I32, _P, _P, _P],
-    "mirror_clip_loss_fwd": [_P, _I32, _P, _F, _F, _P, _P, _P, _P],
-    "mirror_clip_loss_bwd": [_P, _I32, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
+    "mirror_contrastive_nsplit": [_I32, _I32],
+    "mirror_contrastive_stats": [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _I32, _P, _I32, _P, _P, _P],
+    "mirror_contrastive_grad": [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P],
+    "mirror_contrastive_loss": [_P, _P, _P, _I32, _F, _F, _F, _P, _P, _P],
+    "mirror_contrastive_coef": [_P, _I32, _I32, _F, _F, _F, _P, _P, _P],
     "mirror_masked_mse_fwd": [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P],
     "mirror_masked_mse_bwd": [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _F, _P, _I64, _I32, _P, _I64, _I32, _P],
     "mirror_gauss_kl_fwd": [_P, _P, _I64, _I32, _P, _P],

@@ -34,16 +34,34 @@ enum { MB_ERR_ARG = -1, MB_ERR_ALIGN = -2, MB_ERR_DRIVER = -3, MB_ERR_UNSUPPORTE
 
 #define MB_LAUNCH_CHECK() MB_CUDA(cudaGetLastError())
 
-inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+// per-device caches (a process may drive several devices: attributes set on one device do not carry over)
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
+inline int num_sms() {
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
+  }
+  return n[dev];
+}
+// `static DeviceOnce once; if (once.first()) cudaFuncSetAttribute(...)`: true the first time per device (benign race:
+// the attribute set is idempotent)
+struct DeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool first() {
+    const int dev = current_device();
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 
 // ---- stateless counter-based uniform in [0,1): keep-mask of the fused dropout.  32-bit "lowbias32" finaliser over the
 // element index mixed with the 64-bit seed: ~10 integer ops per element (the epilogues evaluate it for every output).

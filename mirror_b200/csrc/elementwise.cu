@@ -540,10 +540,9 @@ extern "C" int mirror_rank_mask(const float* noise, int32_t B, int32_t N, int32_
   MB_CHECK_ARG(noise && mask && B > 0 && N > 0 && keep >= 0 && keep <= N, "rank_mask: bad args");
   const size_t smem = (size_t)N * sizeof(float);
   MB_CHECK_ARG(smem <= 200 * 1024, "rank_mask: N=%d too large for the shared-memory row", N);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     MB_CUDA(cudaFuncSetAttribute(rank_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
   }
   rank_mask_kernel<<<B, 512, smem, STREAM>>>(noise, N, keep, mask);
   MB_LAUNCH_CHECK();

@@ -1067,10 +1067,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
            int vec_ok, cudaStream_t stream) {
   using C = Cfg<BN, TMAS>;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, TMAS, EK>;
-  static bool configured = false;  // benign race: attribute set is idempotent
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.batch1 * p.batch2 * p.split_k;
   const int grid = (int)(total < num_sms() ? total : num_sms());
@@ -1141,10 +1140,9 @@ template <int BN, int A_MN, int B_MN, int CL>
 int launch_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int vec_ok, cudaStream_t stream) {
   using C = Cfg<BN>;
   auto kern = gemm_tcgen05_cluster_kernel<BN, A_MN, B_MN, CL>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.batch1 * p.batch2 * p.split_k;
   const int max_clusters = num_sms() / CL;
@@ -1159,10 +1157,9 @@ template <int BN, bool TMAS, int EK = 0>
 int launch_multi(const MultiMaps& maps, const KParams& p, const MultiInfo& mi, int vec_ok, cudaStream_t stream) {
   using C = Cfg<BN, TMAS>;
   auto kern = gemm_tcgen05_multi_kernel<BN, TMAS, EK>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.batch1 * p.batch2;
   const int grid = (int)(total < num_sms() ? total : num_sms());

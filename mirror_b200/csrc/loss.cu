@@ -6,78 +6,6 @@
 namespace mb {
 namespace {
 
-// ------------------------------------------------------------------ contrastive (ClipLoss / InfoNCE)
-// raw: [B,B] f32 dot products W.R^T (unscaled); logits = s*raw with s = *scale.
-// row_lse[i] = logsumexp_j logits[i,j];  col_lse[j] = logsumexp_i logits[i,j].   One warp per row / thread per column.
-__global__ void clip_row_lse_kernel(const float* __restrict__ raw, int B, const float* __restrict__ scale, float* __restrict__ row_lse) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= B) return;
-  const float s = *scale;
-  const float* r = raw + (long long)i * B;
-  float mx = -INFINITY;
-  for (int j = lane; j < B; j += 32) mx = fmaxf(mx, s * r[j]);
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int j = lane; j < B; j += 32) sum += __expf(s * r[j] - mx);
-  sum = warp_sum(sum);
-  if (lane == 0) row_lse[i] = mx + __logf(sum);
-}
-__global__ void clip_col_lse_kernel(const float* __restrict__ raw, int B, const float* __restrict__ scale, float* __restrict__ col_lse) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= B) return;
-  const float s = *scale;
-  float mx = -INFINITY, sum = 0.f;
-  for (int i = 0; i < B; ++i) {  // online max/sum; loads coalesced across the warp
-    const float v = s * raw[(long long)i * B + j];
-    if (v > mx) {
-      sum = sum * __expf(mx - v) + 1.f;
-      mx = v;
-    } else {
-      sum += __expf(v - mx);
-    }
-  }
-  col_lse[j] = mx + __logf(sum);
-}
-// loss = mean_i( wr*(row_lse_i - l_ii) + wc*(col_lse_i - l_ii) )      (wr=wc=0.5 symmetric; wr=1,wc=0 one-sided)
-__global__ void clip_loss_kernel(const float* __restrict__ raw, int B, const float* __restrict__ scale,
-                                 const float* __restrict__ row_lse, const float* __restrict__ col_lse, float wr, float wc,
-                                 float* __restrict__ loss) {
-  __shared__ float sh[32];
-  const float s = *scale;
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    const float d = s * raw[(long long)i * B + i];
-    acc += wr * (row_lse[i] - d) + wc * (col_lse[i] - d);
-  }
-  acc = block_sum(acc, sh);
-  if (threadIdx.x == 0) *loss = acc / B;
-}
-// G[i,j] = g * s * ( (wr*e^{l-rl_i} + wc*e^{l-cl_j}) - (wr+wc)*[i==j] ) / B   as bf16 (operand of dW = G R, dR = G^T W)
-// dscale += sum_ij (G/s) * raw
-__global__ void clip_grad_kernel(const float* __restrict__ raw, int B, const float* __restrict__ scale,
-                                 const float* __restrict__ row_lse, const float* __restrict__ col_lse, float wr, float wc,
-                                 const float* __restrict__ gout, bf16* __restrict__ G, float* __restrict__ G32,
-                                 float* __restrict__ dscale) {
-  __shared__ float sh[32];
-  const float s = *scale, g = *gout / B;
-  float acc = 0.f;
-  const long long total = (long long)B * B;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(idx / B), j = (int)(idx % B);
-    const float r = raw[idx], l = s * r;
-    float p = wr * __expf(l - row_lse[i]);
-    if (wc != 0.f) p += wc * __expf(l - col_lse[j]);
-    if (i == j) p -= wr + wc;
-    p *= g;
-    acc += p * r;
-    if (G) G[idx] = __float2bfloat16(p * s);
-    if (G32) G32[idx] = p * s;
-  }
-  acc = block_sum(acc, sh);
-  if (threadIdx.x == 0 && dscale) atomicAdd(dscale, acc);
-}
-
 // ------------------------------------------------------------------ masked MSE (retention losses)
 // scratch[0] += sum mask[row] * (a-b)^2 / E ; scratch[1] += sum mask[row]     rows = B*T
 __global__ void masked_mse_fwd_kernel(const float* __restrict__ a, long long a_bs, const float* __restrict__ b, long long b_bs,
@@ -290,26 +218,6 @@ static int ew_grid(long long n, int block) {
 }
 
 /* raw: [B,B] unscaled similarities; scale: device scalar; row_lse/col_lse: [B]; loss: device scalar */
-extern "C" int mirror_clip_loss_fwd(const float* raw, int32_t B, const float* scale, float w_row, float w_col, float* row_lse,
-                                    float* col_lse, float* loss, mirror_stream_t stream) {
-  MB_CHECK_ARG(raw && scale && row_lse && col_lse && loss && B > 0, "clip_loss_fwd: bad args");
-  clip_row_lse_kernel<<<(B + 7) / 8, 256, 0, STREAM>>>(raw, B, scale, row_lse);
-  MB_LAUNCH_CHECK();
-  clip_col_lse_kernel<<<(B + 127) / 128, 128, 0, STREAM>>>(raw, B, scale, col_lse);
-  MB_LAUNCH_CHECK();
-  clip_loss_kernel<<<1, 256, 0, STREAM>>>(raw, B, scale, row_lse, col_lse, w_row, w_col, loss);
-  MB_LAUNCH_CHECK();
-  return 0;
-}
-extern "C" int mirror_clip_loss_bwd(const float* raw, int32_t B, const float* scale, float w_row, float w_col,
-                                    const float* row_lse, const float* col_lse, const float* gout, void* G_bf16, float* G_f32,
-                                    float* dscale, mirror_stream_t stream) {
-  MB_CHECK_ARG(raw && scale && row_lse && col_lse && gout && (G_bf16 || G_f32) && B > 0, "clip_loss_bwd: bad args");
-  clip_grad_kernel<<<ew_grid((long long)B * B, 256), 256, 0, STREAM>>>(raw, B, scale, row_lse, col_lse, w_row, w_col, gout,
-                                                                       reinterpret_cast<bf16*>(G_bf16), G_f32, dscale);
-  MB_LAUNCH_CHECK();
-  return 0;
-}
 
 /* scratch: 2 floats, zeroed here */
 // float4 rows: E and every batch stride a multiple of 4 elements, bases 16-byte aligned, rows wide enough for a warp

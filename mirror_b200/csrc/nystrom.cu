@@ -584,10 +584,9 @@ extern "C" int mirror_pinv_init_softmax_bwd(const float* ga2, const float* gz0, 
   dot_kernel<<<ew_grid(n, 256 * 8), 256, 0, STREAM>>>(gz0, reinterpret_cast<const bf16*>(z0_bf16), n, dotp);
   MB_LAUNCH_CHECK();
   const size_t smem = (size_t)m * 33 * sizeof(float);
-  static bool configured = false;  // benign race: idempotent
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     MB_CUDA(cudaFuncSetAttribute(pinv_init_softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kFuseMaxChunks * 33 * 4));
-    configured = true;
   }
   pinv_init_softmax_bwd_kernel<<<dim3(m / 32, BH), 256, smem, STREAM>>>(ga2, gz0, reinterpret_cast<const bf16*>(a2_bf16), m,
                                                                        reinterpret_cast<const unsigned long long*>(scratch32), dotp,

@@ -512,23 +512,50 @@ def rna_attn_bwd(qkv, dout):
 
 
 @_op
-def clip_loss_fwd(raw, scale, w_row, w_col):
-    B = raw.shape[0]
-    row = torch.empty(B, device=raw.device, dtype=F32)
-    col = torch.empty(B, device=raw.device, dtype=F32)
-    loss = torch.empty((), device=raw.device, dtype=F32)
-    _call("mirror_clip_loss_fwd", _p(_contig(raw), F32), B, _p(scale, F32), w_row, w_col, _p(row), _p(col), _p(loss), launches=3)
-    return loss, row, col
+def contrastive_stats(x, y, scale, diag0=0):
+    """x: [Br,K], y: [Bc,K] bf16 (row stride multiple of 8) -> (lse [Br], diag [Br]) of L = scale * x y^T without L in HBM."""
+    Br, Kd = x.shape
+    Bc = y.shape[0]
+    assert y.shape[1] == Kd and x.stride(1) == 1 and y.stride(1) == 1
+    ns = int(_lib.fn("mirror_contrastive_nsplit")(Br, Bc))
+    part = torch.empty(ns, Br, 2, device=x.device, dtype=F32)
+    lse = torch.empty(Br, device=x.device, dtype=F32)
+    diag = torch.empty(Br, device=x.device, dtype=F32)
+    _call("mirror_contrastive_stats", _p(x, BF16), x.stride(0), _p(y, BF16), y.stride(0), Br, Bc, Kd, _p(scale, F32), diag0, _p(part), ns,
+          _p(lse), _p(diag), launches=2)
+    return lse, diag
 
 
 @_op
-def clip_loss_bwd(raw, scale, w_row, w_col, row, col, gout, dscale, want_f32=False):
-    """returns G = d loss / d raw as bf16 [B,B] (or f32 when want_f32); dscale (0-d f32) is accumulated."""
-    B = raw.shape[0]
-    G = torch.empty(B, B, device=raw.device, dtype=F32 if want_f32 else BF16)
-    _call("mirror_clip_loss_bwd", _p(raw, F32), B, _p(scale, F32), w_row, w_col, _p(row), _p(col), _p(gout, F32),
-          None if want_f32 else _p(G), _p(G) if want_f32 else None, _p(dscale))
-    return G
+def contrastive_grad(x, y, D, E, precise, lo_off, scale, diag0, lse_r, lse_c, a_r, a_c, dscale):
+    """-> dx [Br,E] f32 = G y_value (G recomputed tile by tile, see mirror_contrastive_grad); dscale (0-d) is accumulated."""
+    Br, Kd = x.shape
+    Bc = y.shape[0]
+    dx = torch.empty(Br, E, device=x.device, dtype=F32)
+    _call("mirror_contrastive_grad", _p(x, BF16), x.stride(0), _p(y, BF16), y.stride(0), Br, Bc, Kd, D, E, int(precise), lo_off,
+          _p(scale, F32), diag0, _p(_contig(lse_r), F32), _p(_contig(lse_c), F32), _p(_contig(a_r), F32),
+          _p(_contig(a_c), F32) if a_c is not None else None, _p(dx), E, _p(dscale, F32) if dscale is not None else None)
+    return dx
+
+
+@_op
+def contrastive_loss(lse_r, lse_c, diag, w_r, w_c, mult, per_sample):
+    """-> per-sample losses [B] (per_sample=True) or the 0-d reduction mult * sum_i loss_i."""
+    B = lse_r.shape[0]
+    out = torch.empty(B if per_sample else (), device=lse_r.device, dtype=F32)
+    _call("mirror_contrastive_loss", _p(lse_r, F32), _p(lse_c, F32) if lse_c is not None else None, _p(diag, F32), B, w_r, w_c, mult,
+          _p(out) if per_sample else None, None if per_sample else _p(out))
+    return out
+
+
+@_op
+def contrastive_coef(g, B, w_r, w_c, mult):
+    """upstream gradient (0-d or [B]) -> (a_r, a_c | None): coefficients of the softmax terms in G."""
+    g = _contig(g)
+    a_r = torch.empty(B, device=g.device, dtype=F32)
+    a_c = torch.empty(B, device=g.device, dtype=F32) if w_c != 0.0 else None
+    _call("mirror_contrastive_coef", _p(g, F32), 0 if g.dim() == 0 or g.numel() == 1 and B != 1 else 1, B, w_r, w_c, mult, _p(a_r), _p(a_c))
+    return a_r, a_c
 
 
 def _bt_view(t, E):

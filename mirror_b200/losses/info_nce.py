@@ -50,9 +50,9 @@ class InfoNCE(nn.Module):
                 raise ValueError("Vectors of <query> and <negative_keys> should have the same number of components.")
             raise NotImplementedError("explicit negative_keys: the reference branch never assigns `loss` "
                                       "(losses/info_nce.py:126-143,166); only implicit negatives are implemented")
-        if reduction != "mean":
-            raise NotImplementedError("only reduction='mean' (the trainer's setting) is implemented in the fused kernel")
+        if reduction not in ("mean", "sum", "none"):  # F.cross_entropy's own check (losses/info_nce.py:155-164)
+            raise ValueError(f"{reduction} is not a valid value for reduction")
         q = ops.l2_normalize(query.float(), 1e-12)  # F.normalize default eps
         k = ops.l2_normalize(positive_key.float(), 1e-12)
         scale = torch.full((), 1.0 / temperature, device=query.device, dtype=torch.float32)
-        return ops.clip_loss(q, k, scale, 0.5, 0.5) if symmetric else ops.clip_loss(q, k, scale, 1.0, 0.0)
+        return ops.clip_loss(q, k, scale, 0.5, 0.5, reduction) if symmetric else ops.clip_loss(q, k, scale, 1.0, 0.0, reduction)

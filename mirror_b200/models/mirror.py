@@ -151,6 +151,8 @@ class _NystromParams(nn.Module):
     def __init__(self, dim, heads=8, dropout=0.1, kernel=33):
         super().__init__()
         assert dim % heads == 0 and dim % 2 == 0
+        if heads != ops.WSI_HEADS or kernel != 33:
+            raise NotImplementedError("the Nystrom kernels are written for the reference's 8 heads / 33-tap residual (models/mirror.py:299-309)")
         self.heads, self.dropout = heads, dropout
         self.to_qkv = nn.Linear(dim, dim * 3, bias=False)
         self.to_out = nn.Sequential(nn.Linear(dim, dim), nn.Dropout(dropout))
@@ -168,7 +170,7 @@ class TransLayer(nn.Module):
     def forward(self, x):
         a = self.attn
         return ops.nystrom_layer(x, self.norm.weight, self.norm.bias, a.to_qkv.weight, a.to_out[0].weight, a.to_out[0].bias,
-                                 a.res_conv.weight, a.dropout if self.training else 0.0)
+                                 a.res_conv.weight, a.to_out[1].p if self.training else 0.0, self.norm.eps)
 
 
 class PPEG(nn.Module):
@@ -318,7 +320,10 @@ class FeatureTransMILHybrid(FeatureTransMIL):
 
     def forward_encoder(self, h):
         y, y16, _ = self._tokens(h, drop_wrap=True)  # LayerNorm + `h[:, :-add_length]` (models/mirror.py:372) in one pass
-        self._emb16 = y16  # bf16 copy for the decoders of THIS forward (not a parameter/buffer)
+        # bf16 copy for the retention decoder, attached to the TENSOR it mirrors (with its version counter), not to the
+        # module: a different or modified embedding of the same shape cannot pick it up, and nothing stays pinned on the
+        # module (deepcopy / ModelEma) once the caller drops the embedding
+        y._mirror_side = (y16, y._version)
         return y
 
     def forward_alignment_head(self, h, cls=None):
@@ -333,9 +338,10 @@ class FeatureTransMILHybrid(FeatureTransMIL):
         if noise is None:
             noise = torch.rand(B, N, device=h.device)
         mask = K.rank_mask(noise.float().contiguous(), keep)
-        x16 = getattr(self, "_emb16", None)
-        if x16 is not None and (x16.shape != h.shape or not h.is_contiguous() or not x16.is_contiguous()):
-            x16 = None
+        side = getattr(h, "_mirror_side", None)
+        x16 = None
+        if side is not None and side[1] == h._version and side[0].shape == h.shape and h.is_contiguous() and h.dtype == torch.float32:
+            x16 = side[0]
         r = ops.linear(h, self.retention_embed.weight, self.retention_embed.bias, x16=x16)
         r = ops.MaskPosFn.apply(r, mask, self.mask_token, self.retention_gene_embed, 1)
         for blk in self.retention_blocks:
@@ -347,7 +353,6 @@ class FeatureTransMILHybrid(FeatureTransMIL):
     def forward_decoders(self, h, mask_ratio, noise=None, cls=None):
         a = self.forward_alignment_head(h, cls)
         r, mask = self.forward_retention_head(h, mask_ratio, noise)
-        self._emb16 = None
         return a, r, mask
 
     def forward(self, h, mask_ratio=0.75):
@@ -434,7 +439,11 @@ class MIRROR(nn.Module):
         noise = noise or {}
         # the encoder output is read whole (retention decoder), as its cls row (alignment head, style encoder) and as its
         # patch rows (retention target): one fan-out node, so that the backward merges the three gradients in one pass
-        wsi_cls, wsi_emb, wsi_retention_target = ops.token_fanout(self.wsi_encoder.forward_encoder(wsi_emb))
+        enc = self.wsi_encoder.forward_encoder(wsi_emb)
+        wsi_cls, wsi_emb, wsi_retention_target = ops.token_fanout(enc)
+        side = getattr(enc, "_mirror_side", None)
+        if side is not None and wsi_emb.data_ptr() == enc.data_ptr():  # the fan-out's full view aliases the encoder output
+            wsi_emb._mirror_side = (side[0], wsi_emb._version)
         wa, wr, wm = self.wsi_encoder.forward_decoders(wsi_emb, wsi_mask_ratio, noise.get("wsi_mask"), cls=wsi_cls)
         rna_emb = self.rna_encoder.forward_encoder(rna_emb)
         ra, rr, rm = self.rna_encoder.forward_decoders(rna_emb, rna_mask_ratio, noise.get("rna_mask"))

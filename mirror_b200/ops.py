@@ -23,11 +23,23 @@ _seed_state = {"base": None, "n": 0}
 
 
 def next_seed() -> int:
-    """Host-side counter-based seed for the hashed dropout masks (no device sync)."""
-    if _seed_state["base"] is None:
-        _seed_state["base"] = torch.initial_seed() & 0xFFFFFFFF
+    """Host-side counter-based seed for the hashed dropout masks (no device sync).  The stream restarts whenever
+    torch.manual_seed() changes torch's seed (resume, per-rank seeding after the first forward)."""
+    base = torch.initial_seed() & 0xFFFFFFFF
+    if _seed_state["base"] != base:
+        _seed_state["base"], _seed_state["n"] = base, 0
     _seed_state["n"] += 1
-    return ((_seed_state["base"] * 0x9E3779B1) ^ (_seed_state["n"] * 0x85EBCA77)) & 0x7FFFFFFFFFFFFFFF
+    return ((base * 0x9E3779B1) ^ (_seed_state["n"] * 0x85EBCA77)) & 0x7FFFFFFFFFFFFFFF
+
+
+class Side:
+    """Holder for a bf16 side copy handed to a Function: custom_fwd(cast_inputs=float32) converts every floating-point
+    TENSOR argument under torch.autocast -- a bf16 copy passed bare would come out as fp32 (and be rejected by the GEMM).
+    A plain object is passed through untouched."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
 
 
 def _r8(x):
@@ -86,6 +98,9 @@ class LinearFn(Function):
         N, Kd = weight.shape
         lead = x.shape[:-1]
         rows = x.numel() // Kd
+        x16 = x16.t if isinstance(x16, Side) else x16
+        if x16 is not None and (x16.dtype != BF16 or x16.shape != x.shape):
+            x16 = None
         Kp = _r8(Kd)
         precise = rows <= PRECISE_ROWS
         y = torch.empty(*lead, N, device=x.device, dtype=F32)  # returned as-is (no view) so callers may update it in place
@@ -164,7 +179,8 @@ class LinearFn(Function):
 
 
 def linear(x, weight, bias=None, row_res=None, x16=None, res=None, drop_p=0.0):
-    return LinearFn.apply(x, weight, bias, row_res, x16, res, drop_p, next_seed() if drop_p > 0 else 0)
+    return LinearFn.apply(x, weight, bias, row_res, Side(x16) if x16 is not None else None, res, drop_p,
+                          next_seed() if drop_p > 0 else 0)
 
 
 class StackRowsFn(Function):
@@ -417,7 +433,7 @@ class NystromLayerFn(Function):
 
     @staticmethod
     @_cfwd
-    def forward(ctx, h, ln_w, ln_b, qkv_w, out_w, out_b, conv_w, drop_p, seed):
+    def forward(ctx, h, ln_w, ln_b, qkv_w, out_w, out_b, conv_w, drop_p, seed, eps=1e-5):
         B, S, E = h.shape
         hd = WSI_HEADS
         d, m = E // hd, E // 2
@@ -427,7 +443,7 @@ class NystromLayerFn(Function):
         scale = d ** -0.5
         dev = h.device
         h = h.contiguous()
-        xn16, _, mean, rstd = K.layernorm_fwd(h, ln_w, ln_b, 1e-5, n_out=n, pad=pad)
+        xn16, _, mean, rstd = K.layernorm_fwd(h, ln_w, ln_b, eps, n_out=n, pad=pad)
         wqkv16 = K.cast_bf16(qkv_w)
         qkv = torch.empty(B, n, 3 * E, device=dev, dtype=BF16)
         K.gemm(xn16.view(B * n, E), wqkv16, out_bf16=qkv.view(B * n, 3 * E))
@@ -566,11 +582,11 @@ class NystromLayerFn(Function):
         db = torch.zeros(E, device=dev, dtype=F32)
         dh = torch.empty_like(h)
         K.layernorm_bwd(dxn, h, ln_w, mean, rstd, pad, dh, dy, dg, db)
-        return dh, dg, db, d_qkv_w, d_out_w, d_out_b, d_conv.view(conv_w.shape), None, None
+        return dh, dg, db, d_qkv_w, d_out_w, d_out_b, d_conv.view(conv_w.shape), None, None, None
 
 
-def nystrom_layer(h, norm_w, norm_b, qkv_w, out_w, out_b, conv_w, drop_p):
-    return NystromLayerFn.apply(h, norm_w, norm_b, qkv_w, out_w, out_b, conv_w, drop_p, next_seed() if drop_p > 0 else 0)
+def nystrom_layer(h, norm_w, norm_b, qkv_w, out_w, out_b, conv_w, drop_p, eps=1e-5):
+    return NystromLayerFn.apply(h, norm_w, norm_b, qkv_w, out_w, out_b, conv_w, drop_p, next_seed() if drop_p > 0 else 0, eps)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -671,57 +687,67 @@ class ReparamFn(Function):
 
 
 # ----------------------------------------------------------------------------------------------
+def _r64(x):
+    return (x + 63) // 64 * 64
+
+
+def contrastive_operands(w, r, precise):
+    """bf16 operands of the fused contrastive kernels: plain [B, Dp] copies, or split-3 [B, 3 Dp] (w: hi|lo|hi, r: hi|hi|lo,
+    so that w3 . r3 = hi hi + lo hi + hi lo whichever of the two is the row operand).  Dp = E rounded up to 64 (zeros)."""
+    B, E = w.shape
+    Dp = _r64(E)
+    if precise:
+        return K.cast_split3(w, B, Dp, False, 0), K.cast_split3(r, r.shape[0], Dp, False, 1), Dp
+    return K.cast_bf16(w, Dp), K.cast_bf16(r, Dp), Dp
+
+
 class ClipLossFn(Function):
     """Contrastive loss over logits = scale * W R^T: ClipLoss (losses/mirror_loss.py:37-52, w_row=w_col=0.5) and
-    InfoNCE's implicit-negative branch (losses/info_nce.py:144-164).  `scale` is a 0-d device tensor.
-    Up to PRECISE_ROWS samples the three small GEMMs (logits, dW, dR) run fp32-grade (split-3 bf16 operands): the
-    temperature multiplies every rounding error of the similarities by ~14-100."""
+    InfoNCE's implicit-negative branch (losses/info_nce.py:144-164), reduction 'mean' | 'sum' | 'none'.
+    `scale` is a 0-d device tensor.  The B x B logits never reach HBM (csrc/contrastive.cu): two statistics passes (row
+    log-sum-exp of W R^T and of R W^T) and two gradient passes that recompute the logits tile by tile in TMEM and feed
+    G = dLoss/dlogits straight into a second tcgen05.mma (dW = G R, dR = G^T W).
+    Up to PRECISE_ROWS samples the operands are split-3 bf16 (fp32-grade products): the temperature multiplies every
+    rounding error of the similarities by ~14-100."""
 
     @staticmethod
     @_cfwd
-    def forward(ctx, w, r, scale, w_row, w_col):
+    def forward(ctx, w, r, scale, w_row, w_col, reduction="mean"):
         B, E = w.shape
-        Ep = _r8(E)
         w, r = w.contiguous(), r.contiguous()
         precise = B <= PRECISE_ROWS
-        raw = torch.empty(B, B, device=w.device, dtype=F32)
-        if precise:
-            K.gemm(K.cast_split3(w, B, Ep, False, 0), K.cast_split3(r, B, Ep, False, 1), out_f32=raw)
-            ctx.save_for_backward(w, r)
-        else:
-            w16, r16 = K.cast_bf16(w, Ep), K.cast_bf16(r, Ep)
-            K.gemm(w16[:, :E], r16[:, :E], out_f32=raw)
-            ctx.save_for_backward(w16, r16)
+        w16, r16, Dp = contrastive_operands(w, r, precise)
         scale = scale.reshape(()).contiguous()
-        loss, row, col = K.clip_loss_fwd(raw, scale, w_row, w_col)
-        ctx.aux = (raw, scale, row, col)
-        ctx.meta = (B, E, w_row, w_col, precise)
+        lse_r, diag = K.contrastive_stats(w16, r16, scale)
+        lse_c = K.contrastive_stats(r16, w16, scale)[0] if w_col != 0.0 else None
+        mult = 1.0 / B if reduction == "mean" else 1.0
+        loss = K.contrastive_loss(lse_r, lse_c, diag, w_row, w_col, mult, reduction == "none")
+        ctx.save_for_backward(w16, r16, scale, lse_r, lse_c)
+        ctx.meta = (B, E, Dp, w_row, w_col, precise, mult)
         return loss
 
     @staticmethod
     @once_differentiable
     @_cbwd
     def backward(ctx, gout):
-        ws, rs = ctx.saved_tensors
-        raw, scale, row, col = ctx.aux
-        B, E, w_row, w_col, precise = ctx.meta
-        Bp, Ep = _r8(B), _r8(E)
+        w16, r16, scale, lse_r, lse_c = ctx.saved_tensors
+        B, E, Dp, w_row, w_col, precise, mult = ctx.meta
         dscale = torch.zeros((), device=gout.device, dtype=F32)
-        G = K.clip_loss_bwd(raw, scale, w_row, w_col, row, col, gout.contiguous(), dscale, want_f32=precise)
-        dw = torch.empty(B, E, device=gout.device, dtype=F32)
-        dr = torch.empty(B, E, device=gout.device, dtype=F32)
-        if precise:
-            K.gemm(K.cast_split3(G, B, Bp, False, 0), _T(K.cast_split3(rs, Bp, Ep, True, 1)[:, :E]), out_f32=dw)       # dW = G R
-            K.gemm(_T(K.cast_split3(G, Bp, Bp, True, 0)[:, :B]), _T(K.cast_split3(ws, Bp, Ep, True, 1)[:, :E]), out_f32=dr)  # dR = G^T W
+        a_r, a_c = K.contrastive_coef(gout.contiguous(), B, w_row, w_col, mult)
+        if lse_c is None:  # one-sided: the column terms vanish (a_c = None), the column LSE is never read
+            lse_c = lse_r
+        # w3 = hi|lo|hi (lo block at Dp), r3 = hi|hi|lo (lo block at 2 Dp)
+        dw = K.contrastive_grad(w16, r16, Dp, E, precise, 2 * Dp, scale, 0, lse_r, lse_c, a_r, a_c, dscale)
+        if a_c is None:
+            a_c0 = torch.zeros_like(a_r)
+            dr = K.contrastive_grad(r16, w16, Dp, E, precise, Dp, scale, 0, lse_c, lse_r, a_c0, a_r, None)
         else:
-            assert B % 8 == 0, "batch must be a multiple of 8 beyond PRECISE_ROWS (TMA row stride)"
-            K.gemm(G, _T(rs[:, :E]), out_f32=dw)
-            K.gemm(_T(G), _T(ws[:, :E]), out_f32=dr)
-        return dw, dr, dscale, None, None
+            dr = K.contrastive_grad(r16, w16, Dp, E, precise, Dp, scale, 0, lse_c, lse_r, a_c, a_r, dscale)
+        return dw, dr, dscale, None, None, None
 
 
-def clip_loss(w, r, scale, w_row=0.5, w_col=0.5):
-    return ClipLossFn.apply(w, r, scale, w_row, w_col)
+def clip_loss(w, r, scale, w_row=0.5, w_col=0.5, reduction="mean"):
+    return ClipLossFn.apply(w, r, scale, w_row, w_col, reduction)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -411,19 +411,48 @@ class Emu:
         return g
 
     # ---------------------------------------------------------------- losses
-    def clip_loss_fwd(self, raw, scale, w_row, w_col):
-        l = scale * raw
-        row, col = torch.logsumexp(l, 1), torch.logsumexp(l, 0)
-        d = l.diagonal()
-        return (w_row * (row - d) + w_col * (col - d)).mean(), row, col
+    def contrastive_stats(self, x, y, scale, diag0=0):
+        assert x.dtype == BF16 and y.dtype == BF16 and x.stride(0) % 8 == 0 and y.stride(0) % 8 == 0
+        l = scale * (x.float() @ y.float().T)
+        i = torch.arange(x.shape[0])
+        return torch.logsumexp(l, 1), l[i, i + diag0]
 
-    def clip_loss_bwd(self, raw, scale, w_row, w_col, row, col, gout, dscale, want_f32=False):
-        B = raw.shape[0]
+    def contrastive_grad(self, x, y, D, E, precise, lo_off, scale, diag0, lse_r, lse_c, a_r, a_c, dscale):
+        Br, Kd = x.shape
+        assert D % 64 == 0 and E <= D and (Kd == 3 * D if precise else Kd == D)
+        raw = x.float() @ y.float().T
         l = scale * raw
-        p = w_row * torch.exp(l - row[:, None]) + w_col * torch.exp(l - col[None, :]) - (w_row + w_col) * torch.eye(B)
-        p = p * gout / B
-        dscale += (p * raw).sum()
-        return (p * scale) if want_f32 else (p * scale).to(BF16)
+        pr = a_r[:, None] * torch.exp(l - lse_r[:, None])
+        g = pr.clone()
+        i = torch.arange(Br)
+        if a_c is not None:
+            g = g + a_c[None, :] * torch.exp(l - lse_c[None, :])
+            g[i, i + diag0] -= a_c[i + diag0]
+        g[i, i + diag0] -= a_r
+        if dscale is not None:
+            d = pr.clone()
+            d[i, i + diag0] -= a_r
+            dscale += (d * raw).sum()
+        g = g * scale
+        yf = y.float()
+        if precise:  # G = hi + lo (both bf16), value = hi + lo blocks of y; the lo*lo term is dropped like in the kernel
+            gh = g.to(BF16).float()
+            gl = (g - gh).to(BF16).float()
+            yh, yl = yf[:, :D], yf[:, lo_off:lo_off + D]
+            dx = gh @ yh + gl @ yh + gh @ yl
+        else:
+            dx = g.to(BF16).float() @ yf[:, :D]
+        return dx[:, :E].contiguous()
+
+    def contrastive_loss(self, lse_r, lse_c, diag, w_r, w_c, mult, per_sample):
+        l = w_r * (lse_r - diag)
+        if w_c != 0.0:
+            l = l + w_c * (lse_c - diag)
+        return l if per_sample else l.sum() * mult
+
+    def contrastive_coef(self, g, B, w_r, w_c, mult):
+        v = (g.reshape(-1) * mult).expand(B) if g.numel() == 1 else g * mult
+        return (v * w_r).contiguous(), ((v * w_c).contiguous() if w_c != 0.0 else None)
 
     def masked_mse_fwd(self, a, b, mask):
         E = a.shape[-1]
