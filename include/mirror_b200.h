@@ -231,6 +231,60 @@ int mirror_rna_attn_bwd(const float* qkv, const float* dout, int32_t B, int32_t 
                         mirror_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Flash-style fused softmax products of the Nystrom attention (flash_nystrom.cu).  Replaces, per layer, the einsum +
+ * softmax + einsum chains of nystrom_attention (call site models/mirror.py:299-312):
+ *   out = softmax(q k_l^T) W + res_conv(v)   and   kv = softmax(q_l k^T) v
+ * without the [n x m] / [m x n] probability matrices ever reaching HBM.
+ *   out[b,h,r,:] = sum_j softmax_j(alpha x[b,h,r,:] . y[b,h,j,:]) v[b,h,j,:]  (+ res[b,h,r,:]);   lse2 = log2 sum_j 2^(alpha log2e x.y)
+ * x: [batch, heads, R, d], y / v: [batch, heads, C, d] bf16 views addressed through (ld, head stride, batch stride) in
+ * elements (multiples of 8; bases 16-byte aligned), d % 8 == 0, d <= 128.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  const void* y;
+  const void* v;
+  int64_t x_ld, x_hs, x_bs, y_ld, y_hs, y_bs, v_ld, v_hs, v_bs;
+  int32_t R, C, d, heads, batch;
+  float alpha;
+  void* out; /* bf16 */
+  int64_t o_ld, o_hs, o_bs;
+  const void* res; /* bf16 or NULL */
+  int64_t r_ld, r_hs, r_bs;
+  float* lse2; /* [batch, heads, R] or NULL */
+} mirror_flash_args;
+int mirror_flash_softmax_pv(const mirror_flash_args* a, mirror_stream_t stream);
+
+/* Backward of the product above by recomputation (autograd of the einsum / softmax / einsum chain), one orientation per call.
+ * With P = 2^(alpha log2e S - lse2), dS = alpha P (dP - dot), dot[i] = dO_i . O_i:
+ *   cols = 0 (tile = softmax rows):  S = a b^T (x y^T), dP = c dd^T (dO v^T);  out1 = dS b                 (= dX)
+ *   cols = 1 (tile = keys):          S = a b^T (y x^T), dP = c dd^T (v dO^T);  out1 = dS b (= dY),  out2 = P dd (= dV)
+ * a, c: [batch, heads, T, d];  b, dd: [batch, heads, L, d];  lse2 / dot: [batch, heads, softmax rows] (T for cols = 0, else L).
+ * Each output is bf16 or f32 [batch, heads, T, d] through (ld, hs, bs) with an optional bf16 residual read at row / row_div and
+ * scaled by rscale (the landmark-mean backward: token t receives d_landmark[t / l] / l; the value residual conv^T(dO)). */
+typedef struct {
+  void* ptr;
+  int32_t is_f32;
+  int64_t ld, hs, bs;
+  const void* res;
+  int64_t r_ld, r_hs, r_bs;
+  int32_t row_div;
+  float rscale;
+} mirror_flash_out;
+typedef struct {
+  const void* a;
+  const void* b;
+  const void* c;
+  const void* dd;
+  int64_t a_ld, a_hs, a_bs, b_ld, b_hs, b_bs, c_ld, c_hs, c_bs, d_ld, d_hs, d_bs;
+  int32_t T, L, d, heads, batch, cols;
+  float alpha;
+  const float* lse2;
+  const float* dot;
+  mirror_flash_out out1, out2;
+} mirror_flash_bwd_args;
+int mirror_flash_bwd(const mirror_flash_bwd_args* a, mirror_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Losses (loss.cu).  Loss values, the temperature scale and upstream gradients are DEVICE scalars.
  * ---------------------------------------------------------------------------------------------- */
 /* Fused contrastive loss (contrastive.cu): the B x B logits L = (*scale) X Y^T live only in TMEM.

@@ -44,6 +44,44 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+class FlashArgs(ctypes.Structure):
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("y", ctypes.c_void_p), ("v", ctypes.c_void_p),
+        ("x_ld", ctypes.c_int64), ("x_hs", ctypes.c_int64), ("x_bs", ctypes.c_int64),
+        ("y_ld", ctypes.c_int64), ("y_hs", ctypes.c_int64), ("y_bs", ctypes.c_int64),
+        ("v_ld", ctypes.c_int64), ("v_hs", ctypes.c_int64), ("v_bs", ctypes.c_int64),
+        ("R", ctypes.c_int32), ("C", ctypes.c_int32), ("d", ctypes.c_int32), ("heads", ctypes.c_int32), ("batch", ctypes.c_int32),
+        ("alpha", ctypes.c_float),
+        ("out", ctypes.c_void_p), ("o_ld", ctypes.c_int64), ("o_hs", ctypes.c_int64), ("o_bs", ctypes.c_int64),
+        ("res", ctypes.c_void_p), ("r_ld", ctypes.c_int64), ("r_hs", ctypes.c_int64), ("r_bs", ctypes.c_int64),
+        ("lse2", ctypes.c_void_p),
+    ]
+
+
+class FlashOut(ctypes.Structure):
+    _fields_ = [
+        ("ptr", ctypes.c_void_p), ("is_f32", ctypes.c_int32),
+        ("ld", ctypes.c_int64), ("hs", ctypes.c_int64), ("bs", ctypes.c_int64),
+        ("res", ctypes.c_void_p), ("r_ld", ctypes.c_int64), ("r_hs", ctypes.c_int64), ("r_bs", ctypes.c_int64),
+        ("row_div", ctypes.c_int32), ("rscale", ctypes.c_float),
+    ]
+
+
+class FlashBwdArgs(ctypes.Structure):
+    _fields_ = [
+        ("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("c", ctypes.c_void_p), ("dd", ctypes.c_void_p),
+        ("a_ld", ctypes.c_int64), ("a_hs", ctypes.c_int64), ("a_bs", ctypes.c_int64),
+        ("b_ld", ctypes.c_int64), ("b_hs", ctypes.c_int64), ("b_bs", ctypes.c_int64),
+        ("c_ld", ctypes.c_int64), ("c_hs", ctypes.c_int64), ("c_bs", ctypes.c_int64),
+        ("d_ld", ctypes.c_int64), ("d_hs", ctypes.c_int64), ("d_bs", ctypes.c_int64),
+        ("T", ctypes.c_int32), ("L", ctypes.c_int32), ("d", ctypes.c_int32), ("heads", ctypes.c_int32), ("batch", ctypes.c_int32),
+        ("cols", ctypes.c_int32),
+        ("alpha", ctypes.c_float),
+        ("lse2", ctypes.c_void_p), ("dot", ctypes.c_void_p),
+        ("out1", FlashOut), ("out2", FlashOut),
+    ]
+
+
 def lib():
     """Load the library, (re)building it first when it is missing or older than its sources.  The digest check is cheap
     (hash of csrc/ + the header) and runs under an exclusive file lock: the ranks of a DDP job start together and must not
@@ -108,6 +146,8 @@ SIGNATURES = {
     "mirror_ppeg_bwd": [_P, _P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "mirror_rna_attn_fwd": [_P, _I32, _I32, _P, _P, _P],
     "mirror_rna_attn_bwd": [_P, _P, _I32, _I32, _P, _P, _P],
+    "mirror_flash_softmax_pv": [_P, _P],
+    "mirror_flash_bwd": [_P, _P],
     "mirror_contrastive_nsplit": [_I32, _I32],
     "mirror_contrastive_stats": [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _I32, _P, _I32, _P, _P, _P],
     "mirror_contrastive_grad": [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P],

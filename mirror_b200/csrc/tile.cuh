@@ -87,4 +87,32 @@ inline int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long l
   return 0;
 }
 
+// 4-D bf16 view [n2, n1, rows, cols] with element strides (s2, s1, ld, 1): box = 64 columns x box_rows rows of one (n2, n1)
+// slice.  Coordinates of a load: (col, row, i1, i2).  Columns / rows beyond the extents read as zeros.
+inline int make_map_4d(CUtensorMap* map, const void* ptr, long long cols, long long rows, long long ld, long long n1, long long s1,
+                       long long n2, long long s2, int box_rows) {
+  auto enc = tile_get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MB_ERR_DRIVER;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 7) || (n1 > 1 && (s1 & 7)) || (n2 > 1 && (s2 & 7))) {
+    set_error("tile operand misaligned: ptr=%p ld=%lld s1=%lld s2=%lld (need 16 B / multiples of 8 elements)", ptr, ld, s1, s2);
+    return MB_ERR_ALIGN;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)n1, (cuuint64_t)n2};
+  const cuuint64_t fb = (cuuint64_t)ld * 2;
+  cuuint64_t strides[3] = {fb, n1 > 1 ? (cuuint64_t)s1 * 2 : fb, n2 > 1 ? (cuuint64_t)s2 * 2 : fb};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed (%d): cols=%lld rows=%lld ld=%lld n1=%lld s1=%lld n2=%lld s2=%lld", (int)r, cols, rows, ld,
+              n1, s1, n2, s2);
+    return MB_ERR_DRIVER;
+  }
+  return 0;
+}
+
 }  // namespace mb

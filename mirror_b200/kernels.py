@@ -511,6 +511,76 @@ def rna_attn_bwd(qkv, dout):
     return dqkv
 
 
+def _bhrd(t, name):
+    """(ptr, ld, head stride, batch stride) of a [B,h,rows,d] bf16 view with unit stride on d."""
+    _cuda(t, BF16)
+    if t.dim() != 4 or t.stride(3) != 1:
+        raise ValueError(f"flash: {name} must be a [B,h,rows,d] view with unit stride on d")
+    return t.data_ptr(), t.stride(2), t.stride(1), t.stride(0)
+
+
+@_op
+def flash_softmax_pv(x, y, v, alpha, out, res=None, want_lse=True):
+    """out[B,h,R,d] (bf16 view, written in place) = softmax_rows(alpha x y^T) v (+ res) with the probabilities only in
+    TMEM / shared memory; returns lse2 [B,h,R] f32 (base-2 log-sum-exp of the scaled logits) for the backward."""
+    B, h, R, d = x.shape
+    C = y.shape[2]
+    if y.shape != (B, h, C, d) or v.shape != (B, h, C, d) or out.shape != (B, h, R, d) or (res is not None and res.shape != out.shape):
+        raise ValueError("flash_softmax_pv: shape mismatch")
+    a = _lib.FlashArgs()
+    a.x, a.x_ld, a.x_hs, a.x_bs = _bhrd(x, "x")
+    a.y, a.y_ld, a.y_hs, a.y_bs = _bhrd(y, "y")
+    a.v, a.v_ld, a.v_hs, a.v_bs = _bhrd(v, "v")
+    a.out, a.o_ld, a.o_hs, a.o_bs = _bhrd(out, "out")
+    if res is not None:
+        a.res, a.r_ld, a.r_hs, a.r_bs = _bhrd(res, "res")
+    a.R, a.C, a.d, a.heads, a.batch, a.alpha = R, C, d, h, B, alpha
+    lse2 = torch.empty(B, h, R, device=x.device, dtype=F32) if want_lse else None
+    a.lse2 = lse2.data_ptr() if want_lse else None
+    _lib.check(_lib.fn("mirror_flash_softmax_pv")(ctypes.byref(a), _stream()), "flash_softmax_pv")
+    LAUNCHES[0] += 1
+    return lse2
+
+
+def _flash_out(o, spec, B, h, T, d):
+    """spec = (tensor [B,h,T,d] bf16|f32 view, residual bf16 [B,h,ceil(T/row_div),d] view | None, row_div, rscale)"""
+    t, res, row_div, rscale = spec
+    _cuda(t)
+    if t.shape != (B, h, T, d) or t.stride(3) != 1 or t.dtype not in (BF16, F32):
+        raise ValueError("flash_bwd: outputs must be [B,h,T,d] bf16 / f32 views with unit stride on d")
+    o.ptr, o.is_f32, o.ld, o.hs, o.bs = t.data_ptr(), int(t.dtype == F32), t.stride(2), t.stride(1), t.stride(0)
+    o.row_div, o.rscale = row_div, rscale
+    if res is not None:
+        if res.shape != (B, h, (T + row_div - 1) // row_div, d):
+            raise ValueError("flash_bwd: residual must be [B,h,ceil(T/row_div),d]")
+        o.res, o.r_ld, o.r_hs, o.r_bs = _bhrd(res, "residual")
+
+
+@_op
+def flash_bwd(a, b, c, dd, alpha, lse2, dot, cols, out1, out2=None):
+    """Backward of flash_softmax_pv by recomputation (see mirror_flash_bwd).  a, c: [B,h,T,d]; b, dd: [B,h,L,d] bf16 views;
+    lse2 / dot: [B,h,rows] f32 contiguous (rows = T for cols=False, L for cols=True); out1 / out2: (tensor, residual, row_div, rscale)."""
+    B, h, T, d = a.shape
+    L = b.shape[2]
+    if c.shape != a.shape or b.shape != (B, h, L, d) or dd.shape != b.shape:
+        raise ValueError("flash_bwd: shape mismatch")
+    n_rows = L if cols else T
+    if lse2.shape != (B, h, n_rows) or dot.shape != (B, h, n_rows) or not lse2.is_contiguous() or not dot.is_contiguous():
+        raise ValueError("flash_bwd: lse2 / dot must be contiguous [B,h,rows]")
+    g = _lib.FlashBwdArgs()
+    g.a, g.a_ld, g.a_hs, g.a_bs = _bhrd(a, "a")
+    g.b, g.b_ld, g.b_hs, g.b_bs = _bhrd(b, "b")
+    g.c, g.c_ld, g.c_hs, g.c_bs = _bhrd(c, "c")
+    g.dd, g.d_ld, g.d_hs, g.d_bs = _bhrd(dd, "dd")
+    g.T, g.L, g.d, g.heads, g.batch, g.cols, g.alpha = T, L, d, h, B, int(cols), alpha
+    g.lse2, g.dot = _p(lse2, F32), _p(dot, F32)
+    _flash_out(g.out1, out1, B, h, T, d)
+    if cols:
+        _flash_out(g.out2, out2, B, h, T, d)
+    _lib.check(_lib.fn("mirror_flash_bwd")(ctypes.byref(g), _stream()), "flash_bwd")
+    LAUNCHES[0] += 1
+
+
 @_op
 def contrastive_stats(x, y, scale, diag0=0):
     """x: [Br,K], y: [Bc,K] bf16 (row stride multiple of 8) -> (lse [Br], diag [Br]) of L = scale * x y^T without L in HBM."""

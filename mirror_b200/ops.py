@@ -384,6 +384,7 @@ def _heads(t, col0, E, h=WSI_HEADS):
 
 _AB_F32_DXN = os.environ.get("MIRROR_B200_AB_F32_DXN") == "1"                    # A/B switches (measurement only)
 _FUSED_PINV_BWD = os.environ.get("MIRROR_B200_FUSED_PINV_BWD") == "1"  # opt-in: measured 1.30 ms vs 1.01 ms for the two kernels
+_AB_NO_FLASH = os.environ.get("MIRROR_B200_AB_NO_FLASH") == "1"  # A/B switch (measurement only): materialised attn1 / attn3
 _AB_NO_DOTS = os.environ.get("MIRROR_B200_AB_NO_DOTS") == "1"  # A/B switch (measurement only): two-pass softmax backward everywhere
 
 
@@ -450,9 +451,16 @@ class NystromLayerFn(Function):
         lm = K.landmark_fwd(qkv, m, seg)
         q, k, v = _heads(qkv, 0, E), _heads(qkv, E, E), _heads(qkv, 2 * E, E)
         ql, kl = _heads(lm, 0, E), _heads(lm, E, E)
-        a1, _ = _softmax_gemm(q, kl, n, m, scale)
+        flash = d % 8 == 0 and d <= 128 and not _AB_NO_FLASH  # fused softmax products (csrc/flash_nystrom.cu): attn1 / attn3 never reach HBM
+        a1 = a3 = lse1 = lse3 = None
+        kv = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
+        if flash:
+            lse3 = K.flash_softmax_pv(ql, k, v, scale, kv)                        # kv = softmax(ql k^T) v
+        else:
+            a1, _ = _softmax_gemm(q, kl, n, m, scale)
+            a3, _ = _softmax_gemm(ql, k, m, n, scale)
+            K.gemm(a3, _T(v), out_bf16=kv)
         a2_16, a2_32 = _softmax_gemm(ql, kl, m, m, scale, want_f32=True)
-        a3, _ = _softmax_gemm(ql, k, m, n, scale)
         z16, scratch = K.pinv_init(a2_32)
         iters = []
         mm = (B, hd, m, m)
@@ -470,19 +478,20 @@ class NystromLayerFn(Function):
             K.gemm(z16, _T(Fm), out_bf16=zn16, res=z16)                            # z' = z + z F  (bf16 iterate: measured
             iters += [z16, Em, G1, Fm]                                             #  +3e-4 grad rel-L2 vs an fp32 master copy)
             z16 = zn16
-        kv = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
-        K.gemm(a3, _T(v), out_bf16=kv)
         w_ = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
         K.gemm(z16, _T(kv), out_bf16=w_)
         rc = K.res_conv_fwd(qkv, conv_w.reshape(hd, -1))
         o16 = torch.empty(B, n, E, device=dev, dtype=BF16)
-        K.gemm(a1, _T(w_), out_bf16=_heads(o16, 0, E), res=_heads(rc, 0, E))
+        if flash:
+            lse1 = K.flash_softmax_pv(q, kl, w_, scale, _heads(o16, 0, E), res=_heads(rc, 0, E))   # out = softmax(q kl^T) w + res_conv(v)
+        else:
+            K.gemm(a1, _T(w_), out_bf16=_heads(o16, 0, E), res=_heads(rc, 0, E))
         wout16 = K.cast_bf16(out_w)
         y = torch.empty(B, S, E, device=dev, dtype=F32)
         K.gemm(o16[:, pad:, :], wout16.unsqueeze(0).expand(B, E, E), out_f32=y, bias=out_b, drop_p=drop_p, drop_seed=seed, res=h)
-        ctx.save_for_backward(h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, a1, a2_16, a3, scratch, z16, kv, w_, o16,
-                              wout16, conv_w, rc, *iters)
-        ctx.meta = (B, S, E, pad, n, seg, scale, drop_p, seed)
+        ctx.save_for_backward(h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, lse1 if flash else a1, a2_16, lse3 if flash else a3, scratch,
+                              z16, kv, w_, o16, wout16, conv_w, rc, *iters)
+        ctx.meta = (B, S, E, pad, n, seg, scale, drop_p, seed, flash)
         return y
 
     @staticmethod
@@ -491,11 +500,13 @@ class NystromLayerFn(Function):
     def backward(ctx, dy):
         (h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, a1, a2_16, a3, scratch, zf16, kv, w_, o16, wout16,
          conv_w, rc, *iters) = ctx.saved_tensors
-        B, S, E, pad, n, seg, scale, drop_p, seed = ctx.meta
+        B, S, E, pad, n, seg, scale, drop_p, seed, flash = ctx.meta
         hd = WSI_HEADS
         d, m = E // hd, E // 2
         dev = dy.device
         dy = dy.contiguous()
+        if flash:
+            return NystromLayerFn._backward_flash(ctx, dy)
         q, k, v = _heads(qkv, 0, E), _heads(qkv, E, E), _heads(qkv, 2 * E, E)
         ql, kl = _heads(lm, 0, E), _heads(lm, E, E)
         mm = (B, hd, m, m)
@@ -583,6 +594,97 @@ class NystromLayerFn(Function):
         dh = torch.empty_like(h)
         K.layernorm_bwd(dxn, h, ln_w, mean, rstd, pad, dh, dy, dg, db)
         return dh, dg, db, d_qkv_w, d_out_w, d_out_b, d_conv.view(conv_w.shape), None, None, None
+
+
+def _nystrom_backward_flash(ctx, dy):
+    """Backward of NystromLayerFn with the probability matrices recomputed block by block (csrc/flash_nystrom.cu):
+    four fused launches (two orientations x attn1 / attn3) replace the softmax-gradient passes and the five products that
+    read or wrote the [n x m] matrices."""
+    (h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, lse1, a2_16, lse3, scratch, zf16, kv, w_, o16, wout16,
+     conv_w, rc, *iters) = ctx.saved_tensors
+    B, S, E, pad, n, seg, scale, drop_p, seed, _ = ctx.meta
+    hd = WSI_HEADS
+    d, m = E // hd, E // 2
+    dev = dy.device
+    q, k, v = _heads(qkv, 0, E), _heads(qkv, E, E), _heads(qkv, 2 * E, E)
+    ql, kl = _heads(lm, 0, E), _heads(lm, E, E)
+    mm = (B, hd, m, m)
+
+    # ---- to_out: y = h + drop(o16[pad:] @ Wout^T + b)
+    dyd = torch.empty(B, n, E, device=dev, dtype=BF16)
+    if pad:
+        dyd[:, :pad, :].zero_()
+    K.act_bwd(dy, None, K.ACT_NONE, drop_p, seed, out16=dyd[:, pad:, :])
+    do16 = torch.empty(B, n, E, device=dev, dtype=BF16)
+    K.gemm(dyd.view(B * n, E), _T(wout16), out_bf16=do16.view(B * n, E))
+    d_out_w = wgrad(dyd.view(B * n, E), o16.view(B * n, E), E, E)
+    d_out_b = colsum(dyd.view(B * n, E), E)
+    del dyd
+    do_h = _heads(do16, 0, E)
+
+    # ---- out = attn1 w + res_conv(v): row dots dO . (out - res_conv(v)) per token and head, then the key-stationary pass
+    dots1 = K.rowdot(do16.view(B, n, hd, d), o16.view(B, n, hd, d), rc.view(B, n, hd, d)).permute(0, 2, 1).contiguous()
+    dlm32 = torch.empty(B, m, 2 * E, device=dev, dtype=F32)   # partial landmark gradients (dql | dkl) accumulated in fp32
+    dw16 = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
+    K.flash_bwd(kl, q, w_, do_h, scale, lse1, dots1, True, (_heads(dlm32, E, E), None, 1, 1.0), (dw16, None, 1, 1.0))  # ds1^T q, attn1^T dO
+
+    # ---- w = z kv ; kv = attn3 v
+    gz16 = torch.empty(mm, device=dev, dtype=BF16)
+    K.gemm(dw16, kv, out_bf16=gz16)
+    dkv16 = torch.empty(B, hd, m, d, device=dev, dtype=BF16)
+    K.gemm(_T(zf16), _T(dw16), out_bf16=dkv16)
+    dots3 = K.rowdot(dkv16, kv)
+    K.flash_bwd(ql, k, dkv16, v, scale, lse3, dots3, False, (_heads(dlm32, 0, E), None, 1, 1.0))                   # ds3 k
+    d_conv = torch.zeros(hd, conv_w.numel() // hd, device=dev, dtype=F32)
+    dvc = K.res_conv_bwd(do16, qkv, conv_w.reshape(hd, -1), d_conv)              # conv^T(dO), bf16 [B,n,E]
+
+    # ---- Moore-Penrose iterations, reversed (see NystromLayerFn.backward)
+    gens = []
+    gz32 = None
+    for it in reversed(range(PINV_ITERS)):
+        z16, Em, G1, Fm = iters[4 * it:4 * it + 4]
+        gF = torch.empty(mm, device=dev, dtype=BF16)
+        K.gemm(_T(z16), _T(gz16), out_bf16=gF)
+        gG1q = torch.empty(mm, device=dev, dtype=BF16)
+        K.gemm(_T(Em), _T(gF), out_bf16=gG1q, alpha=0.25)
+        gEn = torch.empty(mm, device=dev, dtype=BF16)
+        K.gemm(gF, G1, more=[(gG1q, Em), (_T(Em), _T(gG1q))], out_bf16=gEn, alpha=-1.0, res=gF, gamma=-1.0, res2=gG1q,
+               gamma2=-4.0)
+        gzn16 = torch.empty(mm, device=dev, dtype=BF16)
+        gzn32 = torch.empty(mm, device=dev, dtype=F32) if it == 0 else None
+        K.gemm(gz16, Fm, more=[(_T(a2_16), _T(gEn))], out_f32=gzn32, out_bf16=gzn16, res=gz16)
+        gens.append((gEn, z16))
+        gz32, gz16 = gzn32, gzn16
+    ga2 = torch.empty(mm, device=dev, dtype=F32)
+    K.gemm(gens[0][0], gens[0][1], more=gens[1:], out_f32=ga2)
+    del gens
+    K.pinv_init_bwd(gz32, iters[0], scratch, ga2, True)
+    ds2, _ = K.softmax_bwd(a2_16, ga2, scale)
+    del ga2, gz32, gz16
+
+    # ---- landmark gradients: dql = ds2 kl + (ds3 k), dkl = ds2^T ql + (ds1^T q); then the token-stationary passes, which add the
+    # landmark-mean backward (token t receives d_landmark[t // seg] / seg) and the value residual in their epilogues
+    dlm16 = torch.empty(B, m, 2 * E, device=dev, dtype=BF16)
+    K.gemm(ds2, _T(kl), out_bf16=_heads(dlm16, 0, E), res=_heads(dlm32, 0, E))
+    K.gemm(_T(ds2), _T(ql), out_bf16=_heads(dlm16, E, E), res=_heads(dlm32, E, E))
+    dqkv16 = torch.empty(B, n, 3 * E, device=dev, dtype=BF16)
+    K.flash_bwd(k, ql, v, dkv16, scale, lse3, dots3, True, (_heads(dqkv16, E, E), _heads(dlm16, E, E), seg, 1.0 / seg),
+                (_heads(dqkv16, 2 * E, E), _heads(dvc, 0, E), 1, 1.0))                                                  # dk, dv
+    K.flash_bwd(q, kl, do_h, w_, scale, lse1, dots1, False, (_heads(dqkv16, 0, E), _heads(dlm16, 0, E), seg, 1.0 / seg))  # dq
+    del do16, dvc, dlm16, dlm32, ds2
+
+    # ---- to_qkv and LayerNorm
+    dxn = torch.empty(B, n, E, device=dev, dtype=BF16)
+    K.gemm(dqkv16.view(B * n, 3 * E), _T(wqkv16), out_bf16=dxn.view(B * n, E))
+    d_qkv_w = wgrad(dqkv16.view(B * n, 3 * E), xn16.view(B * n, E), 3 * E, E)
+    dg = torch.zeros(E, device=dev, dtype=F32)
+    db = torch.zeros(E, device=dev, dtype=F32)
+    dh = torch.empty_like(h)
+    K.layernorm_bwd(dxn, h, ln_w, mean, rstd, pad, dh, dy, dg, db)
+    return dh, dg, db, d_qkv_w, d_out_w, d_out_b, d_conv.view(conv_w.shape), None, None, None
+
+
+NystromLayerFn._backward_flash = staticmethod(_nystrom_backward_flash)
 
 
 def nystrom_layer(h, norm_w, norm_b, qkv_w, out_w, out_b, conv_w, drop_p, eps=1e-5):

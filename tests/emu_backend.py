@@ -411,6 +411,42 @@ class Emu:
         return g
 
     # ---------------------------------------------------------------- losses
+    def flash_softmax_pv(self, x, y, v, alpha, out, res=None, want_lse=True):
+        """unnormalised bf16 probabilities 2^(a2 (S - max)), row sum over the ROUNDED values, O / l in fp32 (the kernel's order)"""
+        for t in (x, y, v, out) + ((res,) if res is not None else ()):
+            assert t.dtype == BF16 and t.stride(3) == 1 and all(s % 8 == 0 for s in t.stride()[:3])
+        a2 = alpha * 1.4426950408889634
+        s_ = torch.matmul(x.float(), y.float().transpose(-1, -2))
+        mx = s_.max(-1, keepdim=True).values
+        p = torch.exp2(a2 * (s_ - mx)).to(BF16).float()
+        l = p.sum(-1, keepdim=True)
+        o = torch.matmul(p, v.float()) / l
+        if res is not None:
+            o = o + res.float()
+        out.copy_(o.to(BF16))
+        return (a2 * mx + torch.log2(l)).squeeze(-1) if want_lse else None
+
+    def flash_bwd(self, a, b, c, dd, alpha, lse2, dot, cols, out1, out2=None):
+        a2 = alpha * 1.4426950408889634
+        s_ = torch.matmul(a.float(), b.float().transpose(-1, -2))   # [.., T, L]
+        dp = torch.matmul(c.float(), dd.float().transpose(-1, -2))
+        if cols:   # statistics run along the block dim (softmax rows = L)
+            p_ = torch.exp2(a2 * s_ - lse2[..., None, :])
+            ds = alpha * p_ * (dp - dot[..., None, :])
+        else:
+            p_ = torch.exp2(a2 * s_ - lse2[..., :, None])
+            ds = alpha * p_ * (dp - dot[..., :, None])
+
+        def store(spec, val):
+            t, res, row_div, rscale = spec
+            if res is not None:
+                val = val + rscale * res.float().repeat_interleave(row_div, dim=-2)[..., : val.shape[-2], :]
+            t.copy_(val.to(t.dtype))
+
+        store(out1, torch.matmul(ds.to(BF16).float(), b.float()))
+        if cols:
+            store(out2, torch.matmul(p_.to(BF16).float(), dd.float()))
+
     def contrastive_stats(self, x, y, scale, diag0=0):
         assert x.dtype == BF16 and y.dtype == BF16 and x.stride(0) % 8 == 0 and y.stride(0) % 8 == 0
         l = scale * (x.float() @ y.float().T)

@@ -250,6 +250,81 @@ def test_rna_attn(B, E):
     both("rna_attn_bwd", (qkv, rn(B, E, seed=1)), tol=1e-5)
 
 
+def _nystrom_views(B, E, n, m, seed=0):
+    """q/k/v interleaved [B,n,3E] and landmarks [B,m,2E] as the Nystrom layer lays them out; returns head views [B,h,rows,d]"""
+    h, d = 8, E // 8
+    qkv = (rn(B, n, 3 * E, seed=seed) * 0.7).to(BF16)
+    lm = (rn(B, m, 2 * E, seed=seed + 1) * 0.7).to(BF16)
+    hv = lambda t, c0: t[:, :, c0:c0 + E].unflatten(-1, (h, d)).permute(0, 2, 1, 3)
+    return qkv, lm, hv
+
+
+@pytest.mark.parametrize("B,E,n,m", [(2, 768, 2304, 384), (1, 768, 768, 384), (3, 192, 192, 96), (2, 192, 96, 96), (1, 384, 960, 192)])
+def test_flash_softmax_pv(B, E, n, m):
+    """csrc/flash_nystrom.cu forward against the dense re-statement: out = softmax(q k_l^T) W + rc (rows = tokens, keys =
+    landmarks, strided head views, residual) and kv = softmax(q_l k^T) v (rows = landmarks, keys = tokens)"""
+    h, d = 8, E // 8
+    qkv, lm, hv = _nystrom_views(B, E, n, m)
+    wv = (rn(B, h, m, d, seed=7) * 0.5).to(BF16)
+    rc = (rn(B, n, E, seed=8) * 0.3).to(BF16)
+    alpha = d ** -0.5
+    for args in (
+        (hv(qkv, 0), hv(lm, E), wv, alpha, torch.zeros(B, n, E, dtype=BF16).unflatten(-1, (h, d)).permute(0, 2, 1, 3), hv(rc, 0)),  # K-C
+        (hv(lm, 0), hv(qkv, E), hv(qkv, 2 * E), alpha, torch.zeros(B, h, m, d, dtype=BF16), None),                              # K-A
+    ):
+        a_cpu = copy.deepcopy(args)
+        a_gpu = to_dev(args)
+        l_cpu = EMU.flash_softmax_pv(*a_cpu)
+        l_gpu = K.flash_softmax_pv(*a_gpu)
+        torch.cuda.synchronize()
+        close(l_gpu, l_cpu, 2e-5, "lse2")
+        close(a_gpu[4], a_cpu[4], 8e-3, "out")
+
+
+@pytest.mark.parametrize("B,E,n,m", [(2, 768, 2304, 384), (1, 768, 768, 384), (3, 192, 192, 96), (2, 192, 96, 96), (1, 384, 960, 192)])
+def test_flash_bwd(B, E, n, m):
+    """csrc/flash_nystrom.cu backward, both orientations, for both Nystrom products: recomputed probabilities, dS through shared
+    memory, landmark-mean broadcast residual (row_div), value residual, f32 and bf16 outputs, strided head-slot outputs"""
+    h, d = 8, E // 8
+    seg = n // m
+    qkv, lm, hv = _nystrom_views(B, E, n, m)
+    alpha = d ** -0.5
+    wv = (rn(B, h, m, d, seed=7) * 0.5).to(BF16)
+    do = (rn(B, n, E, seed=9) * 0.2).to(BF16)
+    dkv = (rn(B, h, m, d, seed=10) * 0.2).to(BF16)
+    dlm16 = (rn(B, m, 2 * E, seed=11) * 0.2).to(BF16)
+    dvc = (rn(B, n, E, seed=12) * 0.2).to(BF16)
+    q, k, v, ql, kl = hv(qkv, 0), hv(qkv, E), hv(qkv, 2 * E), hv(lm, 0), hv(lm, E)
+    # forward statistics on the emulator
+    o1 = torch.zeros(B, h, n, d, dtype=BF16)
+    lse1 = EMU.flash_softmax_pv(q, kl, wv, alpha, o1)
+    dot1 = (hv(do, 0).float() * o1.float()).sum(-1)
+    o3 = torch.zeros(B, h, m, d, dtype=BF16)
+    lse3 = EMU.flash_softmax_pv(ql, k, v, alpha, o3)
+    dot3 = (dkv.float() * o3.float()).sum(-1)
+    z16 = lambda *s_: torch.zeros(*s_, dtype=BF16)
+    z32 = lambda *s_: torch.zeros(*s_, dtype=F32)
+    cases = [
+        # attn1, rows = tokens: dq (+ landmark broadcast)
+        (q, kl, hv(do, 0), wv, alpha, lse1, dot1, False, (hv(z16(B, n, 3 * E), 0), hv(dlm16, 0), seg, 1.0 / seg), None),
+        # attn1, keys = landmarks: dkl part (f32 landmark slot), dW
+        (kl, q, wv, hv(do, 0), alpha, lse1, dot1, True, (hv(z32(B, m, 2 * E), E), None, 1, 1.0), (z16(B, h, m, d), None, 1, 1.0)),
+        # attn3, rows = landmarks: dql part (f32 landmark slot)
+        (ql, k, dkv, v, alpha, lse3, dot3, False, (hv(z32(B, m, 2 * E), 0), None, 1, 1.0), None),
+        # attn3, keys = tokens: dk (+ landmark broadcast), dv (+ value residual)
+        (k, ql, v, dkv, alpha, lse3, dot3, True, (hv(z16(B, n, 3 * E), E), hv(dlm16, E), seg, 1.0 / seg), (hv(z16(B, n, 3 * E), 2 * E), hv(dvc, 0), 1, 1.0)),
+    ]
+    for i, args in enumerate(cases):
+        a_cpu = copy.deepcopy(args)
+        a_gpu = to_dev(args)
+        EMU.flash_bwd(*a_cpu)
+        K.flash_bwd(*a_gpu)
+        torch.cuda.synchronize()
+        close(a_gpu[8][0], a_cpu[8][0], 1e-2, f"case {i} out1")
+        if args[9] is not None:
+            close(a_gpu[9][0], a_cpu[9][0], 1e-2, f"case {i} out2")
+
+
 def _contrastive_problem(Br, Bc, E, precise, seed=0):
     """bf16 operands as ops.contrastive_operands builds them (on the CPU emulator), unit-norm rows, temperature 0.07."""
     x = torch.nn.functional.normalize(rn(Br, E, seed=seed), dim=-1)
