@@ -283,6 +283,9 @@ typedef struct {
   mirror_flash_out out1, out2;
 } mirror_flash_bwd_args;
 int mirror_flash_bwd(const mirror_flash_bwd_args* a, mirror_stream_t stream);
+/* debug hook (measurement only, tools/flash_trace.py): CTA 0 of the flash kernels appends (event id << 48 | clock) entries to
+ * buf[1..capacity), buf[0] counts them; buf = NULL switches the trace off (the default). */
+int mirror_debug_flash_trace(void* buf, int64_t capacity);
 
 /* ------------------------------------------------------------------------------------------------
  * Losses (loss.cu).  Loss values, the temperature scale and upstream gradients are DEVICE scalars.

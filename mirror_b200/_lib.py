@@ -148,6 +148,7 @@ SIGNATURES = {
     "mirror_rna_attn_bwd": [_P, _P, _I32, _I32, _P, _P, _P],
     "mirror_flash_softmax_pv": [_P, _P],
     "mirror_flash_bwd": [_P, _P],
+    "mirror_debug_flash_trace": [_P, _I64],
     "mirror_contrastive_nsplit": [_I32, _I32],
     "mirror_contrastive_stats": [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _I32, _P, _I32, _P, _P, _P],
     "mirror_contrastive_grad": [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P],

@@ -23,7 +23,7 @@ def _digest(paths):
     h = hashlib.sha256()
     for p in sorted(paths):
         with open(p, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())  # location-independent: the tree is copied to other paths (GPU boxes)
             h.update(f.read())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()

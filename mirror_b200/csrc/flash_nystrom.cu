@@ -2,22 +2,47 @@
 // SURVEY.md §2.1 kernels K-A / K-C): the [rows x keys] probability matrices
 //     attn1 = softmax(q k_l^T)   [n x m]   ->  out = attn1 W + res_conv(v)
 //     attn3 = softmax(q_l k^T)   [m x n]   ->  kv  = attn3 v
-// never exist in HBM.  Forward: O = softmax(alpha X Y^T) V with the logits tile in TMEM, probabilities written as a bf16
-// shared-memory tile and consumed by a second tcgen05.mma; two passes over the (cheap, K = head_dim) logits -- row maxima
+// never exist in HBM -- nor in shared memory: the probabilities are written back into TENSOR MEMORY as bf16 and consumed as
+// the A operand of the second tcgen05.mma (the "TS" form: A from TMEM, B from shared memory).
+// Forward: O = softmax(alpha X Y^T) V, logits tile in TMEM, two passes over the (cheap, K = head_dim) logits -- row maxima
 // first, then exp / row sums / P V -- so the accumulator never has to be rescaled.  Backward (flash_bwd below): logits and
-// dP = dO V^T are recomputed per 128 x 64 block, dS = alpha P (dP - D) goes through shared memory into
+// dP = dO V^T are recomputed per 128 x 64 block, dS = alpha P (dP - D) overwrites the logits in TMEM and feeds
 // dX += dS Y (row-stationary) or dY += dS^T X, dV += P^T dO (column-stationary).
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5 softmax / epilogue
-// (thread = row of the 128-row tile).  Persistent: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..9 softmax / epilogue
+// (thread = row of the 128-row tile x half of a block's columns).  Persistent: a CTA walks tiles blockIdx.x,
+// blockIdx.x + gridDim.x, ...  Every hand-off is at least double buffered (logits and probabilities in TMEM, operand tiles
+// in shared memory), so TMA, tensor core and the softmax warps each run at their own pace.
 #include "tile.cuh"
 
 namespace mb {
 namespace {
 
-constexpr int kThreadsF = 192;
+constexpr int kThreadsF = 64 + 8 * 32;
 constexpr int kTB = 128 * 128;  // bytes of one [128 rows x 64 cols] bf16 tile
+constexpr int kHB = 64 * 128;   // bytes of one [64 rows x 64 cols] bf16 tile
 constexpr float kLog2e = 1.4426950408889634f;
+
+// Optional event trace of CTA 0 (debug / measurement only; mirror_debug_flash_trace installs a buffer, NULL = off).  Each traced
+// role (region 0 producer, 1 MMA issuer, 2 softmax warp 2) appends plain stores to its own quarter of the buffer -- no atomics, so
+// an event costs a few cycles: entry = (event id << 48) | (clock64 & 2^48-1); the first word of a region counts its entries.
+__device__ unsigned long long* g_trace = nullptr;
+__device__ unsigned long long g_trace_cap = 0;
+struct Tracer {
+  unsigned long long* base;
+  unsigned int n, cap;
+  __device__ __forceinline__ void init(int region) {
+    base = (blockIdx.x == 0 && g_trace) ? g_trace + region * (g_trace_cap / 4) : nullptr;
+    cap = (unsigned int)(g_trace_cap / 4);
+    n = 0;
+  }
+  __device__ __forceinline__ void ev(int id) {
+    if (base && n + 1 < cap) {
+      base[++n] = ((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xffffffffffffull);
+      base[0] = n;
+    }
+  }
+};
 
 struct FwdParams {
   int R, C;        // softmax rows / keys per (batch, head)
@@ -35,10 +60,10 @@ struct FwdParams {
 struct FwdSmem {
   static constexpr int X = 2 * 2 * kTB;   // two row tiles in flight x two K blocks
   static constexpr int Y = 2 * 2 * kTB;   // ring of two key blocks x two K blocks
-  static constexpr int V = 2 * kTB;       // one key block of values: two 64-column chunks [128 keys x 64]
-  static constexpr int P = 2 * kTB;       // probabilities [128 rows x 128 keys] as two K blocks
+  static constexpr int V = 2 * 2 * kTB;   // ring of two value blocks: two 64-column chunks [128 keys x 64] each
+  static constexpr int ROWS = 2 * 2 * 128 * 4;  // row maxima / row sums of the two column halves
   static constexpr int BARS = 32 * 8 + 16;
-  static constexpr int TOTAL = X + Y + V + P + BARS + 1024;
+  static constexpr int TOTAL = X + Y + V + ROWS + BARS + 1024;
 };
 
 __global__ void __launch_bounds__(kThreadsF, 1)
@@ -49,21 +74,22 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* sX = smem;
   uint8_t* sY = sX + FwdSmem::X;
   uint8_t* sV = sY + FwdSmem::Y;
-  uint8_t* sP = sV + FwdSmem::V;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FwdSmem::P);
+  float* rowmax = reinterpret_cast<float*>(sV + FwdSmem::V);
+  float* rowsum = rowmax + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FwdSmem::V + FwdSmem::ROWS);
   uint64_t* x_full = bars;          // [2]
   uint64_t* x_empty = bars + 2;     // [2]
   uint64_t* y_full = bars + 4;      // [2]
   uint64_t* y_empty = bars + 6;     // [2]
   uint64_t* s_full = bars + 8;      // [2]
   uint64_t* s_empty = bars + 10;    // [2]
-  uint64_t* v_full = bars + 12;
-  uint64_t* v_empty = bars + 13;
-  uint64_t* p_full = bars + 14;
-  uint64_t* p_empty = bars + 15;
-  uint64_t* o_full = bars + 16;
-  uint64_t* o_empty = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* v_full = bars + 12;     // [2]
+  uint64_t* v_empty = bars + 14;    // [2]
+  uint64_t* p_full = bars + 16;     // [2]
+  uint64_t* p_empty = bars + 18;    // [2]
+  uint64_t* o_full = bars + 20;
+  uint64_t* o_empty = bars + 21;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.d + 63) / 64;      // 64-column K blocks of the head dim
@@ -85,14 +111,14 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_init(&y_full[i], 1);
         mbar_init(&y_empty[i], 1);
         mbar_init(&s_full[i], 1);
-        mbar_init(&s_empty[i], 4);
+        mbar_init(&s_empty[i], 8);
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_empty[i], 1);
+        mbar_init(&p_full[i], 8);
+        mbar_init(&p_empty[i], 1);
       }
-      mbar_init(v_full, 1);
-      mbar_init(v_empty, 1);
-      mbar_init(p_full, 4);
-      mbar_init(p_empty, 1);
       mbar_init(o_full, 1);
-      mbar_init(o_empty, 4);
+      mbar_init(o_empty, 8);
       fence_mbar_init();
     }
     __syncwarp();
@@ -102,11 +128,14 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t kColO = 256;  // TMEM: logits buffers at columns [0,128) and [128,256), output accumulator at [256, 256+dpad)
+  // TMEM columns: logits S[2] at 0 / 128, output accumulator at 256 (dpad <= 128), probabilities P[2] (bf16 pairs) at 384 / 448
+  constexpr uint32_t kColO = 256, kColP = 384;
 
   if (warp == 0) {
     // ----------------------------------------------------------------------------------------------- TMA producer
     if (elect_one()) {
+      Tracer tr;
+      tr.init(0);
       uint32_t ycount = 0, vcount = 0, ti = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
         const int rt = w % p.tiles_r;
@@ -116,23 +145,28 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(&x_empty[xb], ((ti >> 1) & 1) ^ 1);
         mbar_expect_tx(&x_full[xb], nkb * kTB);
         for (int kb = 0; kb < nkb; ++kb) tma_load_4d(&tmX, &x_full[xb], sX + (xb * 2 + kb) * kTB, kb * 64, rt * 128, h, b);
+        tr.ev(1);
         auto y_load = [&](int s) {
           const int jb = s % p.nb, st = ycount & 1;
           mbar_wait(&y_empty[st], ((ycount >> 1) & 1) ^ 1);
           mbar_expect_tx(&y_full[st], nkb * kTB);
           for (int kb = 0; kb < nkb; ++kb) tma_load_4d(&tmY, &y_full[st], sY + (st * 2 + kb) * kTB, kb * 64, jb * 128, h, b);
+          tr.ev(2);
           ++ycount;
         };
+        // loads are issued in the order the MMA warp consumes them: S(0), S(1), then per step [P V(s)], S(s+2)
         y_load(0);
+        y_load(1);
         for (int s = 0; s < ns; ++s) {
-          if (s + 1 < ns) y_load(s + 1);
           if (s >= p.nb) {
-            const int jb = s - p.nb;
-            mbar_wait(v_empty, (vcount & 1) ^ 1);
-            mbar_expect_tx(v_full, nvc * kTB);
-            for (int c = 0; c < nvc; ++c) tma_load_4d(&tmV, v_full, sV + c * kTB, c * 64, jb * 128, h, b);
+            const int jb = s - p.nb, st = vcount & 1;
+            mbar_wait(&v_empty[st], ((vcount >> 1) & 1) ^ 1);
+            mbar_expect_tx(&v_full[st], nvc * kTB);
+            for (int c = 0; c < nvc; ++c) tma_load_4d(&tmV, &v_full[st], sV + (st * 2 + c) * kTB, c * 64, jb * 128, h, b);
+            tr.ev(3);
             ++vcount;
           }
+          if (s + 2 < ns) y_load(s + 2);
         }
       }
     }
@@ -141,56 +175,67 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_pv = make_idesc_bf16(128, p.dpad, 0, 1);
-      uint32_t ycount = 0, scount = 0, pvcount = 0, ti = 0;
+      Tracer tr;
+      tr.init(1);
+      uint32_t scount = 0, pvcount = 0, ti = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
         const int xb = ti & 1;
         mbar_wait(&x_full[xb], (ti >> 1) & 1);
         tc_fence_after();
         const uint32_t xa = smem_u32(sX + xb * 2 * kTB);
+        tr.ev(10);
         auto issue_s = [&]() {
-          const int sb = scount & 1, st = ycount & 1;
+          const int sb = scount & 1;  // logits buffer and Y ring stage advance together
           mbar_wait(&s_empty[sb], ((scount >> 1) & 1) ^ 1);
-          mbar_wait(&y_full[st], (ycount >> 1) & 1);
+          tr.ev(14);
+          mbar_wait(&y_full[sb], (scount >> 1) & 1);
           tc_fence_after();
-          const uint32_t ya = smem_u32(sY + st * 2 * kTB);
+          tr.ev(11);
+          const uint32_t ya = smem_u32(sY + sb * 2 * kTB);
           for (int ks = 0; ks < nks; ++ks)
             umma_f16(tmem_base + sb * 128, desc_kmajor(xa + (ks >> 2) * kTB, ks & 3), desc_kmajor(ya + (ks >> 2) * kTB, ks & 3), idesc_s,
                      ks > 0 ? 1u : 0u);
-          umma_commit(&y_empty[st]);
+          umma_commit(&y_empty[sb]);
           umma_commit(&s_full[sb]);
           ++scount;
-          ++ycount;
         };
         issue_s();
+        issue_s();
         for (int s = 0; s < ns; ++s) {
-          if (s + 1 < ns) issue_s();
-          if (s + 1 == ns) umma_commit(&x_empty[xb]);  // every logits product of this row tile has been issued
           if (s >= p.nb) {
-            if (s == p.nb) {  // first P V of the tile overwrites the accumulator: the previous tile's epilogue must have read it
-              mbar_wait(o_empty, (ti & 1) ^ 1);
-            }
-            mbar_wait(p_full, pvcount & 1);
-            mbar_wait(v_full, pvcount & 1);
+            const int pb = pvcount & 1;
+            if (s == p.nb) mbar_wait(o_empty, (ti & 1) ^ 1);  // the previous tile's epilogue has read the accumulator
+            mbar_wait(&p_full[pb], (pvcount >> 1) & 1);
+            tr.ev(15);
+            mbar_wait(&v_full[pb], (pvcount >> 1) & 1);
             tc_fence_after();
-            const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+            tr.ev(12);
+            const uint32_t va = smem_u32(sV + pb * 2 * kTB);
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              umma_f16(tmem_base + kColO, desc_kmajor(pa + (kk >> 2) * kTB, kk & 3), desc_mnmajor(va, kTB, kk), idesc_pv,
-                       (s > p.nb || kk > 0) ? 1u : 0u);
-            umma_commit(p_empty);
-            umma_commit(v_empty);
+            for (int kk = 0; kk < 8; ++kk)  // contraction over the block's 128 keys: 8 TMEM columns (16 bf16) of P per step
+              umma_f16_ts(tmem_base + kColO, tmem_base + kColP + pb * 64 + kk * 8, desc_mnmajor(va, kTB, kk), idesc_pv,
+                          (s > p.nb || kk > 0) ? 1u : 0u);
+            umma_commit(&p_empty[pb]);
+            umma_commit(&v_empty[pb]);
             ++pvcount;
           }
+          if (s + 2 < ns) issue_s();
+          if (s + 3 == ns) umma_commit(&x_empty[xb]);  // every logits product of this row tile has been issued
         }
+        if (ns == 2) umma_commit(&x_empty[xb]);
         umma_commit(o_full);
+        tr.ev(13);
       }
     }
   } else {
     // ----------------------------------------------------------------------------------------------- softmax / epilogue warps
-    const int q = warp & 3;
+    // eight warps: two per TMEM lane quarter, each owning 64 of a key block's 128 columns (thread = row x column half)
+    const int q = warp & 3, hf = (warp - 2) >> 2;
     const int rl = q * 32 + lane;
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
     const float a2 = p.alpha * kLog2e;
+    Tracer tr;
+    tr.init(2);
     uint32_t scount = 0, pvcount = 0, ti = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
       const int rt = w % p.tiles_r;
@@ -198,121 +243,115 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const int h = bh % p.heads, b = bh / p.heads;
       const int row = rt * 128 + rl;
       const bool row_ok = row < p.R;
-      // ---- pass 0: row maxima of the (unscaled) logits; alpha > 0 so max commutes with the scaling
+      const bf16* rrow = p.res ? p.res + b * p.r_bs + h * p.r_hs + (long long)row * p.r_ld : nullptr;
+      if (rrow && row_ok) prefetch_l2(rrow + (hf * 64 < p.d ? hf * 64 : 0));
+      // ---- pass 0: row maxima of the (unscaled) logits; alpha > 0 so max commutes with the scaling.
+      // (All per-chunk loops below are deliberately NOT unrolled across chunks: the kernel's code must stay well inside the
+      // 32 KB instruction cache -- with everything unrolled the once-per-tile epilogue ran at ~17 cycles per instruction.)
       float mx = -INFINITY;
       for (int jb = 0; jb < p.nb; ++jb, ++scount) {
         const int sb = scount & 1;
         mbar_wait(&s_full[sb], (scount >> 1) & 1);
         tc_fence_after();
-        const int cvalid = p.C - jb * 128;
+        if (warp == 2 && lane == 0) tr.ev(20);
+        const int cvalid = p.C - jb * 128 - hf * 64;  // keys of this warp's half that exist
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          if (ch * 32 >= cvalid) break;
+        for (int cc = 0; cc < 2; ++cc) {
+          const int cv = cvalid - cc * 32;
+          if (cv <= 0) break;  // warp-uniform
           uint32_t acc[32];
-          tmem_ld_32x32(lane_base + sb * 128 + ch * 32, acc);
+          tmem_ld_32x32(lane_base + sb * 128 + hf * 64 + cc * 32, acc);
           tmem_ld_wait();
-          if (cvalid - ch * 32 >= 32) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(acc[e]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (e < cvalid - ch * 32) mx = fmaxf(mx, __uint_as_float(acc[e]));
+          for (int e = 0; e < 32; e += 2) {
+            const float a = e < cv ? __uint_as_float(acc[e]) : -INFINITY, c = e + 1 < cv ? __uint_as_float(acc[e + 1]) : -INFINITY;
+            mx = fmaxf(mx, fmaxf(a, c));
           }
         }
+        if (warp == 2 && lane == 0) tr.ev(21);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[sb]);
       }
+      rowmax[hf * 128 + rl] = mx;
+      named_bar_sync(1, 256);
+      if (warp == 2 && lane == 0) tr.ev(22);
+      mx = fmaxf(rowmax[rl], rowmax[128 + rl]);
       const float m2 = mx * a2;
-      // ---- pass 1: P = 2^(a2 S - m2) -> bf16 tile; row sums
+      // ---- pass 1: P = 2^(a2 S - m2) -> bf16 -> tensor memory; row sums
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
       for (int jb = 0; jb < p.nb; ++jb, ++scount, ++pvcount) {
-        const int sb = scount & 1;
+        const int sb = scount & 1, pb = pvcount & 1;
         mbar_wait(&s_full[sb], (scount >> 1) & 1);
+        mbar_wait(&p_empty[pb], ((pvcount >> 1) & 1) ^ 1);  // P V of two blocks ago has consumed this probability buffer
         tc_fence_after();
-        const int cvalid = p.C - jb * 128;
+        if (warp == 2 && lane == 0) tr.ev(23);
+        const int cvalid = p.C - jb * 128 - hf * 64;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          float v[32];
-          if (ch * 32 < cvalid) {
-            uint32_t acc[32];
-            tmem_ld_32x32(lane_base + sb * 128 + ch * 32, acc);
+        for (int cc = 0; cc < 2; ++cc) {  // one 32-column chunk at a time: logits -> exp -> row sum -> bf16 pairs -> 16 TMEM columns
+          const int cv = cvalid - cc * 32;
+          uint32_t acc[32], wd[16];
+          if (cv > 0) {  // warp-uniform
+            tmem_ld_32x32(lane_base + sb * 128 + hf * 64 + cc * 32, acc);
             tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = fast_exp2(fmaf(a2, __uint_as_float(acc[e]), -m2));
-            if (cvalid - ch * 32 < 32) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (e >= cvalid - ch * 32) v[e] = 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = 0.f;
           }
-          uint4 pc[4];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t wd[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              wd[u] = pack_bf16(v[g * 8 + 2 * u], v[g * 8 + 2 * u + 1]);
-              // the row sum is taken over the ROUNDED probabilities: O / l is then an exact convex combination of the values
-              l4[u] += __uint_as_float(wd[u] << 16) + __uint_as_float(wd[u] & 0xffff0000u);
-            }
-            pc[g] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+          for (int u = 0; u < 16; ++u) {
+            float x0 = fast_exp2(fmaf(a2, __uint_as_float(acc[2 * u]), -m2)), x1 = fast_exp2(fmaf(a2, __uint_as_float(acc[2 * u + 1]), -m2));
+            x0 = 2 * u < cv ? x0 : 0.f;  // ragged tail of the last key block
+            x1 = 2 * u + 1 < cv ? x1 : 0.f;
+            l4[u & 3] += x0 + x1;
+            wd[u] = pack_bf16(x0, x1);
           }
-          if (ch == 0) mbar_wait(p_empty, (pvcount & 1) ^ 1);  // the previous block's P V has consumed the tile
-          tile_store_32cols(smem_u32(sP) + (ch >> 1) * kTB, rl, ch & 1, pc);
+          tmem_st_32x32_x16(lane_base + kColP + pb * 64 + hf * 32 + cc * 16, wd);
         }
+        tmem_st_wait();
         tc_fence_before();
-        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&s_empty[sb]);
-          mbar_arrive(p_full);
+          mbar_arrive(&p_full[pb]);
         }
+        if (warp == 2 && lane == 0) tr.ev(26);
       }
-      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      rowsum[hf * 128 + rl] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      named_bar_sync(1, 256);
+      if (warp == 2 && lane == 0) tr.ev(27);
+      const float l = rowsum[rl] + rowsum[128 + rl];
       const float inv = 1.f / l;
-      // ---- epilogue: out = O / l (+ residual), bf16
+      // ---- epilogue: out = O / l (+ residual), bf16.  The accumulator is drained in 16-column pieces; the two warps of a lane
+      // quarter take alternate pieces, so both finish together (a warp that finishes early would spin at the next tile's barrier
+      // with the higher scheduling priority and slow its partner down)
       mbar_wait(o_full, ti & 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0) tr.ev(28);
       bf16* orow = p.out + b * p.o_bs + h * p.o_hs + (long long)row * p.o_ld;
-      const bf16* rrow = p.res ? p.res + b * p.r_bs + h * p.r_hs + (long long)row * p.r_ld : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.dpad; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld_32x32(lane_base + kColO + c0, acc);
+      for (int c0 = hf * 16; c0 < p.d; c0 += 32) {
+        uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+        if (rrow && row_ok) {  // (already in L2) in flight while the accumulator piece is fetched
+          r0 = ldg_v4(rrow + c0);
+          if (c0 + 8 < p.d) r1 = ldg_v4(rrow + c0 + 8);
+        }
+        uint32_t acc[16];
+        tmem_ld_32x32_x16(lane_base + kColO + c0, acc);
         tmem_ld_wait();
-        if (!row_ok) continue;
+        if (row_ok) {
+          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          uint32_t o[8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int c = c0 + g * 8;
-          if (c >= p.d) break;
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[g * 8 + e]) * inv;
-          if (c + 8 <= p.d) {
-            if (rrow) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + c);
-              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                f[2 * u] += __uint_as_float(rw[u] << 16);
-                f[2 * u + 1] += __uint_as_float(rw[u] & 0xffff0000u);
-              }
-            }
-            *reinterpret_cast<uint4*>(orow + c) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-          } else {
-            for (int e = 0; e < 8 && c + e < p.d; ++e) orow[c + e] = __float2bfloat16(f[e] + (rrow ? __bfloat162float(rrow[c + e]) : 0.f));
-          }
+          for (int u = 0; u < 8; ++u)
+            o[u] = pack_bf16(fmaf(__uint_as_float(acc[2 * u]), inv, __uint_as_float(rw[u] << 16)),
+                             fmaf(__uint_as_float(acc[2 * u + 1]), inv, __uint_as_float(rw[u] & 0xffff0000u)));
+          stg_v4(orow + c0, make_uint4(o[0], o[1], o[2], o[3]));
+          if (c0 + 8 < p.d) stg_v4(orow + c0 + 8, make_uint4(o[4], o[5], o[6], o[7]));
         }
       }
-      if (row_ok && p.lse2) p.lse2[((long long)b * p.heads + h) * p.R + row] = m2 + fast_log2(l);
+      if (hf == 0 && row_ok && p.lse2) p.lse2[((long long)b * p.heads + h) * p.R + row] = m2 + fast_log2(l);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
+      if (warp == 2 && lane == 0) tr.ev(29);
     }
   }
 
@@ -324,7 +363,6 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   }
 }
 
-
 // =================================================================================================================
 // Backward.  One kernel, two orientations of the same block computation (P never read from / written to HBM):
 //   ROWS (COLS = false): tile = 128 softmax rows i, blocks = 64 keys j
@@ -334,10 +372,12 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 //        S' = A_T B_blk^T (y x^T), dP' = C_T D_blk^T (v dO^T), statistics per BLOCK column
 //        out1[j,:] += sum_i dS'_ji B_blk[i,:]  -> dY          out2[j,:] += sum_i P'_ji D_blk[i,:]  -> dV
 // with P = 2^(a2 S - lse2), dS = alpha P (dP - dot), dot_i = dO_i . O_i (row dots of the forward product, precomputed).
-// The B_blk / D_blk tiles are loaded once and used twice: as the K-major operand of the logits products and as the
-// MN-major operand of the output products (the [64 x 64] swizzled tile is the same bytes under both readings).
+// dS (and P') overwrite the logits (dP) they were computed from in tensor memory and are the TMEM A operand of the output
+// products; the B_blk / D_blk tiles are loaded once and used twice: as the K-major operand of the logits products and as
+// the MN-major operand of the output products (the [64 x 64] swizzled tile is the same bytes under both readings).
+// The tensor-core instructions execute in issue order, so a logits buffer needs no "empty" barrier: the products that
+// overwrite it are issued after the output products that read it.
 constexpr int kThreadsB = 64 + 8 * 32;
-constexpr int kHB = 64 * 128;  // bytes of one [64 rows x 64 cols] bf16 tile
 
 struct BwdOut {
   void* ptr;        // bf16 or f32 [batch, heads, rows, d] through (bs, hs, ld)
@@ -358,26 +398,28 @@ struct BwdParams {
   int n_rows;         // softmax rows per (batch, head) (= T for ROWS, = L for COLS)
   BwdOut o1, o2;
   int tiles, nblk;
+  int ntb, nst;       // tile-operand buffers (1 or 2) and block stages (4 or 2): six 32 KB units in total
 };
 
 struct BwdSmem {
-  static constexpr int AT = 2 * kTB;      // A_T: two K blocks of [128 x 64]
-  static constexpr int CT = 2 * kTB;
-  static constexpr int STAGE = 4 * kHB;   // B_blk (two K blocks of [64 x 64]) + D_blk
-  static constexpr int NST = 3;
-  static constexpr int DS = kTB;          // dS tile [128 x 64]
-  static constexpr int PT = kTB;          // P tile (COLS only)
-  static constexpr int CS = 2 * 64 * 8;   // per-block column statistics (COLS only), double buffered
+  static constexpr int UNIT = 4 * kHB;     // 32 KB: (A_T or C_T: two K blocks of [128 x 64]) or (one stage: B_blk + D_blk)
+  static constexpr int UNITS = 6;
+  static constexpr int CS = 8 * 32 * 8;    // per-warp column statistics (COLS only)
   static constexpr int BARS = 32 * 8 + 16;
-  static constexpr int TOTAL = AT + CT + NST * STAGE + DS + PT + CS + BARS + 1024;
+  static constexpr int TOTAL = UNITS * UNIT + CS + BARS + 1024;
 };
 
-template <bool COLS>
-__device__ __forceinline__ void bwd_store_out(const BwdOut& o, uint32_t taddr, int dpad, int d, int b, int h, int row, bool row_ok) {
+__device__ __forceinline__ void bwd_store_out(const BwdOut& o, uint32_t taddr, int c_lo, int c_hi, int d, int b, int h, int row, bool row_ok) {
   const long long base = b * o.bs + h * o.hs + (long long)row * o.ld;
   const bf16* rrow = o.res ? o.res + b * o.r_bs + h * o.r_hs + (long long)(row / o.row_div) * o.r_ld : nullptr;
 #pragma unroll 1
-  for (int c0 = 0; c0 < dpad; c0 += 32) {
+  for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+    uint4 rres[4];
+    if (rrow && row_ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (c0 + g * 8 < d) rres[g] = ldg_v4(rrow + c0 + g * 8);
+    }
     uint32_t acc[32];
     tmem_ld_32x32(taddr + c0, acc);
     tmem_ld_wait();
@@ -385,26 +427,26 @@ __device__ __forceinline__ void bwd_store_out(const BwdOut& o, uint32_t taddr, i
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int c = c0 + g * 8;
-      if (c >= d) break;
-      float f[8];
+      if (c < d) {
+        float f[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[g * 8 + e]);
-      if (rrow) {
-        const uint4 rv = *reinterpret_cast<const uint4*>(rrow + c);
-        const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[g * 8 + e]);
+        if (rrow) {
+          const uint32_t rw[4] = {rres[g].x, rres[g].y, rres[g].z, rres[g].w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          f[2 * u] = fmaf(o.rscale, __uint_as_float(rw[u] << 16), f[2 * u]);
-          f[2 * u + 1] = fmaf(o.rscale, __uint_as_float(rw[u] & 0xffff0000u), f[2 * u + 1]);
+          for (int u = 0; u < 4; ++u) {
+            f[2 * u] = fmaf(o.rscale, __uint_as_float(rw[u] << 16), f[2 * u]);
+            f[2 * u + 1] = fmaf(o.rscale, __uint_as_float(rw[u] & 0xffff0000u), f[2 * u + 1]);
+          }
         }
-      }
-      if (o.is_f32) {
-        float* op = reinterpret_cast<float*>(o.ptr) + base + c;
-        *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
-        *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
-      } else {
-        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(o.ptr) + base + c) =
-            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        if (o.is_f32) {
+          float* op = reinterpret_cast<float*>(o.ptr) + base + c;
+          stg_v4(op, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+          stg_v4(op + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+        } else {
+          stg_v4(reinterpret_cast<bf16*>(o.ptr) + base + c,
+                 make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+        }
       }
     }
   }
@@ -416,29 +458,25 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sC = sA + BwdSmem::AT;
-  uint8_t* sSt = sC + BwdSmem::CT;
-  uint8_t* sDS = sSt + BwdSmem::NST * BwdSmem::STAGE;
-  uint8_t* sPT = sDS + BwdSmem::DS;
-  float2* colstat = reinterpret_cast<float2*>(sPT + BwdSmem::PT);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPT + BwdSmem::PT + BwdSmem::CS);
-  uint64_t* at_full = bars;
-  uint64_t* at_empty = bars + 1;
-  uint64_t* st_full = bars + 2;    // [3]
-  uint64_t* st_empty = bars + 5;   // [3]
-  uint64_t* s_full = bars + 8;     // [2]
-  uint64_t* s_empty = bars + 10;   // [2]
-  uint64_t* ds_full = bars + 12;
-  uint64_t* ds_empty = bars + 13;
-  uint64_t* o_full = bars + 14;
-  uint64_t* o_empty = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint8_t* sTile = smem;                               // ntb x (A_T | C_T)
+  uint8_t* sSt = smem + p.ntb * 2 * BwdSmem::UNIT;     // nst stages
+  float2* colstat = reinterpret_cast<float2*>(smem + BwdSmem::UNITS * BwdSmem::UNIT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::UNITS * BwdSmem::UNIT + BwdSmem::CS);
+  uint64_t* at_full = bars;        // [2]
+  uint64_t* at_empty = bars + 2;   // [2]
+  uint64_t* st_full = bars + 4;    // [4]
+  uint64_t* st_empty = bars + 8;   // [4]
+  uint64_t* s_full = bars + 12;    // [2]
+  uint64_t* ds_full = bars + 14;   // [2]
+  uint64_t* o_full = bars + 16;
+  uint64_t* o_empty = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.d + 63) / 64;
   const int nks = (p.d + 15) / 16;
   const int total = p.batch * p.heads * p.tiles;
+  const int ntb = p.ntb, nst = p.nst;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -448,18 +486,16 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1) {
     if (elect_one()) {
-      mbar_init(at_full, 1);
-      mbar_init(at_empty, 1);
-      for (int i = 0; i < BwdSmem::NST; ++i) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&at_full[i], 1);
+        mbar_init(&at_empty[i], 1);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&ds_full[i], 8);
+      }
+      for (int i = 0; i < 4; ++i) {
         mbar_init(&st_full[i], 1);
         mbar_init(&st_empty[i], 1);
       }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&s_full[i], 1);
-        mbar_init(&s_empty[i], 8);
-      }
-      mbar_init(ds_full, 8);
-      mbar_init(ds_empty, 1);
       mbar_init(o_full, 1);
       mbar_init(o_empty, 8);
       fence_mbar_init();
@@ -481,17 +517,19 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int tt = w % p.tiles;
         const int bh = w / p.tiles;
         const int h = bh % p.heads, b = bh / p.heads;
-        mbar_wait(at_empty, (ti & 1) ^ 1);
-        mbar_expect_tx(at_full, 2 * nkb * kTB);
+        const int tb = ti % ntb;
+        mbar_wait(&at_empty[tb], ((ti / ntb) & 1) ^ 1);
+        mbar_expect_tx(&at_full[tb], 2 * nkb * kTB);
+        uint8_t* ta = sTile + tb * 2 * BwdSmem::UNIT;
         for (int kb = 0; kb < nkb; ++kb) {
-          tma_load_4d(&tmA, at_full, sA + kb * kTB, kb * 64, tt * 128, h, b);
-          tma_load_4d(&tmC, at_full, sC + kb * kTB, kb * 64, tt * 128, h, b);
+          tma_load_4d(&tmA, &at_full[tb], ta + kb * kTB, kb * 64, tt * 128, h, b);
+          tma_load_4d(&tmC, &at_full[tb], ta + BwdSmem::UNIT + kb * kTB, kb * 64, tt * 128, h, b);
         }
         for (int blk = 0; blk < p.nblk; ++blk, ++bc) {
-          const int st = bc % BwdSmem::NST;
-          mbar_wait(&st_empty[st], ((bc / BwdSmem::NST) & 1) ^ 1);
+          const int st = bc % nst;
+          mbar_wait(&st_empty[st], ((bc / nst) & 1) ^ 1);
           mbar_expect_tx(&st_full[st], 2 * nkb * kHB);
-          uint8_t* base = sSt + st * BwdSmem::STAGE;
+          uint8_t* base = sSt + st * BwdSmem::UNIT;
           for (int kb = 0; kb < nkb; ++kb) {
             tma_load_4d(&tmB, &st_full[st], base + kb * kHB, kb * 64, blk * 64, h, b);
             tma_load_4d(&tmD, &st_full[st], base + (2 + kb) * kHB, kb * 64, blk * 64, h, b);
@@ -506,15 +544,16 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t idesc_o = make_idesc_bf16(128, p.dpad, 0, 1);
       uint32_t sdc = 0, oc = 0, ti = 0;  // blocks whose logits products / output products have been issued
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
-        mbar_wait(at_full, ti & 1);
+        const int tb = ti % ntb;
+        mbar_wait(&at_full[tb], (ti / ntb) & 1);
         tc_fence_after();
-        const uint32_t aa = smem_u32(sA), ca = smem_u32(sC);
+        const uint32_t aa = smem_u32(sTile + tb * 2 * BwdSmem::UNIT), ca = aa + BwdSmem::UNIT;
+        int issued = 0;
         auto issue_sd = [&]() {
-          const int buf = sdc & 1, st = sdc % BwdSmem::NST;
-          mbar_wait(&s_empty[buf], ((sdc >> 1) & 1) ^ 1);
-          mbar_wait(&st_full[st], (sdc / BwdSmem::NST) & 1);
+          const int buf = sdc & 1, st = sdc % nst;
+          mbar_wait(&st_full[st], (sdc / nst) & 1);
           tc_fence_after();
-          const uint32_t ba = smem_u32(sSt + st * BwdSmem::STAGE), da = ba + 2 * kHB;
+          const uint32_t ba = smem_u32(sSt + st * BwdSmem::UNIT), da = ba + 2 * kHB;
           for (int ks = 0; ks < nks; ++ks)
             umma_f16(tmem_base + buf * 128, desc_kmajor(aa + (ks >> 2) * kTB, ks & 3), desc_kmajor(ba + (ks >> 2) * kHB, ks & 3), idesc_s,
                      ks > 0 ? 1u : 0u);
@@ -523,26 +562,29 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                      ks > 0 ? 1u : 0u);
           umma_commit(&s_full[buf]);
           ++sdc;
+          if (++issued == p.nblk) umma_commit(&at_empty[tb]);  // all logits products of this tile are issued
         };
         issue_sd();
+        if (p.nblk > 1) issue_sd();
         for (int blk = 0; blk < p.nblk; ++blk) {
-          if (blk + 1 < p.nblk) issue_sd();
-          if (blk + 1 == p.nblk) umma_commit(at_empty);  // all logits products of this tile are issued
+          const int buf = oc & 1, st = oc % nst;
           if (blk == 0) mbar_wait(o_empty, (ti & 1) ^ 1);
-          mbar_wait(ds_full, oc & 1);
+          mbar_wait(&ds_full[buf], (oc >> 1) & 1);
           tc_fence_after();
-          const int st = oc % BwdSmem::NST;
-          const uint32_t ba = smem_u32(sSt + st * BwdSmem::STAGE), da = ba + 2 * kHB;
-          const uint32_t dsa = smem_u32(sDS), pta = smem_u32(sPT);
+          const uint32_t ba = smem_u32(sSt + st * BwdSmem::UNIT), da = ba + 2 * kHB;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_base + kCol1, desc_kmajor(dsa, kk), desc_mnmajor(ba, kHB, kk), idesc_o, (blk > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk)  // contraction over the block's 64 columns: 8 TMEM columns (16 bf16) of dS per step
+            umma_f16_ts(tmem_base + kCol1, tmem_base + buf * 128 + (kk >> 1) * 32 + (kk & 1) * 8, desc_mnmajor(ba, kHB, kk), idesc_o,
+                        (blk > 0 || kk > 0) ? 1u : 0u);
           if (COLS) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_base + kCol2, desc_kmajor(pta, kk), desc_mnmajor(da, kHB, kk), idesc_o, (blk > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16_ts(tmem_base + kCol2, tmem_base + buf * 128 + 64 + (kk >> 1) * 32 + (kk & 1) * 8, desc_mnmajor(da, kHB, kk), idesc_o,
+                          (blk > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&st_empty[st]);
-          umma_commit(ds_empty);
           ++oc;
+          if (blk + 2 < p.nblk) issue_sd();  // overwrites the buffer whose dS / P the products above have just read (in-order pipe)
         }
         umma_commit(o_full);
       }
@@ -551,9 +593,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ----------------------------------------------------------------------------------------------- softmax / epilogue warps
     const int q = warp & 3, hf = (warp - 2) >> 2;  // TMEM lane quarter; which 32 of the block's 64 columns
     const int rl = q * 32 + lane;
-    const int t = threadIdx.x - 64;  // 0..255
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
     const float a2 = p.alpha * kLog2e;
+    float2* cs = colstat + (warp - 2) * 32;  // this warp's private copy of its 32 columns' statistics
     uint32_t bc = 0, ti = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
       const int tt = w % p.tiles;
@@ -564,18 +606,30 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const float* lse_bh = p.lse2 + (long long)bh * p.n_rows;
       const float* dot_bh = p.dot + (long long)bh * p.n_rows;
       float r_lse = INFINITY, r_dot = 0.f;
-      if (!COLS && row_ok) {
+      float2 nxt = make_float2(INFINITY, 0.f);
+      if (COLS) {
+        const int i = hf * 32 + lane;
+        if (i < p.L) nxt = make_float2(lse_bh[i], dot_bh[i]);
+      } else if (row_ok) {
         r_lse = lse_bh[row];
         r_dot = dot_bh[row];
       }
+      {  // residual rows of the epilogue: pull them towards L2 while the tile computes
+        const BwdOut& o = (COLS && hf) ? p.o2 : p.o1;
+        if (o.res && row_ok) {
+          const bf16* rr = o.res + b * o.r_bs + h * o.r_hs + (long long)(row / o.row_div) * o.r_ld;
+          prefetch_l2(rr);
+          if (p.d > 64) prefetch_l2(rr + 64);
+        }
+      }
       for (int blk = 0; blk < p.nblk; ++blk, ++bc) {
         const int buf = bc & 1;
-        if (COLS) {  // statistics of this block's 64 softmax rows
-          if (t < 64) {
-            const int i = blk * 64 + t;
-            colstat[buf * 64 + t] = i < p.L ? make_float2(lse_bh[i], dot_bh[i]) : make_float2(INFINITY, 0.f);
-          }
-          named_bar_sync(1, 256);
+        if (COLS) {  // statistics of this block's softmax rows (this warp's 32 columns); the next block's travel meanwhile
+          __syncwarp();
+          cs[lane] = nxt;
+          __syncwarp();
+          const int i = (blk + 1) * 64 + hf * 32 + lane;
+          nxt = (blk + 1 < p.nblk && i < p.L) ? make_float2(lse_bh[i], dot_bh[i]) : make_float2(INFINITY, 0.f);
         }
         mbar_wait(&s_full[buf], (bc >> 1) & 1);
         tc_fence_after();
@@ -583,52 +637,44 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_32x32(lane_base + buf * 128 + hf * 32, sa);
         tmem_ld_32x32(lane_base + buf * 128 + 64 + hf * 32, da);
         tmem_ld_wait();
-        float pv[32], dv[32];
+        uint32_t wds[16], wpp[16];
         if (COLS) {
-          const float2* cs = colstat + buf * 64 + hf * 32;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float2 c = cs[e];
-            pv[e] = fast_exp2(fmaf(a2, __uint_as_float(sa[e]), -c.x));
-            dv[e] = p.alpha * pv[e] * (__uint_as_float(da[e]) - c.y);
+          for (int u = 0; u < 16; ++u) {
+            const float2 c0 = cs[2 * u], c1 = cs[2 * u + 1];
+            const float p0 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u]), -c0.x));
+            const float p1 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u + 1]), -c1.x));
+            wpp[u] = pack_bf16(p0, p1);
+            wds[u] = pack_bf16(p.alpha * p0 * (__uint_as_float(da[2 * u]) - c0.y), p.alpha * p1 * (__uint_as_float(da[2 * u + 1]) - c1.y));
           }
         } else {
           const int cvalid = p.L - blk * 64 - hf * 32;  // keys of this chunk that exist
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float pe = fast_exp2(fmaf(a2, __uint_as_float(sa[e]), -r_lse));
-            if (e >= cvalid) pe = 0.f;
-            dv[e] = p.alpha * pe * (__uint_as_float(da[e]) - r_dot);
+          for (int u = 0; u < 16; ++u) {
+            float p0 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u]), -r_lse));
+            float p1 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u + 1]), -r_lse));
+            if (2 * u >= cvalid) p0 = 0.f;
+            if (2 * u + 1 >= cvalid) p1 = 0.f;
+            wds[u] = pack_bf16(p.alpha * p0 * (__uint_as_float(da[2 * u]) - r_dot), p.alpha * p1 * (__uint_as_float(da[2 * u + 1]) - r_dot));
           }
         }
-        uint4 pd[4], pp[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          pd[g] = make_uint4(pack_bf16(dv[g * 8], dv[g * 8 + 1]), pack_bf16(dv[g * 8 + 2], dv[g * 8 + 3]), pack_bf16(dv[g * 8 + 4], dv[g * 8 + 5]),
-                             pack_bf16(dv[g * 8 + 6], dv[g * 8 + 7]));
-          if (COLS)
-            pp[g] = make_uint4(pack_bf16(pv[g * 8], pv[g * 8 + 1]), pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]), pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]),
-                               pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]));
-        }
-        mbar_wait(ds_empty, (bc & 1) ^ 1);  // the previous block's output products have consumed the tiles
-        tile_store_32cols(smem_u32(sDS), rl, hf, pd);
-        if (COLS) tile_store_32cols(smem_u32(sPT), rl, hf, pp);
+        // dS over the logits it came from, P' over dP (both already in registers); 16 TMEM columns = this warp's 32 bf16 columns
+        // (each warp writes only over the columns it has itself just read: [hf*32, hf*32+16) of the S / dP regions)
+        tmem_st_32x32_x16(lane_base + buf * 128 + hf * 32, wds);
+        if (COLS) tmem_st_32x32_x16(lane_base + buf * 128 + 64 + hf * 32, wpp);
+        tmem_st_wait();
         tc_fence_before();
-        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&s_empty[buf]);
-          mbar_arrive(ds_full);
-        }
+        if (lane == 0) mbar_arrive(&ds_full[buf]);
       }
-      // ---- epilogue: each of the two warps sharing a lane quarter stores one of the outputs (ROWS: the two halves of out1's columns)
+      // ---- epilogue.  COLS: the two warps of a lane quarter store one output each; ROWS: one half of out1's columns each
       mbar_wait(o_full, ti & 1);
       tc_fence_after();
       if (COLS) {
-        if (hf == 0) bwd_store_out<COLS>(p.o1, lane_base + kCol1, p.dpad, p.d, b, h, row, row_ok);
-        else bwd_store_out<COLS>(p.o2, lane_base + kCol2, p.dpad, p.d, b, h, row, row_ok);
-      } else if (hf == 0) {
-        bwd_store_out<COLS>(p.o1, lane_base + kCol1, p.dpad, p.d, b, h, row, row_ok);
+        if (hf == 0) bwd_store_out(p.o1, lane_base + kCol1, 0, p.dpad, p.d, b, h, row, row_ok);
+        else bwd_store_out(p.o2, lane_base + kCol2, 0, p.dpad, p.d, b, h, row, row_ok);
+      } else {
+        bwd_store_out(p.o1, lane_base + kCol1, hf * 64, min(p.dpad, hf * 64 + 64), p.d, b, h, row, row_ok);
       }
       tc_fence_before();
       __syncwarp();
@@ -724,6 +770,9 @@ extern "C" int mirror_flash_bwd(const mirror_flash_bwd_args* a, mirror_stream_t 
   }
   p.tiles = (a->T + 127) / 128;
   p.nblk = (a->L + 63) / 64;
+  // six 32 KB units of shared memory: short tiles (few blocks) double-buffer the tile operands, long tiles deepen the block ring
+  p.ntb = p.nblk <= 12 ? 2 : 1;
+  p.nst = p.nblk <= 12 ? 2 : 4;
   const long long total = (long long)p.batch * p.heads * p.tiles;
   const int grid = (int)(total < num_sms() ? total : num_sms());
   if (a->cols) {
@@ -736,5 +785,14 @@ extern "C" int mirror_flash_bwd(const mirror_flash_bwd_args* a, mirror_stream_t 
     flash_bwd_kernel<false><<<grid, kThreadsB, BwdSmem::TOTAL, STREAM>>>(tmA, tmB, tmC, tmD, p);
   }
   MB_LAUNCH_CHECK();
+  return 0;
+}
+
+// debug hook (measurement only): install / remove the event-trace buffer read by tools/flash_trace.py
+extern "C" int mirror_debug_flash_trace(void* buf, int64_t capacity) {
+  unsigned long long* pbuf = reinterpret_cast<unsigned long long*>(buf);
+  unsigned long long cap = (unsigned long long)capacity;
+  MB_CUDA(cudaMemcpyToSymbol(g_trace, &pbuf, sizeof(pbuf)));
+  MB_CUDA(cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap)));
   return 0;
 }

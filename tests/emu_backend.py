@@ -412,15 +412,15 @@ class Emu:
 
     # ---------------------------------------------------------------- losses
     def flash_softmax_pv(self, x, y, v, alpha, out, res=None, want_lse=True):
-        """unnormalised bf16 probabilities 2^(a2 (S - max)), row sum over the ROUNDED values, O / l in fp32 (the kernel's order)"""
+        """unnormalised probabilities 2^(a2 (S - max)): fp32 row sum, bf16 operands of the value product, O / l in fp32 (the kernel's order)"""
         for t in (x, y, v, out) + ((res,) if res is not None else ()):
             assert t.dtype == BF16 and t.stride(3) == 1 and all(s % 8 == 0 for s in t.stride()[:3])
         a2 = alpha * 1.4426950408889634
         s_ = torch.matmul(x.float(), y.float().transpose(-1, -2))
         mx = s_.max(-1, keepdim=True).values
-        p = torch.exp2(a2 * (s_ - mx)).to(BF16).float()
+        p = torch.exp2(a2 * (s_ - mx))
         l = p.sum(-1, keepdim=True)
-        o = torch.matmul(p, v.float()) / l
+        o = torch.matmul(p.to(BF16).float(), v.float()) / l
         if res is not None:
             o = o + res.float()
         out.copy_(o.to(BF16))

@@ -33,7 +33,10 @@ runs = {
     "bwd a3 cols (dk, dv)": lambda: K.flash_bwd(k, ql, v, dkv, alpha, lse3, dot3, True, (hv(dqkv, E), hv(dlm16, E), seg, 1.0 / seg), (hv(dqkv, 2 * E), hv(dvc, 0), 1, 1.0)),
 }
 elems = B * h * n * m
+only = sys.argv[2] if len(sys.argv) > 2 else ""
 for name, fn in runs.items():
+    if only not in name:
+        continue
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
