@@ -33,6 +33,10 @@ const char* mirror_last_error(void);
 int mirror_abi_version(void);
 /* 1 when the current device is compute capability 10.x (tcgen05/TMEM present). */
 int mirror_device_supported(void);
+/* Graph-safe dropout: while a DEVICE counter is installed (NULL = off, the default), every dropout launch (GEMM epilogues,
+ * mirror_act_fwd / mirror_act_bwd) mixes *device_counter into its seed at run time, so a replayed CUDA graph draws fresh
+ * masks when the owner bumps the counter between replays (mirror_b200/step.py). */
+int mirror_set_dropout_epoch(const void* device_counter);
 
 /* ------------------------------------------------------------------------------------------------
  * Batched GEMM on 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed, persistent).
@@ -331,6 +335,23 @@ int mirror_sym_kl_bwd(const float* scores, int32_t B, int32_t P, const float* go
                       mirror_stream_t stream);
 /* total = sum_i w_i*term_i, losses/mirror_loss.py:121-127 (weights are host floats) */
 int mirror_loss_combine(const float* terms5, const float* weights5_host, float* total, mirror_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step tail (optim.cu) over FLAT fp32 buffers; every per-step scalar is read from device memory (graph-replayable).
+ * Replaces optimizer.step() of train_mirror.py:1230 (opt: adam; torch.optim.Adam semantics, or AdamW with decoupled = 1),
+ * clip_grad mode "norm" (:1222-1229) and the logit_scale clamp (:1254-1256).
+ * ---------------------------------------------------------------------------------------------- */
+/* p,g,m,v: [n] f32, 16-byte aligned.  *lr, *step (the 1-based update count, as float) and *grad_scale (may be NULL) are device
+ * scalars: g is multiplied by *grad_scale first (the clip coefficient). */
+int mirror_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, float beta1, float beta2,
+                     float eps, float weight_decay, int32_t decoupled, const float* step, const float* grad_scale,
+                     mirror_stream_t stream);
+/* *out = sum g[i]^2 */
+int mirror_grad_sumsq(const float* g, int64_t n, float* out, mirror_stream_t stream);
+/* one launch for the scalar bookkeeping: *coef = min(1, max_norm / (sqrt(*sumsq) + 1e-6)) (1 when sumsq is NULL or
+ * max_norm <= 0), *step += 1, *clamp_param = clamp(*clamp_param, lo, hi); each pointer may be NULL */
+int mirror_tail_scalars(const float* sumsq, float max_norm, float* coef, float* step, float* clamp_param, float lo, float hi,
+                        mirror_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,8 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static const unsigned long long* g_drop_epoch = nullptr;  // process-wide (one process per GPU), set around graph capture
+const unsigned long long* drop_epoch_ptr() { return g_drop_epoch; }
 }  // namespace mb
 
 extern "C" const char* mirror_last_error(void) { return mb::g_err; }
@@ -21,4 +23,8 @@ extern "C" int mirror_device_supported(void) {
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
   return major == 10;
+}
+extern "C" int mirror_set_dropout_epoch(const void* device_counter) {
+  mb::g_drop_epoch = reinterpret_cast<const unsigned long long*>(device_counter);
+  return 0;
 }

@@ -83,6 +83,14 @@ __device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t idx) {
   return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
 
+// Graph-safe dropout: a CUDA graph bakes the by-value seed of every captured launch, so a replayed step would repeat its
+// masks.  mirror_set_dropout_epoch installs a DEVICE counter; while it is set, every dropout launch mixes *epoch into its
+// seed at run time (the owner of the counter bumps it once per replay).  NULL (the default) = seeds are used as passed.
+const unsigned long long* drop_epoch_ptr();
+__device__ __forceinline__ uint64_t epoch_seed(uint64_t seed, const unsigned long long* epoch) {
+  return epoch ? seed ^ (*epoch * 0x9E3779B97F4A7C15ull) : seed;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
@@ -135,6 +143,7 @@ struct Epi {
   int act;
   float drop_p, drop_scale;
   uint64_t drop_seed;
+  const unsigned long long* drop_epoch;  // optional device counter mixed into drop_seed (graph replay), see epoch_seed
   const void* res;
   const bf16* res2;  // second residual, bf16, same element strides as res
   int res_is_bf16;
@@ -164,7 +173,7 @@ __device__ __forceinline__ void epi_store_scalar(const Epi& e, float acc, int b1
   else if (e.act == MIRROR_ACT_GELU) v = gelu_erf(v);
   if (e.drop_p > 0.f) {
     const uint64_t idx = ((uint64_t)(b2 * e.batch1 + b1) * e.M + row) * e.N + col;
-    v = hash_u01(e.drop_seed, idx) >= e.drop_p ? v * e.drop_scale : 0.f;
+    v = hash_u01(epoch_seed(e.drop_seed, e.drop_epoch), idx) >= e.drop_p ? v * e.drop_scale : 0.f;
   }
   if (e.res) {
     const long long off = b2 * e.r_bs2 + b1 * e.r_bs1 + (long long)(row / e.res_row_div) * e.ldr + col;

@@ -113,7 +113,8 @@ __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ s
 
 // out = dropout(act(pre)) as bf16 (and optionally f32)
 __global__ void act_fwd_kernel(const float* __restrict__ pre, long long n, int act, float drop_p, float drop_scale,
-                               uint64_t seed, bf16* __restrict__ o16, float* __restrict__ o32) {
+                               uint64_t seed, const unsigned long long* epoch, bf16* __restrict__ o16, float* __restrict__ o32) {
+  seed = epoch_seed(seed, epoch);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = pre[i];
     if (act == MIRROR_ACT_RELU) v = fmaxf(v, 0.f);
@@ -126,8 +127,9 @@ __global__ void act_fwd_kernel(const float* __restrict__ pre, long long n, int a
 // dx = dy * dropmask * act'(pre) on [B,T,C] views with independent batch / row strides (padded layouts).
 __global__ void act_bwd_kernel(const float* __restrict__ dy, long long bs_dy, long long ld_dy, const float* __restrict__ pre,
                                long long bs_pre, long long ld_pre, int B, int T, int C, int act, float drop_p, float drop_scale,
-                               uint64_t seed, bf16* __restrict__ o16, long long bs16, long long ld16, float* __restrict__ o32,
-                               long long bs32, long long ld32) {
+                               uint64_t seed, const unsigned long long* epoch, bf16* __restrict__ o16, long long bs16, long long ld16,
+                               float* __restrict__ o32, long long bs32, long long ld32) {
+  seed = epoch_seed(seed, epoch);
   const long long total = (long long)B * T * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -151,7 +153,9 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, long long bs_dy, lo
 __global__ void __launch_bounds__(256)
 act_bwd_rows_kernel(const float* __restrict__ dy, long long bs_dy, long long ld_dy, const float* __restrict__ pre, long long bs_pre,
                     long long ld_pre, int B, int T, int C, int act, float drop_p, float drop_scale, uint64_t seed,
-                    bf16* __restrict__ o16, long long bs16, long long ld16, float* __restrict__ o32, long long bs32, long long ld32) {
+                    const unsigned long long* epoch, bf16* __restrict__ o16, long long bs16, long long ld16, float* __restrict__ o32,
+                    long long bs32, long long ld32) {
+  seed = epoch_seed(seed, epoch);
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const long long rows = (long long)B * T;
   for (long long r = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
@@ -492,7 +496,7 @@ extern "C" int mirror_token_fanout_bwd(const float* d_full, const float* d_cls, 
 extern "C" int mirror_act_fwd(const float* pre, int64_t n, int32_t act, float drop_p, uint64_t seed, void* out_bf16,
                               float* out_f32, mirror_stream_t stream) {
   MB_CHECK_ARG(pre && n > 0 && (out_bf16 || out_f32) && drop_p >= 0.f && drop_p < 1.f, "act_fwd: bad args");
-  act_fwd_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(pre, n, act, drop_p, 1.f / (1.f - drop_p), seed,
+  act_fwd_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(pre, n, act, drop_p, 1.f / (1.f - drop_p), seed, drop_epoch_ptr(),
                                                        reinterpret_cast<bf16*>(out_bf16), out_f32);
   MB_LAUNCH_CHECK();
   return 0;
@@ -509,12 +513,12 @@ extern "C" int mirror_act_bwd(const float* dy, int64_t bs_dy, int64_t ld_dy, con
   if (C % 4 == 0 && C >= 128 && al(dy, bs_dy, ld_dy, 4) && al(pre, bs_pre, ld_pre, 4) && al(out_bf16, bs16, ld16, 2) &&
       al(out_f32, bs32, ld32, 4)) {
     act_bwd_rows_kernel<<<grid_for((long long)B * T, 8), 256, 0, STREAM>>>(
-        dy, bs_dy, ld_dy, pre, bs_pre, ld_pre, B, T, C, act, drop_p, 1.f / (1.f - drop_p), seed, reinterpret_cast<bf16*>(out_bf16),
-        bs16, ld16, out_f32, bs32, ld32);
+        dy, bs_dy, ld_dy, pre, bs_pre, ld_pre, B, T, C, act, drop_p, 1.f / (1.f - drop_p), seed, drop_epoch_ptr(),
+        reinterpret_cast<bf16*>(out_bf16), bs16, ld16, out_f32, bs32, ld32);
   } else {
     act_bwd_kernel<<<grid_for((long long)B * T * C, 256), 256, 0, STREAM>>>(
-        dy, bs_dy, ld_dy, pre, bs_pre, ld_pre, B, T, C, act, drop_p, 1.f / (1.f - drop_p), seed, reinterpret_cast<bf16*>(out_bf16),
-        bs16, ld16, out_f32, bs32, ld32);
+        dy, bs_dy, ld_dy, pre, bs_pre, ld_pre, B, T, C, act, drop_p, 1.f / (1.f - drop_p), seed, drop_epoch_ptr(),
+        reinterpret_cast<bf16*>(out_bf16), bs16, ld16, out_f32, bs32, ld32);
   }
   MB_LAUNCH_CHECK();
   return 0;

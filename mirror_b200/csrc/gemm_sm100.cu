@@ -191,8 +191,9 @@ __device__ __forceinline__ void epilogue_chunk_vec(const Epi& e, uint32_t taddr,
   }
   if (e.drop_p > 0.f) {
     const uint64_t base = ((uint64_t)(b2 * e.batch1 + b1) * e.M + row) * e.N + col0;
+    const uint64_t seed = epoch_seed(e.drop_seed, e.drop_epoch);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = hash_u01(e.drop_seed, base + j) >= e.drop_p ? v[j] * e.drop_scale : 0.f;
+    for (int j = 0; j < 32; ++j) v[j] = hash_u01(seed, base + j) >= e.drop_p ? v[j] * e.drop_scale : 0.f;
   }
   if (e.res && row_ok) {
     if (e.res_is_bf16) {
@@ -1179,7 +1180,7 @@ int fill_epi(const mirror_gemm_args* g, Epi* e) {
                "gemm: split_k supports only alpha and an fp32 accumulate target");
   e->M = g->M; e->N = g->N; e->batch1 = g->batch1;
   e->alpha = g->alpha; e->diag = g->diag; e->bias = g->bias; e->act = g->act;
-  e->drop_p = g->drop_p; e->drop_scale = 1.f / (1.f - g->drop_p); e->drop_seed = g->drop_seed;
+  e->drop_p = g->drop_p; e->drop_scale = 1.f / (1.f - g->drop_p); e->drop_seed = g->drop_seed; e->drop_epoch = drop_epoch_ptr();
   e->res = g->res; e->res_is_bf16 = g->res_is_bf16; e->gamma = g->gamma;
   e->res2 = reinterpret_cast<const bf16*>(g->res2); e->gamma2 = g->gamma2;
   e->res_row_div = g->res_row_div > 1 ? g->res_row_div : 1;

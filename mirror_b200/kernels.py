@@ -685,3 +685,36 @@ def loss_combine(terms5, weights):
     w = (ctypes.c_float * 5)(*weights)
     _call("mirror_loss_combine", _p(_contig(terms5), F32), ctypes.cast(w, ctypes.c_void_p), _p(total))
     return total
+
+
+# ---- step tail (csrc/optim.cu) and graph-safe dropout -------------------------------------------------------------------
+def set_dropout_epoch(counter):
+    """Install (or, with None, remove) the int64 DEVICE counter that every dropout launch mixes into its seed (graph replay)."""
+    if _TEST_BACKEND is not None:
+        return _TEST_BACKEND.set_dropout_epoch(counter)
+    if counter is not None:
+        _cuda(counter, torch.int64)
+    _lib.check(_lib.fn("mirror_set_dropout_epoch")(counter.data_ptr() if counter is not None else None), "set_dropout_epoch")
+
+
+@_op
+def adam_step_(p, g, m, v, lr, beta1, beta2, eps, weight_decay, decoupled, step, grad_scale=None):
+    """In-place Adam / AdamW update of the flat fp32 buffers; lr, step and grad_scale are 0-d / 1-element device tensors."""
+    n = p.numel()
+    assert g.numel() == n and m.numel() == n and v.numel() == n
+    _call("mirror_adam_step", _p(_contig(p), F32), _p(_contig(g), F32), _p(_contig(m), F32), _p(_contig(v), F32), n, _p(lr, F32), beta1, beta2,
+          eps, weight_decay, int(decoupled), _p(step, F32), _p(grad_scale, F32) if grad_scale is not None else None)
+
+
+@_op
+def grad_sumsq(g):
+    out = torch.empty((), device=g.device, dtype=F32)
+    _call("mirror_grad_sumsq", _p(_contig(g), F32), g.numel(), _p(out), launches=1)
+    return out
+
+
+@_op
+def tail_scalars_(sumsq=None, max_norm=0.0, coef=None, step=None, clamp_param=None, lo=0.0, hi=0.0):
+    """One launch: coef <- clip coefficient, step += 1, clamp_param <- clamp(clamp_param, lo, hi) (each optional)."""
+    _call("mirror_tail_scalars", _p(sumsq, F32) if sumsq is not None else None, max_norm, _p(coef, F32) if coef is not None else None,
+          _p(step, F32) if step is not None else None, _p(clamp_param, F32) if clamp_param is not None else None, lo, hi)

@@ -16,8 +16,9 @@ __all__ = ["InfoNCE"]
 
 
 class InfoNCE(nn.Module):
-    def __init__(self, temperature=0.1, reduction="mean", negative_mode="unpaired", symmetric=False):
+    def __init__(self, temperature=0.1, reduction="mean", negative_mode="unpaired", symmetric=False, global_negatives=False, group=None):
         super().__init__()
+        self.global_negatives, self.group = global_negatives, group  # extension, default off (see losses/mirror_loss.ClipLoss)
         self.temperature = temperature
         self.reduction = reduction
         self.negative_mode = negative_mode
@@ -55,4 +56,6 @@ class InfoNCE(nn.Module):
         q = ops.l2_normalize(query.float(), 1e-12)  # F.normalize default eps
         k = ops.l2_normalize(positive_key.float(), 1e-12)
         scale = torch.full((), 1.0 / temperature, device=query.device, dtype=torch.float32)
-        return ops.clip_loss(q, k, scale, 0.5, 0.5, reduction) if symmetric else ops.clip_loss(q, k, scale, 1.0, 0.0, reduction)
+        from .mirror_loss import _negatives_group
+        group = _negatives_group(getattr(self, "global_negatives", False), getattr(self, "group", None))
+        return ops.clip_loss(q, k, scale, 0.5, 0.5, reduction, group) if symmetric else ops.clip_loss(q, k, scale, 1.0, 0.0, reduction, group)

@@ -10,25 +10,42 @@ from torch import nn
 from .. import ops
 
 
+def _negatives_group(global_negatives, group):
+    """None (rank-local negatives, the reference's behaviour under DDP: SURVEY.md fact 5) or the process group whose ranks
+    pool their embeddings as negatives."""
+    if not global_negatives:
+        return None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    group = group if group is not None else dist.group.WORLD
+    return group if dist.get_world_size(group) > 1 else None
+
+
 class ClipLoss(nn.Module):
-    def __init__(self, cache_labels=False):
+    """``global_negatives`` / ``group`` are extensions (default off = reference behaviour): the contrastive term is taken
+    against the embeddings of every rank (embedding + log-sum-exp all-gathers, see ops.ClipLossFn)."""
+
+    def __init__(self, cache_labels=False, global_negatives=False, group=None):
         super().__init__()
         self.cache_labels = cache_labels  # labels are implicit (the diagonal) in the fused kernels
         self.prev_num_logits = 0
         self.labels = {}
+        self.global_negatives, self.group = global_negatives, group
 
     def forward(self, wsi_features, rna_features, logit_scale, output_dict=False):
         if not torch.is_tensor(logit_scale):
             logit_scale = torch.tensor(float(logit_scale), device=wsi_features.device)
-        loss = ops.clip_loss(wsi_features, rna_features, logit_scale.float(), 0.5, 0.5)
+        loss = ops.clip_loss(wsi_features, rna_features, logit_scale.float(), 0.5, 0.5,
+                             group=_negatives_group(self.global_negatives, self.group))
         return {"contrastive_loss": loss} if output_dict else loss
 
 
 class MIRRORLoss(nn.Module):
     def __init__(self, clip_loss_cache_labels=True, alignment_loss_weight=0.5, wsi_retention_loss_weight=0.1,
-                 rna_retention_loss_weight=0.1, style_loss_weight=0.1, cluster_loss_weight=0.2):
+                 rna_retention_loss_weight=0.1, style_loss_weight=0.1, cluster_loss_weight=0.2, global_negatives=False, group=None):
         super().__init__()
-        self.clip_loss = ClipLoss(cache_labels=clip_loss_cache_labels)
+        self.clip_loss = ClipLoss(cache_labels=clip_loss_cache_labels, global_negatives=global_negatives, group=group)
         self.alignment_loss_weight = alignment_loss_weight
         self.wsi_retention_loss_weight = wsi_retention_loss_weight
         self.rna_retention_loss_weight = rna_retention_loss_weight

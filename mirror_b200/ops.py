@@ -803,6 +803,16 @@ def contrastive_operands(w, r, precise):
     return K.cast_bf16(w, Dp), K.cast_bf16(r, Dp), Dp
 
 
+def _gather_rows(t, group):
+    """all-gather of a [B_local, ...] tensor along dim 0 -> [world * B_local, ...] (rank-major).  No gradient flows through it:
+    ClipLossFn's backward forms the exact gradient of the local rows from the gathered statistics instead."""
+    import torch.distributed as dist
+    t = t.contiguous()
+    out = torch.empty(dist.get_world_size(group) * t.shape[0], *t.shape[1:], device=t.device, dtype=t.dtype)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out
+
+
 class ClipLossFn(Function):
     """Contrastive loss over logits = scale * W R^T: ClipLoss (losses/mirror_loss.py:37-52, w_row=w_col=0.5) and
     InfoNCE's implicit-negative branch (losses/info_nce.py:144-164), reduction 'mean' | 'sum' | 'none'.
@@ -810,46 +820,75 @@ class ClipLossFn(Function):
     log-sum-exp of W R^T and of R W^T) and two gradient passes that recompute the logits tile by tile in TMEM and feed
     G = dLoss/dlogits straight into a second tcgen05.mma (dW = G R, dR = G^T W).
     Up to PRECISE_ROWS samples the operands are split-3 bf16 (fp32-grade products): the temperature multiplies every
-    rounding error of the similarities by ~14-100."""
+    rounding error of the similarities by ~14-100.
+
+    ``group`` (a torch.distributed process group; None = the reference's rank-local negatives): global
+    negatives.  The embeddings of all ranks are all-gathered; this rank evaluates its B_local rows of W_loc R_glob^T and of
+    R_loc W_glob^T (its rows and its columns of the global logits matrix), returns the mean over ITS samples, and a second,
+    tiny all-gather of the two log-sum-exp vectors lets its backward form the exact gradient of the global-batch loss with
+    respect to its local embeddings -- contributions of the other ranks' loss terms included -- so no gradient is sent back
+    through the gather.  The gradient is that of SUM over ranks of the per-rank losses (every rank receives the same upstream
+    gradient), which DDP's averaging turns into the gradient of their mean = the single-process global-batch loss."""
 
     @staticmethod
     @_cfwd
-    def forward(ctx, w, r, scale, w_row, w_col, reduction="mean"):
+    def forward(ctx, w, r, scale, w_row, w_col, reduction="mean", group=None):
         B, E = w.shape
         w, r = w.contiguous(), r.contiguous()
-        precise = B <= PRECISE_ROWS
-        w16, r16, Dp = contrastive_operands(w, r, precise)
+        rank = 0
+        wg, rg = w, r
+        if group is not None:
+            import torch.distributed as dist
+            rank = dist.get_rank(group)
+            wg, rg = _gather_rows(w, group), _gather_rows(r, group)
+        Bg = wg.shape[0]
+        diag0 = rank * B
+        precise = Bg <= PRECISE_ROWS
+        w16, r16, Dp = contrastive_operands(wg, rg, precise)   # operands of the whole (global) batch; local rows are a slice
+        w16l, r16l = w16[diag0:diag0 + B], r16[diag0:diag0 + B]
         scale = scale.reshape(()).contiguous()
-        lse_r, diag = K.contrastive_stats(w16, r16, scale)
-        lse_c = K.contrastive_stats(r16, w16, scale)[0] if w_col != 0.0 else None
+        lse_r, diag = K.contrastive_stats(w16l, r16, scale, diag0)
+        lse_c = K.contrastive_stats(r16l, w16, scale, diag0)[0] if w_col != 0.0 else None
         mult = 1.0 / B if reduction == "mean" else 1.0
         loss = K.contrastive_loss(lse_r, lse_c, diag, w_row, w_col, mult, reduction == "none")
-        ctx.save_for_backward(w16, r16, scale, lse_r, lse_c)
-        ctx.meta = (B, E, Dp, w_row, w_col, precise, mult)
+        lse_rg, lse_cg = lse_r, lse_c
+        if group is not None:  # statistics of every row / column of the global logits, for the backward of the local rows
+            lse_rg = _gather_rows(lse_r, group)
+            lse_cg = _gather_rows(lse_c, group) if lse_c is not None else None
+        ctx.save_for_backward(w16, r16, scale, lse_rg, lse_cg)
+        ctx.meta = (B, Bg, diag0, E, Dp, w_row, w_col, precise, mult)
         return loss
 
     @staticmethod
     @once_differentiable
     @_cbwd
     def backward(ctx, gout):
-        w16, r16, scale, lse_r, lse_c = ctx.saved_tensors
-        B, E, Dp, w_row, w_col, precise, mult = ctx.meta
+        w16, r16, scale, lse_rg, lse_cg = ctx.saved_tensors
+        B, Bg, diag0, E, Dp, w_row, w_col, precise, mult = ctx.meta
+        w16l, r16l = w16[diag0:diag0 + B], r16[diag0:diag0 + B]
         dscale = torch.zeros((), device=gout.device, dtype=F32)
         a_r, a_c = K.contrastive_coef(gout.contiguous(), B, w_row, w_col, mult)
-        if lse_c is None:  # one-sided: the column terms vanish (a_c = None), the column LSE is never read
-            lse_c = lse_r
+        if lse_cg is None:  # one-sided: the column terms vanish (a_c = None), the column LSE is never read
+            lse_cg = lse_rg
+        lse_r, lse_c = lse_rg[diag0:diag0 + B], lse_cg[diag0:diag0 + B]
+        a_rg, a_cg = a_r, a_c
+        if Bg != B:  # coefficients of the other ranks' samples: the same upstream gradient on every rank (see the class docstring)
+            if gout.numel() != 1:
+                raise NotImplementedError("global negatives need a scalar reduction ('mean' or 'sum')")
+            a_rg = a_r[:1].expand(Bg).contiguous()
+            a_cg = a_c[:1].expand(Bg).contiguous() if a_c is not None else None
         # w3 = hi|lo|hi (lo block at Dp), r3 = hi|hi|lo (lo block at 2 Dp)
-        dw = K.contrastive_grad(w16, r16, Dp, E, precise, 2 * Dp, scale, 0, lse_r, lse_c, a_r, a_c, dscale)
+        dw = K.contrastive_grad(w16l, r16, Dp, E, precise, 2 * Dp, scale, diag0, lse_r, lse_cg, a_r, a_cg, dscale)
         if a_c is None:
             a_c0 = torch.zeros_like(a_r)
-            dr = K.contrastive_grad(r16, w16, Dp, E, precise, Dp, scale, 0, lse_c, lse_r, a_c0, a_r, None)
+            dr = K.contrastive_grad(r16l, w16, Dp, E, precise, Dp, scale, diag0, lse_c, lse_rg, a_c0, a_rg, None)
         else:
-            dr = K.contrastive_grad(r16, w16, Dp, E, precise, Dp, scale, 0, lse_c, lse_r, a_c, a_r, dscale)
-        return dw, dr, dscale, None, None, None
+            dr = K.contrastive_grad(r16l, w16, Dp, E, precise, Dp, scale, diag0, lse_c, lse_rg, a_c, a_rg, dscale)
+        return dw, dr, dscale, None, None, None, None
 
 
-def clip_loss(w, r, scale, w_row=0.5, w_col=0.5, reduction="mean"):
-    return ClipLossFn.apply(w, r, scale, w_row, w_col, reduction)
+def clip_loss(w, r, scale, w_row=0.5, w_col=0.5, reduction="mean", group=None):
+    return ClipLossFn.apply(w, r, scale, w_row, w_col, reduction, group)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -527,3 +527,30 @@ class Emu:
 
     def loss_combine(self, terms5, weights):
         return (terms5 * torch.tensor(weights, dtype=F32)).sum()
+
+    # ---- step tail (csrc/optim.cu)
+    def set_dropout_epoch(self, counter):
+        self.drop_epoch = counter  # the emulated dropout ignores it (graph replay does not exist on the CPU)
+
+    def adam_step_(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, decoupled, step, grad_scale=None):
+        lr, t = float(lr), float(step)
+        gg = g * (float(grad_scale) if grad_scale is not None else 1.0)
+        if weight_decay != 0.0:
+            if decoupled:
+                p.mul_(1.0 - lr * weight_decay)
+            else:
+                gg = gg + weight_decay * p
+        m.mul_(beta1).add_(gg, alpha=1 - beta1)
+        v.mul_(beta2).addcmul_(gg, gg, value=1 - beta2)
+        p.sub_((lr / (1 - beta1 ** t)) * m / (v.sqrt() / (1 - beta2 ** t) ** 0.5 + eps))
+
+    def grad_sumsq(self, g):
+        return (g.double() ** 2).sum().float()
+
+    def tail_scalars_(self, sumsq=None, max_norm=0.0, coef=None, step=None, clamp_param=None, lo=0.0, hi=0.0):
+        if coef is not None:
+            coef.fill_(min(1.0, max_norm / (float(sumsq) ** 0.5 + 1e-6)) if sumsq is not None and max_norm > 0 else 1.0)
+        if step is not None:
+            step.add_(1.0)
+        if clamp_param is not None:
+            clamp_param.clamp_(lo, hi)

@@ -74,3 +74,135 @@ def test_ddp_two_ranks_average_local_gradients():
         want = 0.5 * (g0[k] + g1[k])
         err = float((torch.from_numpy(got[k]) - want).norm() / (want.norm() + 1e-12))
         assert err < 1e-5, (k, err)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Global negatives (extension): embedding all-gather + log-sum-exp all-gather, no gradient reduce-scatter.
+# Oracle for the W-rank run = the reference algorithm run SINGLE-PROCESS on the concatenated global batch.
+def _worker_global(rank, world, port, q):
+    for p in (HERE, os.path.dirname(HERE)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import emu_backend
+    import parity
+    from mirror_b200.losses import MIRRORLoss
+    emu_backend.use()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg, sd, wsi, rna, noise = _problem(rank)
+    model = parity.build_product(cfg, sd).eval()
+    ddp = torch.nn.parallel.DistributedDataParallel(model)
+    out = ddp(wsi, rna, 0.75, 0.75, noise=noise)
+    losses = MIRRORLoss(global_negatives=True)(*out)
+    losses[0].backward()
+    ls = torch.stack([l.detach() for l in losses])
+    dist.all_reduce(ls)  # mean over ranks of the per-rank losses = the global-batch loss
+    ls /= world
+    if rank == 0:
+        q.put(({n: p.grad.clone().numpy() for n, p in model.named_parameters()}, ls.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_global_negatives_two_ranks_equal_single_process_global_batch():
+    import parity
+    from oracle import mirror_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_global, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, got_losses = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    # single-process oracle on the concatenated batch (rank-major), same weights, same per-slide inputs and noise
+    parts = [_problem(r) for r in range(2)]
+    cfg, sd = parts[0][0], parts[0][1]
+    wsi = torch.cat([p[2] for p in parts])
+    rna = torch.cat([p[3] for p in parts])
+    noise = {k: torch.cat([p[4][k] for p in parts]) for k in parts[0][4]}
+    _, o_loss, o_g = parity.run_oracle(sd, wsi, rna, noise)
+    # 2e-3 on this miniature configuration (E=192, 4 slides): the single-process product is 1.7e-3 off the fp32 oracle in the
+    # align term here (bf16 encoder, temperature 1/0.07); the exchange itself is checked to 1e-5 by the test below
+    for name, a, b in zip(parity.LOSS_NAMES, got_losses, o_loss):
+        assert abs(float(a) - float(b)) <= 2e-3 * abs(float(b)), (name, float(a), float(b))
+    keys = sorted(o_g)
+    gp = torch.cat([torch.from_numpy(got[k]).flatten() for k in keys])
+    go = torch.cat([o_g[k].flatten() for k in keys])
+    assert parity.rel(gp, go) <= 1e-2, parity.rel(gp, go)
+    # the contrastive term is what the exchange changes: check the parameters it alone reaches
+    for k in ("logit_scale", "wsi_encoder.alignment_head.weight", "rna_encoder.alignment_head.weight"):
+        assert parity.rel(torch.from_numpy(got[k]), o_g[k]) <= 1e-2, (k, parity.rel(torch.from_numpy(got[k]), o_g[k]))
+
+
+def _worker_clip(rank, world, port, q):
+    for p in (HERE, os.path.dirname(HERE)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import emu_backend
+    from mirror_b200 import ops
+    emu_backend.use()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = {}
+    for sym in (True, False):
+        w, r, s_ = _clip_problem()
+        B = w.shape[0] // world
+        wl = w[rank * B:(rank + 1) * B].clone().requires_grad_(True)
+        rl = r[rank * B:(rank + 1) * B].clone().requires_grad_(True)
+        s_ = s_.clone().requires_grad_(True)
+        loss = ops.clip_loss(wl, rl, s_, 0.5 if sym else 1.0, 0.5 if sym else 0.0, "mean", dist.group.WORLD)
+        (0.37 * loss).backward()
+        pack = torch.cat([loss.detach().reshape(1), s_.grad.reshape(1), wl.grad.flatten(), rl.grad.flatten()])
+        outs = [torch.empty_like(pack) for _ in range(world)]
+        dist.all_gather(outs, pack)
+        res[sym] = [o.numpy() for o in outs]
+    if rank == 0:
+        q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _clip_problem():
+    g = torch.Generator().manual_seed(77)
+    w = torch.nn.functional.normalize(torch.randn(12, 40, generator=g), dim=-1)
+    r = torch.nn.functional.normalize(torch.randn(12, 40, generator=g), dim=-1)
+    return w, r, torch.tensor(1 / 0.07)
+
+
+def test_global_negative_exchange_is_exact():
+    """ops.ClipLossFn with a process group (3 ranks x 4 samples) against the SAME function on the concatenated batch in one
+    process: mean of the per-rank losses, DDP-style averaged d(scale), and the local embedding gradients (which include the
+    other ranks' loss terms) must agree to rounding -- with no gradient sent back through the gather."""
+    import emu_backend
+    from mirror_b200 import ops
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_clip, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    emu_backend.use()
+    try:
+        for sym in (True, False):
+            w, r, s_ = _clip_problem()
+            w.requires_grad_(True), r.requires_grad_(True), s_.requires_grad_(True)
+            loss = ops.clip_loss(w, r, s_, 0.5 if sym else 1.0, 0.5 if sym else 0.0, "mean")
+            (0.37 * loss).backward()
+            B, E = w.shape[0] // world, w.shape[1]
+            packs = [torch.from_numpy(x) for x in got[sym]]
+            assert abs(float(sum(p[0] for p in packs) / world) - float(loss)) <= 1e-5 * abs(float(loss))
+            assert abs(float(sum(p[1] for p in packs) / world) - float(s_.grad)) <= 1e-4 * abs(float(s_.grad)) + 1e-7
+            for rk, p in enumerate(packs):  # DDP averages over ranks: (1/world) * local gradient = gradient of the global-batch loss
+                dw, dr = p[2:2 + B * E].view(B, E) / world, p[2 + B * E:].view(B, E) / world
+                assert float((dw - w.grad[rk * B:(rk + 1) * B]).norm() / w.grad.norm()) <= 1e-4
+                assert float((dr - r.grad[rk * B:(rk + 1) * B]).norm() / r.grad.norm()) <= 1e-4
+    finally:
+        emu_backend.release()
