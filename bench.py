@@ -579,7 +579,11 @@ def main():
                                     "sample": f"1 warm-up + 3 timed steps of {args.cpu_batch} slides (same N/Dw/Dr, fp32 oracle port, dropout off, "
                                               f"{time.time() - t0:.0f} s of CPU work)"}
         print(json.dumps(line), flush=True)
+    if args.graph:
+        gs.close()  # before the communicator goes away: the graph holds NCCL kernels
     if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

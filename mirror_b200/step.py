@@ -188,6 +188,14 @@ class GraphedStep:
             self._body()
         return self.stats[0]
 
+    def close(self):
+        """Drop the captured graph.  Call it before ``destroy_process_group``: a live graph that holds NCCL kernels keeps the
+        communicator busy and the teardown waits for it forever."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+
     def read_stats(self):
         """{name: float} of the last step: ONE device->host copy (the trainer's seven .item() calls, train_mirror.py:1256-1274)."""
         return dict(zip(self.STATS, self.stats.tolist()))
