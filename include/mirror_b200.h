@@ -131,6 +131,10 @@ int mirror_cast_split3(const float* src, int64_t rows, int32_t cols, int64_t lds
                        int32_t stack_rows, int32_t order, mirror_stream_t stream);
 /* dst[r,0:cols] = src[r,0:cols] with row strides: gathers `wsi_emb[:, 0, :]` (models/mirror.py:896) into a dense block */
 int mirror_copy_rows_f32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd, mirror_stream_t stream);
+/* dst[r, 0:cols] (f32, dense) = src[idx[r], 0:cols], src fp32 or bf16 (src_bf16) with row stride lds, n_src rows: the per-slide
+ * patch resampling of datasets/dataset_pretrain.py:157-161 over the packed features of a batch, on the device (mirror_b200/data.py) */
+int mirror_gather_rows(const void* src, int32_t src_bf16, int64_t lds, int64_t n_src, const int64_t* idx, int64_t rows, int32_t cols,
+                       float* dst, mirror_stream_t stream);
 /* out[r] = sum_c a[r,c]*(b[r,c] - sub[r,c]) over contiguous bf16 rows (cols % 8 == 0, sub may be NULL): the row dots dO.O of a
  * softmax backward; `sub` removes a residual that was added to O after the attention product */
 int mirror_rowdot_bf16(const void* a, const void* b, const void* sub, int64_t rows, int32_t cols, float* out, mirror_stream_t stream);

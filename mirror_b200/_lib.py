@@ -162,6 +162,7 @@ SIGNATURES = {
     "mirror_sym_kl_bwd": [_P, _I32, _I32, _P, _F, _P, _P, _P],
     "mirror_loss_combine": [_P, _P, _P, _P],
     "mirror_set_dropout_epoch": [_P],
+    "mirror_gather_rows": [_P, _I32, _I64, _I64, _P, _I64, _I32, _P, _P],
     "mirror_adam_step": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _I32, _P, _P, _P],
     "mirror_grad_sumsq": [_P, _I64, _P, _P],
     "mirror_tail_scalars": [_P, _F, _P, _P, _P, _F, _F, _P],

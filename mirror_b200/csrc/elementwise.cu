@@ -111,6 +111,45 @@ __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ s
     dst[i] += alpha * src[i];
 }
 
+// dst[r, :] = float(src[idx[r], :]): the dataset's per-slide resampling (datasets/dataset_pretrain.py:157-161) done on the device
+// over the packed patch features of the batch; src is fp32 (src_bf16 = 0) or bf16 (= 1: half the H2D bytes of the feature
+// store).  One warp per output row, 16-byte lanes; HBM-bound (reads + writes rows * cols elements once).
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const void* __restrict__ src, int src_bf16, long long lds, const long long* __restrict__ idx, long long rows, int cols,
+                   long long n_src, float* __restrict__ dst) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long r = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
+    long long s = idx[r];
+    s = s < 0 ? 0 : (s >= n_src ? n_src - 1 : s);  // clamp: a bad index must not read out of bounds
+    float* d = dst + r * cols;
+    if (src_bf16) {
+      const bf16* sp = reinterpret_cast<const bf16*>(src) + s * lds;
+      if ((cols & 7) == 0 && (lds & 7) == 0) {
+        for (int c = lane * 8; c < cols; c += 256) {
+          const uint4 v = *reinterpret_cast<const uint4*>(sp + c);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          float4 lo, hi;
+          lo.x = __uint_as_float(w[0] << 16); lo.y = __uint_as_float(w[0] & 0xffff0000u);
+          lo.z = __uint_as_float(w[1] << 16); lo.w = __uint_as_float(w[1] & 0xffff0000u);
+          hi.x = __uint_as_float(w[2] << 16); hi.y = __uint_as_float(w[2] & 0xffff0000u);
+          hi.z = __uint_as_float(w[3] << 16); hi.w = __uint_as_float(w[3] & 0xffff0000u);
+          *reinterpret_cast<float4*>(d + c) = lo;
+          *reinterpret_cast<float4*>(d + c + 4) = hi;
+        }
+      } else {
+        for (int c = lane; c < cols; c += 32) d[c] = __bfloat162float(sp[c]);
+      }
+    } else {
+      const float* sp = reinterpret_cast<const float*>(src) + s * lds;
+      if ((cols & 3) == 0 && (lds & 3) == 0) {
+        for (int c = lane * 4; c < cols; c += 128) *reinterpret_cast<float4*>(d + c) = *reinterpret_cast<const float4*>(sp + c);
+      } else {
+        for (int c = lane; c < cols; c += 32) d[c] = sp[c];
+      }
+    }
+  }
+}
+
 // out = dropout(act(pre)) as bf16 (and optionally f32)
 __global__ void act_fwd_kernel(const float* __restrict__ pre, long long n, int act, float drop_p, float drop_scale,
                                uint64_t seed, const unsigned long long* epoch, bf16* __restrict__ o16, float* __restrict__ o32) {
@@ -610,6 +649,17 @@ extern "C" int mirror_reparam_bwd(const float* dz, const float* logvar, const fl
                                   mirror_stream_t stream) {
   MB_CHECK_ARG(dz && logvar && eps && dmu && dlogvar && n > 0, "reparam_bwd: bad args");
   reparam_bwd_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(dz, logvar, eps, n, dmu, dlogvar);
+  MB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mirror_gather_rows(const void* src, int32_t src_bf16, int64_t lds, int64_t n_src, const int64_t* idx, int64_t rows,
+                                  int32_t cols, float* dst, mirror_stream_t stream) {
+  MB_CHECK_ARG(src && idx && dst && rows > 0 && cols > 0 && n_src > 0 && lds >= cols, "gather_rows: bad args");
+  MB_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+               "gather_rows: buffers must be 16-byte aligned");
+  gather_rows_kernel<<<grid_for(rows, 8), 256, 0, STREAM>>>(src, src_bf16, lds, reinterpret_cast<const long long*>(idx), rows, cols,
+                                                           n_src, dst);
   MB_LAUNCH_CHECK();
   return 0;
 }

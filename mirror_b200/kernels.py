@@ -442,13 +442,14 @@ def res_conv_bwd(dout16, qkv, w, dw):
 
 
 @_op
-def pinv_init(a2):
-    """a2: [B,h,m,m] f32 -> (z16, scratch) with z0 = a2^T / (max rowsum * max colsum) in bf16."""
+def pinv_init(a2, z16=None, scratch=None):
+    """a2: [..,m,m] f32 -> (z16, scratch) with z0 = a2^T / (max rowsum * max colsum) in bf16, the maxima taken over ALL matrices of
+    a2 (the reference's batch-global scale).  z16 / scratch: optional preallocated outputs (slices of per-slide buffers)."""
     m = a2.shape[-1]
     BH = a2.numel() // (m * m)
-    z16 = torch.empty_like(a2, dtype=BF16)
-    scratch = torch.empty(8, device=a2.device, dtype=F32)
-    _call("mirror_pinv_init", _p(_contig(a2), F32), BH, m, _p(scratch), None, _p(z16), launches=2)
+    z16 = torch.empty_like(a2, dtype=BF16) if z16 is None else z16
+    scratch = torch.empty(8, device=a2.device, dtype=F32) if scratch is None else scratch
+    _call("mirror_pinv_init", _p(_contig(a2), F32), BH, m, _p(_contig(scratch)), None, _p(_contig(z16)), launches=2)
     return z16, scratch
 
 
@@ -718,3 +719,17 @@ def tail_scalars_(sumsq=None, max_norm=0.0, coef=None, step=None, clamp_param=No
     """One launch: coef <- clip coefficient, step += 1, clamp_param <- clamp(clamp_param, lo, hi) (each optional)."""
     _call("mirror_tail_scalars", _p(sumsq, F32) if sumsq is not None else None, max_norm, _p(coef, F32) if coef is not None else None,
           _p(step, F32) if step is not None else None, _p(clamp_param, F32) if clamp_param is not None else None, lo, hi)
+
+
+# ---- input pipeline (mirror_b200/data.py) ----------------------------------------------------------------------------------
+@_op
+def gather_rows(src, idx, out=None):
+    """out[r, :] = float(src[idx[r], :]); src: [n_src, cols] f32 or bf16 (row stride >= cols), idx: int64 [...] -> out [..., cols] f32."""
+    if src.dim() != 2 or src.stride(1) != 1 or src.dtype not in (F32, BF16):
+        raise ValueError("gather_rows needs a [rows, cols] fp32 / bf16 source with unit column stride")
+    _cuda(src), _cuda(idx, torch.int64)
+    cols = src.shape[1]
+    out = torch.empty(*idx.shape, cols, device=src.device, dtype=F32) if out is None else out
+    _call("mirror_gather_rows", src.data_ptr(), int(src.dtype == BF16), src.stride(0), src.shape[0], _p(_contig(idx)), idx.numel(), cols,
+          _p(_contig(out), F32))
+    return out

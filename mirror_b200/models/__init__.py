@@ -1,3 +1,3 @@
-from .mirror import MIRROR, MIRRORDualEncoder, mirror, mirror_dual_encoder
+from .mirror import MIRROR, MIRRORClassifier, MIRRORDualEncoder, mirror, mirror_classifier, mirror_dual_encoder
 
-__all__ = ["MIRROR", "MIRRORDualEncoder", "mirror", "mirror_dual_encoder"]
+__all__ = ["MIRROR", "MIRRORClassifier", "MIRRORDualEncoder", "mirror", "mirror_classifier", "mirror_dual_encoder"]

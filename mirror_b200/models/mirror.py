@@ -167,10 +167,11 @@ class TransLayer(nn.Module):
         self.norm = nn.LayerNorm(dim)
         self.attn = _NystromParams(dim)
 
-    def forward(self, x):
+    def forward(self, x, per_slide_scale=False):
+        """per_slide_scale: the Moore-Penrose initial scale per slide instead of over the batch (variable-length bags)."""
         a = self.attn
         return ops.nystrom_layer(x, self.norm.weight, self.norm.bias, a.to_qkv.weight, a.to_out[0].weight, a.to_out[0].bias,
-                                 a.res_conv.weight, a.to_out[1].p if self.training else 0.0, self.norm.eps)
+                                 a.res_conv.weight, a.to_out[1].p if self.training else 0.0, self.norm.eps, per_slide_scale)
 
 
 class PPEG(nn.Module):
@@ -200,16 +201,16 @@ class FeatureTransMIL(nn.Module):
         self.layer2 = TransLayer(dim=embed_dim)
         self.norm = nn.LayerNorm(embed_dim)
 
-    def _tokens(self, h, drop_wrap=False):
+    def _tokens(self, h, drop_wrap=False, per_slide_scale=False):
         """fc1+ReLU, wrap pad, cls, layer1, PPEG, layer2, final norm -> ([B,S,E] f32, bf16 copy, add_length).
         ``drop_wrap``: the final norm returns only the N+1 real tokens (contiguous [B,N+1,E]); add_length is then 0."""
         N = h.shape[1]
         Hs = int(np.ceil(np.sqrt(N)))
         add = Hs * Hs - N
         x = ops.WsiEmbedFn.apply(h.float(), self._fc1[0].weight, self._fc1[0].bias, self.cls_token)
-        x = self.layer1(x)
+        x = self.layer1(x, per_slide_scale)
         x = self.pos_layer(x)
-        x = self.layer2(x)
+        x = self.layer2(x, per_slide_scale)
         if drop_wrap:
             y, y16 = ops.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps, keep=N + 1)
             return y, y16, 0
@@ -318,8 +319,8 @@ class FeatureTransMILHybrid(FeatureTransMIL):
             nn.init.constant_(m.bias, 0)
             nn.init.constant_(m.weight, 1.0)
 
-    def forward_encoder(self, h):
-        y, y16, _ = self._tokens(h, drop_wrap=True)  # LayerNorm + `h[:, :-add_length]` (models/mirror.py:372) in one pass
+    def forward_encoder(self, h, per_slide_scale=False):
+        y, y16, _ = self._tokens(h, drop_wrap=True, per_slide_scale=per_slide_scale)  # LayerNorm + `h[:, :-add_length]` (models/mirror.py:372) in one pass
         # bf16 copy for the retention decoder, attached to the TENSOR it mirrors (with its version counter), not to the
         # module: a different or modified embedding of the same shape cannot pick it up, and nothing stays pinned on the
         # module (deepcopy / ModelEma) once the caller drops the embedding
@@ -331,9 +332,11 @@ class FeatureTransMILHybrid(FeatureTransMIL):
         cls = h[:, 0, :] if cls is None else cls
         return ops.linear(ops.l2_normalize(cls, eps), self.alignment_head.weight, self.alignment_head.bias)
 
-    def forward_retention_head(self, h, mask_ratio, noise=None):
+    def forward_retention_head(self, h, mask_ratio, noise=None, per_slide_scale=False):
         B, T, E = h.shape  # T = N + 1
         N = T - 1
+        if T > self.retention_gene_embed.shape[1]:
+            raise ValueError(f"{N} patches exceed the position table (wsi_num_tokens = {self.retention_gene_embed.shape[1] - 1})")
         keep = int(N * (1 - mask_ratio))
         if noise is None:
             noise = torch.rand(B, N, device=h.device)
@@ -343,16 +346,17 @@ class FeatureTransMILHybrid(FeatureTransMIL):
         if side is not None and side[1] == h._version and side[0].shape == h.shape and h.is_contiguous() and h.dtype == torch.float32:
             x16 = side[0]
         r = ops.linear(h, self.retention_embed.weight, self.retention_embed.bias, x16=x16)
-        r = ops.MaskPosFn.apply(r, mask, self.mask_token, self.retention_gene_embed, 1)
+        pos = self.retention_gene_embed if T == self.retention_gene_embed.shape[1] else self.retention_gene_embed[:, :T]
+        r = ops.MaskPosFn.apply(r, mask, self.mask_token, pos, 1)
         for blk in self.retention_blocks:
-            r = blk(r)
+            r = blk(r, per_slide_scale)
         r, r16 = ops.layer_norm(r, self.retention_norm.weight, self.retention_norm.bias, self.retention_norm.eps)
         r = ops.linear(r, self.retention_head.weight, self.retention_head.bias, x16=r16)
         return ops.drop_first_token(r), mask
 
-    def forward_decoders(self, h, mask_ratio, noise=None, cls=None):
+    def forward_decoders(self, h, mask_ratio, noise=None, cls=None, per_slide_scale=False):
         a = self.forward_alignment_head(h, cls)
-        r, mask = self.forward_retention_head(h, mask_ratio, noise)
+        r, mask = self.forward_retention_head(h, mask_ratio, noise, per_slide_scale)
         return a, r, mask
 
     def forward(self, h, mask_ratio=0.75):
@@ -451,6 +455,55 @@ class MIRROR(nn.Module):
         return (wa, wr, wsi_retention_target, wm, ws, wmu, wls, ra, rr, rna_emb, rm, rs, rmu, rls, self.logit_scale.exp())
 
 
+def _length_groups(bags):
+    """{N: [slide indices]} in first-appearance order."""
+    groups = {}
+    for i, b in enumerate(bags):
+        if b.dim() != 2:
+            raise ValueError("every bag must be a [N_i, Dw] tensor")
+        groups.setdefault(int(b.shape[0]), []).append(i)
+    return groups
+
+
+def _forward_varlen(self, bags, rna_emb, wsi_mask_ratio=0.75, rna_mask_ratio=0.75, noise=None):
+    """Variable-length bags: ``bags`` is a list of [N_i, Dw] feature tensors, one per slide, instead of the
+    reference's resample-every-slide-to-N batch (datasets/dataset_pretrain.py:157-161).  Every slide keeps its own geometry
+    -- H_i = ceil(sqrt(N_i)), S_i = H_i^2 + 1, landmark group size ceil(S_i / m), Moore-Penrose scale, int(N_i (1 - r)) kept
+    tokens, position table sliced to N_i + 1 rows (N_i <= wsi_num_tokens) -- i.e. the result is the reference at B = 1 per
+    slide with wsi_num_tokens = N_i.  Slides of EQUAL length run as one dense batch through the fixed-length kernels
+    (bucket the dataset by length to keep the launch count down); the ragged retention outputs are packed along the token
+    axis, [1, sum N_i, E] with mask [1, sum N_i], which MIRRORLoss's masked MSE consumes unchanged.  Returns the 15-tuple of
+    ``forward`` with the batch-level entries in the order of ``bags``.
+    ``noise["wsi_mask"]``: optional list of [1, N_i] tensors (parity tests)."""
+    noise = noise or {}
+    B = len(bags)
+    enc = self.wsi_encoder
+    cls_rows, wa_rows, wr_parts, wt_parts, wm_parts = [None] * B, [None] * B, [None] * B, [None] * B, [None] * B
+    for N, idx in _length_groups(bags).items():
+        x = torch.stack([bags[i] for i in idx]) if len(idx) > 1 else bags[idx[0]][None]
+        h = enc.forward_encoder(x, per_slide_scale=True)
+        cls, full, tgt = ops.token_fanout(h)
+        side = getattr(h, "_mirror_side", None)
+        if side is not None and full.data_ptr() == h.data_ptr():
+            full._mirror_side = (side[0], full._version)
+        nz = None
+        if noise.get("wsi_mask") is not None:
+            nz = torch.cat([noise["wsi_mask"][i].reshape(1, N) for i in idx])
+        wa, wr, wm = enc.forward_decoders(full, wsi_mask_ratio, nz, cls=cls, per_slide_scale=True)
+        for j, i in enumerate(idx):
+            cls_rows[i], wa_rows[i] = cls[j:j + 1], wa[j:j + 1]
+            wr_parts[i], wt_parts[i], wm_parts[i] = wr[j], tgt[j], wm[j]
+    wsi_cls, wa = torch.cat(cls_rows), torch.cat(wa_rows)
+    wr, wt, wm = torch.cat(wr_parts)[None], torch.cat(wt_parts)[None], torch.cat(wm_parts)[None]
+    rna_emb = self.rna_encoder.forward_encoder(rna_emb)
+    ra, rr, rm = self.rna_encoder.forward_decoders(rna_emb, rna_mask_ratio, noise.get("rna_mask"))
+    ws, wmu, wls, rs, rmu, rls = self.forward_style_clustering(wsi_cls, rna_emb, noise.get("wsi_eps"), noise.get("rna_eps"))
+    return (wa, wr, wt, wm, ws, wmu, wls, ra, rr, rna_emb, rm, rs, rmu, rls, self.logit_scale.exp())
+
+
+MIRROR.forward_varlen = _forward_varlen
+
+
 class MIRRORDualEncoder(nn.Module):
     """The 2-output model ``train_pretrain.py:1119-1122`` unpacks (the reference registers none):
     FeatureTransMIL cls embedding (models/mirror.py:352-380) and TransFormer embedding (:283-289)."""
@@ -465,6 +518,43 @@ class MIRRORDualEncoder(nn.Module):
 
     def forward(self, wsi_emb, rna_emb):
         return self.wsi_encoder(wsi_emb), self.rna_encoder(rna_emb)
+
+
+class MIRRORClassifier(nn.Module):
+    """models/mirror.py:921-1015: the downstream (sub-typing / survival) model -- FeatureTransMIL cls embedding, optional
+    TransFormer RNA embedding, "add" or "concat" fusion, linear head -- on the same kernels, with the reference's attribute
+    names and state_dict keys (``wsi_encoder.*``, ``rna_encoder.*``, ``head.*``) so that a split pre-training checkpoint
+    (tools/split_weights.py) loads with ``load_checkpoint(strict=False)``."""
+
+    def __init__(self, wsi_embed_dim: int, rna_embed_dim: int, embed_dim: int, num_classes: int, rna_encoder_depth: int = 2,
+                 rna_gene_embed: str = "learn", rna_mlp_ratio: float = 2.572, rna_pos_drop_rate: float = 0.0,
+                 rna_proj_drop_rate: float = 0.1, rna_attn_drop_rate: float = 0.0, rna_drop_path_rate: float = 0.0,
+                 rna_norm_layer=None, rna_act_layer=None, fusion: str = "concat") -> None:
+        super().__init__()
+        self.wsi_embed_dim, self.rna_embed_dim, self.embed_dim = wsi_embed_dim, rna_embed_dim, embed_dim
+        self.rna_encoder_depth, self.rna_gene_embed, self.rna_mlp_ratio = rna_encoder_depth, rna_gene_embed, rna_mlp_ratio
+        self.rna_pos_drop_rate, self.rna_proj_drop_rate = rna_pos_drop_rate, rna_proj_drop_rate
+        self.attn_drop_rate, self.drop_path_rate = rna_attn_drop_rate, rna_drop_path_rate
+        self.rna_norm_layer, self.rna_act_layer = rna_norm_layer, rna_act_layer
+        self.num_classes, self.fusion = num_classes, fusion
+        assert self.fusion in ["add", "concat"], "Fusion must be either add or concat"
+        self.wsi_encoder = FeatureTransMIL(input_dim=wsi_embed_dim, embed_dim=embed_dim)
+        self.rna_encoder = TransFormer(input_dim=rna_embed_dim, embed_dim=embed_dim, depth=rna_encoder_depth,
+                                       gene_embed=rna_gene_embed, mlp_ratio=rna_mlp_ratio, pos_drop_rate=rna_pos_drop_rate,
+                                       proj_drop_rate=rna_proj_drop_rate, attn_drop_rate=rna_attn_drop_rate,
+                                       drop_path_rate=rna_drop_path_rate, norm_layer=rna_norm_layer, act_layer=rna_act_layer)
+        self.head = nn.Linear(embed_dim * (2 if fusion == "concat" else 1), num_classes)
+
+    def forward(self, wsi_emb: torch.Tensor, rna_emb: Optional[torch.Tensor] = None) -> torch.Tensor:
+        w = self.wsi_encoder(wsi_emb)
+        if rna_emb is None:
+            return ops.linear(w, self.head.weight, self.head.bias)
+        r = self.rna_encoder(rna_emb)
+        if self.fusion == "add":
+            # W (w + r) + b as two products sharing the bias: no separate add kernel, both gradients from the same GEMMs
+            return ops.linear(w, self.head.weight, self.head.bias, res=ops.linear(r, self.head.weight))
+        E = self.embed_dim  # concat: [w | r] W^T = w W[:, :E]^T + r W[:, E:]^T
+        return ops.linear(w, self.head.weight[:, :E], self.head.bias, res=ops.linear(r, self.head.weight[:, E:]))
 
 
 _MIRROR_ARGS = {
@@ -487,6 +577,15 @@ def _filtered(kwargs, accepted):
 @register_model
 def mirror(**kwargs):
     return MIRROR(**_filtered(kwargs, _MIRROR_ARGS))
+
+
+_CLS_ARGS = {"wsi_embed_dim", "rna_embed_dim", "embed_dim", "rna_encoder_depth", "rna_gene_embed", "rna_mlp_ratio", "rna_pos_drop_rate",
+             "rna_proj_drop_rate", "rna_attn_drop_rate", "rna_drop_path_rate", "rna_norm_layer", "rna_act_layer", "num_classes", "fusion"}
+
+
+@register_model
+def mirror_classifier(**kwargs):
+    return MIRRORClassifier(**_filtered(kwargs, _CLS_ARGS))
 
 
 @register_model

@@ -434,7 +434,7 @@ class NystromLayerFn(Function):
 
     @staticmethod
     @_cfwd
-    def forward(ctx, h, ln_w, ln_b, qkv_w, out_w, out_b, conv_w, drop_p, seed, eps=1e-5):
+    def forward(ctx, h, ln_w, ln_b, qkv_w, out_w, out_b, conv_w, drop_p, seed, eps=1e-5, per_slide_scale=False):
         B, S, E = h.shape
         hd = WSI_HEADS
         d, m = E // hd, E // 2
@@ -461,7 +461,13 @@ class NystromLayerFn(Function):
             a3, _ = _softmax_gemm(ql, k, m, n, scale)
             K.gemm(a3, _T(v), out_bf16=kv)
         a2_16, a2_32 = _softmax_gemm(ql, kl, m, m, scale, want_f32=True)
-        z16, scratch = K.pinv_init(a2_32)
+        if per_slide_scale and B > 1:  # variable-length bags: every slide is its own "batch" (the reference at B = 1 per slide)
+            z16 = torch.empty_like(a2_32, dtype=BF16)
+            scratch = torch.empty(B, 8, device=dev, dtype=F32)
+            for b in range(B):
+                K.pinv_init(a2_32[b], z16[b], scratch[b])
+        else:
+            z16, scratch = K.pinv_init(a2_32)
         iters = []
         mm = (B, hd, m, m)
         for _ in range(PINV_ITERS):
@@ -492,6 +498,7 @@ class NystromLayerFn(Function):
         ctx.save_for_backward(h, ln_w, mean, rstd, xn16, wqkv16, qkv, lm, lse1 if flash else a1, a2_16, lse3 if flash else a3, scratch,
                               z16, kv, w_, o16, wout16, conv_w, rc, *iters)
         ctx.meta = (B, S, E, pad, n, seg, scale, drop_p, seed, flash)
+        ctx.per_slide_scale = bool(per_slide_scale and B > 1)
         return y
 
     @staticmethod
@@ -569,7 +576,11 @@ class NystromLayerFn(Function):
         ga2 = torch.empty(mm, device=dev, dtype=F32)
         K.gemm(gens[0][0], gens[0][1], more=gens[1:], out_f32=ga2)
         del gens
-        if _FUSED_PINV_BWD and m % 32 == 0 and m <= 512:  # iters[0] = z0 (bf16)
+        if ctx.per_slide_scale:
+            for b in range(B):
+                K.pinv_init_bwd(gz32[b], iters[0][b], scratch[b], ga2[b], True)
+            ds2, _ = K.softmax_bwd(a2_16, ga2, scale)
+        elif _FUSED_PINV_BWD and m % 32 == 0 and m <= 512:  # iters[0] = z0 (bf16)
             ds2 = K.pinv_init_softmax_bwd(ga2, gz32, iters[0], a2_16, scratch, scale)
         else:
             K.pinv_init_bwd(gz32, iters[0], scratch, ga2, True)
@@ -593,7 +604,7 @@ class NystromLayerFn(Function):
         db = torch.zeros(E, device=dev, dtype=F32)
         dh = torch.empty_like(h)
         K.layernorm_bwd(dxn, h, ln_w, mean, rstd, pad, dh, dy, dg, db)
-        return dh, dg, db, d_qkv_w, d_out_w, d_out_b, d_conv.view(conv_w.shape), None, None, None
+        return dh, dg, db, d_qkv_w, d_out_w, d_out_b, d_conv.view(conv_w.shape), None, None, None, None
 
 
 def _nystrom_backward_flash(ctx, dy):
@@ -658,7 +669,11 @@ def _nystrom_backward_flash(ctx, dy):
     ga2 = torch.empty(mm, device=dev, dtype=F32)
     K.gemm(gens[0][0], gens[0][1], more=gens[1:], out_f32=ga2)
     del gens
-    K.pinv_init_bwd(gz32, iters[0], scratch, ga2, True)
+    if ctx.per_slide_scale:
+        for b in range(B):
+            K.pinv_init_bwd(gz32[b], iters[0][b], scratch[b], ga2[b], True)
+    else:
+        K.pinv_init_bwd(gz32, iters[0], scratch, ga2, True)
     ds2, _ = K.softmax_bwd(a2_16, ga2, scale)
     del ga2, gz32, gz16
 
@@ -681,14 +696,15 @@ def _nystrom_backward_flash(ctx, dy):
     db = torch.zeros(E, device=dev, dtype=F32)
     dh = torch.empty_like(h)
     K.layernorm_bwd(dxn, h, ln_w, mean, rstd, pad, dh, dy, dg, db)
-    return dh, dg, db, d_qkv_w, d_out_w, d_out_b, d_conv.view(conv_w.shape), None, None, None
+    return dh, dg, db, d_qkv_w, d_out_w, d_out_b, d_conv.view(conv_w.shape), None, None, None, None
 
 
 NystromLayerFn._backward_flash = staticmethod(_nystrom_backward_flash)
 
 
-def nystrom_layer(h, norm_w, norm_b, qkv_w, out_w, out_b, conv_w, drop_p, eps=1e-5):
-    return NystromLayerFn.apply(h, norm_w, norm_b, qkv_w, out_w, out_b, conv_w, drop_p, next_seed() if drop_p > 0 else 0, eps)
+def nystrom_layer(h, norm_w, norm_b, qkv_w, out_w, out_b, conv_w, drop_p, eps=1e-5, per_slide_scale=False):
+    return NystromLayerFn.apply(h, norm_w, norm_b, qkv_w, out_w, out_b, conv_w, drop_p, next_seed() if drop_p > 0 else 0, eps,
+                                per_slide_scale)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -239,6 +239,30 @@ def mirror_forward(sd: SD, wsi: Tensor, rna: Tensor, noise: Dict[str, Tensor],
             ra, rr, rna_emb, rm, rs, rmu, rls, sd["logit_scale"].exp())
 
 
+def mirror_forward_varlen(sd: SD, bags, rna: Tensor, noise: Dict[str, object],
+                          wsi_mask_ratio: float = 0.75, rna_mask_ratio: float = 0.75):
+    """Variable-length bags (no reference counterpart in batched form): every slide i with its own N_i patches
+    is encoded and decoded by the reference algorithm AT B = 1 with wsi_num_tokens = N_i (own H_i, S_i, landmark group size,
+    pinv scale; position table retention_gene_embed sliced to its first N_i + 1 rows), the batch-level parts (RNA encoder,
+    style / cluster heads) run on the whole batch.  Ragged retention outputs are packed along the token axis as
+    [1, sum N_i, E] with mask [1, sum N_i], for which losses/mirror_loss.py:98-103 is exactly the token-weighted masked MSE.
+    noise["wsi_mask"] is a list of [1, N_i] tensors."""
+    pfx = "wsi_encoder"
+    was, wrs, wts, wms, cls = [], [], [], [], []
+    for i, bag in enumerate(bags):
+        emb, _ = wsi_encoder(sd, bag[None])
+        sdi = dict(sd)
+        sdi[pfx + ".retention_gene_embed"] = sd[pfx + ".retention_gene_embed"][:, : bag.shape[0] + 1]
+        wa, wr, wm = wsi_decoders(sdi, emb, wsi_mask_ratio, noise["wsi_mask"][i])
+        was.append(wa), wrs.append(wr), wts.append(emb[:, 1:]), wms.append(wm), cls.append(emb[:, 0])
+    rna_emb = rna_encoder(sd, rna.to(was[0].dtype))
+    ra, rr, rm = rna_decoders(sd, rna_emb, rna_mask_ratio, noise["rna_mask"])
+    ws, wmu, wls = style_heads(sd, torch.cat(cls), noise["wsi_eps"])
+    rs, rmu, rls = style_heads(sd, rna_emb, noise["rna_eps"])
+    return (torch.cat(was), torch.cat(wrs, 1), torch.cat(wts, 1), torch.cat(wms, 1), ws, wmu, wls,
+            ra, rr, rna_emb, rm, rs, rmu, rls, sd["logit_scale"].exp())
+
+
 def dual_encoder_forward(sd: SD, wsi: Tensor, rna: Tensor):
     """2-output model train_pretrain.py:1119-1122 expects: FeatureTransMIL cls
     embedding (models/mirror.py:352-380) and TransFormer output (:283-289)."""

@@ -332,15 +332,18 @@ class Emu:
         dw += gw.view(h, -1)
         return gv.permute(0, 2, 1, 3).reshape(B, n, E).to(BF16)
 
-    def pinv_init(self, a2):
+    def pinv_init(self, a2, z16=None, scratch=None):
         ax = a2.abs()
         rs, cs = ax.sum(-1), ax.sum(-2)
-        scratch = torch.zeros(8)
+        scratch = torch.zeros(8) if scratch is None else scratch
         scratch[0], scratch[1] = rs.max(), cs.max()
         scratch[3], scratch[4] = float(rs.flatten().argmax()), float(cs.flatten().argmax())
         z = a2.transpose(-1, -2) / (scratch[0] * scratch[1])
-        z = z.contiguous()
-        return z.to(BF16), scratch
+        z = z.contiguous().to(BF16)
+        if z16 is not None:
+            z16.copy_(z)
+            z = z16
+        return z, scratch
 
     def pinv_init_bwd(self, gz0, z0_16, scratch, gx, accumulate):
         c, r = scratch[0], scratch[1]
@@ -527,6 +530,13 @@ class Emu:
 
     def loss_combine(self, terms5, weights):
         return (terms5 * torch.tensor(weights, dtype=F32)).sum()
+
+    def gather_rows(self, src, idx, out=None):
+        y = src[idx.clamp(0, src.shape[0] - 1)].float()
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
 
     # ---- step tail (csrc/optim.cu)
     def set_dropout_epoch(self, counter):
