@@ -262,10 +262,12 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           uint32_t acc[32];
           tmem_ld_32x32(lane_base + sb * 128 + hf * 64 + cc * 32, acc);
           tmem_ld_wait();
+          if (cv >= 32) {  // full chunk (every chunk of the model's shapes: keys are multiples of 128): no per-element masks
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float a = e < cv ? __uint_as_float(acc[e]) : -INFINITY, c = e + 1 < cv ? __uint_as_float(acc[e + 1]) : -INFINITY;
-            mx = fmaxf(mx, fmaxf(a, c));
+            for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(acc[e]), __uint_as_float(acc[e + 1])));
+          } else {  // ragged tail of the last key block (cold: the model's key counts are multiples of 128)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, e < cv ? __uint_as_float(acc[e]) : -INFINITY);
           }
         }
         if (warp == 2 && lane == 0) tr.ev(21);
@@ -295,13 +297,21 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             tmem_ld_32x32(lane_base + sb * 128 + hf * 64 + cc * 32, acc);
             tmem_ld_wait();
           }
+          if (cv >= 32) {
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            float x0 = fast_exp2(fmaf(a2, __uint_as_float(acc[2 * u]), -m2)), x1 = fast_exp2(fmaf(a2, __uint_as_float(acc[2 * u + 1]), -m2));
-            x0 = 2 * u < cv ? x0 : 0.f;  // ragged tail of the last key block
-            x1 = 2 * u + 1 < cv ? x1 : 0.f;
-            l4[u & 3] += x0 + x1;
-            wd[u] = pack_bf16(x0, x1);
+            for (int u = 0; u < 16; ++u) {
+              const float x0 = fast_exp2(fmaf(a2, __uint_as_float(acc[2 * u]), -m2)), x1 = fast_exp2(fmaf(a2, __uint_as_float(acc[2 * u + 1]), -m2));
+              l4[u & 3] += x0 + x1;
+              wd[u] = pack_bf16(x0, x1);
+            }
+          } else {  // ragged tail of the last key block (cold)
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const float x0 = 2 * u < cv ? fast_exp2(fmaf(a2, __uint_as_float(acc[2 * u]), -m2)) : 0.f;
+              const float x1 = 2 * u + 1 < cv ? fast_exp2(fmaf(a2, __uint_as_float(acc[2 * u + 1]), -m2)) : 0.f;
+              l4[u & 3] += x0 + x1;
+              wd[u] = pack_bf16(x0, x1);
+            }
           }
           tmem_st_32x32_x16(lane_base + kColP + pb * 64 + hf * 32 + cc * 16, wd);
         }
@@ -595,6 +605,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int rl = q * 32 + lane;
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
     const float a2 = p.alpha * kLog2e;
+    const float log2_alpha = fast_log2(p.alpha);
     float2* cs = colstat + (warp - 2) * 32;  // this warp's private copy of its 32 columns' statistics
     uint32_t bc = 0, ti = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
@@ -609,9 +620,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float2 nxt = make_float2(INFINITY, 0.f);
       if (COLS) {
         const int i = hf * 32 + lane;
-        if (i < p.L) nxt = make_float2(lse_bh[i], dot_bh[i]);
+        if (i < p.L) nxt = make_float2(lse_bh[i], p.alpha * dot_bh[i]);  // (lse, alpha dot): dS = P (alpha dP - alpha dot)
       } else if (row_ok) {
-        r_lse = lse_bh[row];
+        r_lse = lse_bh[row] - log2_alpha;  // 2^(a2 S - lse + log2 alpha) = alpha P
         r_dot = dot_bh[row];
       }
       {  // residual rows of the epilogue: pull them towards L2 while the tile computes
@@ -629,7 +640,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           cs[lane] = nxt;
           __syncwarp();
           const int i = (blk + 1) * 64 + hf * 32 + lane;
-          nxt = (blk + 1 < p.nblk && i < p.L) ? make_float2(lse_bh[i], dot_bh[i]) : make_float2(INFINITY, 0.f);
+          nxt = (blk + 1 < p.nblk && i < p.L) ? make_float2(lse_bh[i], p.alpha * dot_bh[i]) : make_float2(INFINITY, 0.f);
         }
         mbar_wait(&s_full[buf], (bc >> 1) & 1);
         tc_fence_after();
@@ -645,17 +656,25 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float p0 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u]), -c0.x));
             const float p1 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u + 1]), -c1.x));
             wpp[u] = pack_bf16(p0, p1);
-            wds[u] = pack_bf16(p.alpha * p0 * (__uint_as_float(da[2 * u]) - c0.y), p.alpha * p1 * (__uint_as_float(da[2 * u + 1]) - c1.y));
+            wds[u] = pack_bf16(p0 * fmaf(p.alpha, __uint_as_float(da[2 * u]), -c0.y), p1 * fmaf(p.alpha, __uint_as_float(da[2 * u + 1]), -c1.y));
           }
         } else {
           const int cvalid = p.L - blk * 64 - hf * 32;  // keys of this chunk that exist
+          // alpha rides in the exponent: alpha 2^x = 2^(x + log2 alpha), so dS = (alpha P) (dP - dot) costs one FADD + one FMUL
+          if (cvalid >= 32) {
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            float p0 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u]), -r_lse));
-            float p1 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u + 1]), -r_lse));
-            if (2 * u >= cvalid) p0 = 0.f;
-            if (2 * u + 1 >= cvalid) p1 = 0.f;
-            wds[u] = pack_bf16(p.alpha * p0 * (__uint_as_float(da[2 * u]) - r_dot), p.alpha * p1 * (__uint_as_float(da[2 * u + 1]) - r_dot));
+            for (int u = 0; u < 16; ++u) {
+              const float p0 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u]), -r_lse));
+              const float p1 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u + 1]), -r_lse));
+              wds[u] = pack_bf16(p0 * (__uint_as_float(da[2 * u]) - r_dot), p1 * (__uint_as_float(da[2 * u + 1]) - r_dot));
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const float p0 = 2 * u < cvalid ? fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u]), -r_lse)) : 0.f;
+              const float p1 = 2 * u + 1 < cvalid ? fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u + 1]), -r_lse)) : 0.f;
+              wds[u] = pack_bf16(p0 * (__uint_as_float(da[2 * u]) - r_dot), p1 * (__uint_as_float(da[2 * u + 1]) - r_dot));
+            }
           }
         }
         // dS over the logits it came from, P' over dP (both already in registers); 16 TMEM columns = this warp's 32 bf16 columns
