@@ -36,7 +36,7 @@ cnt = len(ev)
 t0 = ev[0][0]
 names = {1: "P x_load", 2: "P y_load", 3: "P v_load", 10: "M tile", 14: "M s_empty ok", 11: "M S issue", 15: "M p_full ok", 12: "M PV issue", 13: "M o_full commit",
          20: "S p0 s_full", 21: "S p0 ld done", 22: "S bar1", 23: "S p1 s_full", 24: "S p1 ld done", 25: "S p_empty ok", 26: "S P stored", 27: "S bar2",
-         28: "S o_full", 29: "S epi done", 30: "S e0 start", 31: "S e0 ld done", 32: "S e0 stored", 33: "S e1 start", 34: "S e1 ld done", 35: "S e1 stored"}
+         28: "S o_full", 29: "S epi done", 30: "S e0 start", 31: "S epi acc in regs", 32: "S e0 stored", 33: "S tile start", 34: "S e1 ld done", 35: "S e1 stored"}
 print(f"{cnt} events")
 skip = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
 for t, i in ev[skip:skip + 260]:
