@@ -17,6 +17,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
 # --use_fast_math would change erff/expf accuracy in the loss math; keep IEEE-ish defaults instead.
 FLAGS.remove("--use_fast_math")
+FLAGS += os.environ.get("MIRROR_B200_EXTRA_NVCC_FLAGS", "").split()  # e.g. -DMIRROR_FLASH_TRACE (tools/flash_trace.py); part of the digest
 
 
 def _digest(paths):

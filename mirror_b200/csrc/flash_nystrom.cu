@@ -542,6 +542,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ----------------------------------------------------------------------------------------------- TMA producer
     if (elect_one()) {
+      Tracer tr;
+      tr.init(0);
       uint32_t bc = 0, ti = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
         const int tt = w % p.tiles;
@@ -556,6 +558,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_load_4d(&tmA, &at_full[tb], ta + kb * kTB, kb * 64, tt * 128, h, b);
           tma_load_4d(&tmC, &at_full[tb], ta + BwdSmem::UNIT + kb * kTB, kb * 64, tt * 128, h, b);
         }
+        tr.ev(60);
 #pragma unroll 1
         for (int blk = 0; blk < p.nblk; ++blk, ++bc) {
           const int st = bc % nst;
@@ -567,6 +570,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_4d(&tmB, &st_full[st], base + kb * kHB, kb * 64, blk * 64, h, b);
             tma_load_4d(&tmD, &st_full[st], base + (2 + kb) * kHB, kb * 64, blk * 64, h, b);
           }
+          tr.ev(61);
         }
       }
     }
@@ -576,10 +580,13 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, p.dpad, 0, 1);
       uint32_t sdc = 0, oc = 0, ti = 0;  // blocks whose logits products / output products have been issued
+      Tracer tr;
+      tr.init(1);
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
         const int tb = ti % ntb;
         mbar_wait(&at_full[tb], (ti / ntb) & 1);
         tc_fence_after();
+        tr.ev(40);
         const uint32_t aa = smem_u32(sTile + tb * 2 * BwdSmem::UNIT), ca = aa + BwdSmem::UNIT;
         int issued = 0;
         auto issue_sd = [&]() {
@@ -594,6 +601,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma_f16(tmem_base + buf * 128 + 64, desc_kmajor(ca + (ks >> 2) * kTB, ks & 3), desc_kmajor(da + (ks >> 2) * kHB, ks & 3), idesc_s,
                      ks > 0 ? 1u : 0u);
           umma_commit(&s_full[buf]);
+          tr.ev(41);
           ++sdc;
           if (++issued == p.nblk) umma_commit(&at_empty[tb]);  // all logits products of this tile are issued
         };
@@ -604,6 +612,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (blk == 0) mbar_wait(o_empty, (ti & 1) ^ 1);
           mbar_wait(&ds_full[buf], (oc >> 1) & 1);
           tc_fence_after();
+          tr.ev(42);
           const uint32_t ba = smem_u32(sSt + st * BwdSmem::UNIT), da = ba + 2 * kHB;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)  // contraction over the block's 64 columns: 8 TMEM columns (16 bf16) of dS per step
@@ -616,10 +625,12 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                           (blk > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&st_empty[st]);
+          tr.ev(43);
           ++oc;
           if (blk + 2 < p.nblk) issue_sd();  // overwrites the buffer whose dS / P the products above have just read (in-order pipe)
         }
         umma_commit(o_full);
+        tr.ev(44);
       }
     }
   } else {
@@ -631,7 +642,11 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float log2_alpha = fast_log2(p.alpha);
     float2* cs = colstat + (warp - 2) * 32;  // this warp's private copy of its 32 columns' statistics
     uint32_t bc = 0, ti = 0;
+    Tracer tr;
+    tr.init(2);
+    const bool tracer = warp == 2 && lane == 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
+      if (tracer) tr.ev(50);
       const int tt = w % p.tiles;
       const int bh = w / p.tiles;
       const int h = bh % p.heads, b = bh / p.heads;
@@ -667,6 +682,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         mbar_wait(&s_full[buf], (bc >> 1) & 1);
         tc_fence_after();
+        if (tracer) tr.ev(51);
         uint32_t sa[32], da[32];
         tmem_ld_32x32(lane_base + buf * 128 + hf * 32, sa);
         tmem_ld_32x32(lane_base + buf * 128 + 64 + hf * 32, da);
@@ -708,10 +724,12 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ds_full[buf]);
+        if (tracer) tr.ev(52);
       }
       // ---- epilogue.  COLS: the two warps of a lane quarter store one output each; ROWS: one half of out1's columns each
       mbar_wait(o_full, ti & 1);
       tc_fence_after();
+      if (tracer) tr.ev(53);
       if (COLS) {
         if (hf == 0) bwd_store_out(p.o1, lane_base + kCol1, 0, p.dpad, p.d, b, h, row, row_ok);
         else bwd_store_out(p.o2, lane_base + kCol2, 0, p.dpad, p.d, b, h, row, row_ok);
@@ -721,6 +739,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
+      if (tracer) tr.ev(54);
     }
   }
 
@@ -813,8 +832,10 @@ extern "C" int mirror_flash_bwd(const mirror_flash_bwd_args* a, mirror_stream_t 
   p.tiles = (a->T + 127) / 128;
   p.nblk = (a->L + 63) / 64;
   // six 32 KB units of shared memory: short tiles (few blocks) double-buffer the tile operands, long tiles deepen the block ring
-  p.ntb = p.nblk <= 12 ? 2 : 1;
-  p.nst = p.nblk <= 12 ? 2 : 4;
+  // (measured with the event trace: with two stages a short tile stalls ~1.4 k cycles per block on the TMA latency of the stage that
+  // the output products have just released; four stages keep the loads two blocks ahead, also across tile boundaries)
+  p.ntb = 1;
+  p.nst = 4;
   const long long total = (long long)p.batch * p.heads * p.tiles;
   const int grid = (int)(total < num_sms() ? total : num_sms());
   if (a->cols) {
