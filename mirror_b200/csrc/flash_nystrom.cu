@@ -589,17 +589,26 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tr.ev(40);
         const uint32_t aa = smem_u32(sTile + tb * 2 * BwdSmem::UNIT), ca = aa + BwdSmem::UNIT;
         int issued = 0;
+        // Descriptors are formed ONCE per tile / stage and advanced by compile-time constants per k-step (one uniform add each):
+        // this single thread's issue rate is on the critical path of every block (16-20 tcgen05.mma per 64-key block).
+        const uint64_t dA0 = desc_kmajor(aa, 0), dC0 = desc_kmajor(ca, 0);
         auto issue_sd = [&]() {
           const int buf = sdc & 1, st = sdc % nst;
           mbar_wait(&st_full[st], (sdc / nst) & 1);
           tc_fence_after();
           const uint32_t ba = smem_u32(sSt + st * BwdSmem::UNIT), da = ba + 2 * kHB;
-          for (int ks = 0; ks < nks; ++ks)
-            umma_f16(tmem_base + buf * 128, desc_kmajor(aa + (ks >> 2) * kTB, ks & 3), desc_kmajor(ba + (ks >> 2) * kHB, ks & 3), idesc_s,
-                     ks > 0 ? 1u : 0u);
-          for (int ks = 0; ks < nks; ++ks)
-            umma_f16(tmem_base + buf * 128 + 64, desc_kmajor(ca + (ks >> 2) * kTB, ks & 3), desc_kmajor(da + (ks >> 2) * kHB, ks & 3), idesc_s,
-                     ks > 0 ? 1u : 0u);
+          const uint64_t dB0 = desc_kmajor(ba, 0), dD0 = desc_kmajor(da, 0);
+          const uint32_t ts = tmem_base + buf * 128;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            if (ks < nks)
+              umma_f16(ts, dA0 + ((((ks >> 2) * kTB) + (ks & 3) * 32) >> 4), dB0 + ((((ks >> 2) * kHB) + (ks & 3) * 32) >> 4), idesc_s,
+                       ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            if (ks < nks)
+              umma_f16(ts + 64, dC0 + ((((ks >> 2) * kTB) + (ks & 3) * 32) >> 4), dD0 + ((((ks >> 2) * kHB) + (ks & 3) * 32) >> 4), idesc_s,
+                       ks > 0 ? 1u : 0u);
           umma_commit(&s_full[buf]);
           tr.ev(41);
           ++sdc;
@@ -614,15 +623,15 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           tr.ev(42);
           const uint32_t ba = smem_u32(sSt + st * BwdSmem::UNIT), da = ba + 2 * kHB;
+          const uint64_t dBm = desc_mnmajor(ba, kHB, 0), dDm = desc_mnmajor(da, kHB, 0);
+          const uint32_t tb_ = tmem_base + buf * 128;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)  // contraction over the block's 64 columns: 8 TMEM columns (16 bf16) of dS per step
-            umma_f16_ts(tmem_base + kCol1, tmem_base + buf * 128 + (kk >> 1) * 32 + (kk & 1) * 8, desc_mnmajor(ba, kHB, kk), idesc_o,
-                        (blk > 0 || kk > 0) ? 1u : 0u);
+            umma_f16_ts(tmem_base + kCol1, tb_ + (kk >> 1) * 32 + (kk & 1) * 8, dBm + kk * (2048 >> 4), idesc_o, (blk > 0 || kk > 0) ? 1u : 0u);
           if (COLS) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_f16_ts(tmem_base + kCol2, tmem_base + buf * 128 + 64 + (kk >> 1) * 32 + (kk & 1) * 8, desc_mnmajor(da, kHB, kk), idesc_o,
-                          (blk > 0 || kk > 0) ? 1u : 0u);
+              umma_f16_ts(tmem_base + kCol2, tb_ + 64 + (kk >> 1) * 32 + (kk & 1) * 8, dDm + kk * (2048 >> 4), idesc_o, (blk > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&st_empty[st]);
           tr.ev(43);
