@@ -135,6 +135,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // programmatic dependent launch (common.cuh): the setup above overlapped the previous grid's tail
+  pdl_launch_dependents();
   // TMEM columns: logits S[2] at 0 / 128, output accumulator at 256 (dpad <= 128), probabilities P[2] (bf16 pairs) at 384 / 448
   constexpr uint32_t kColO = 256, kColP = 384;
 
@@ -537,6 +539,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr uint32_t kCol1 = 256, kCol2 = 384;  // TMEM: (S | dP) buffers at [0,128) and [128,256); out1 at 256, out2 at 384
 
   if (warp == 0) {
@@ -809,8 +813,7 @@ extern "C" int mirror_flash_softmax_pv(const mirror_flash_args* a, mirror_stream
   if (once.first()) MB_CUDA(cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
   const long long total = (long long)p.batch * p.heads * p.tiles_r;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  flash_fwd_kernel<<<grid, kThreadsF, FwdSmem::TOTAL, STREAM>>>(tmX, tmY, tmV, p);
-  MB_LAUNCH_CHECK();
+  MB_CUDA(launch_pdl(flash_fwd_kernel, dim3(grid), dim3(kThreadsF), FwdSmem::TOTAL, STREAM, tmX, tmY, tmV, p));
   return 0;
 }
 
@@ -850,11 +853,11 @@ extern "C" int mirror_flash_bwd(const mirror_flash_bwd_args* a, mirror_stream_t 
   if (a->cols) {
     static DeviceOnce once;
     if (once.first()) MB_CUDA(cudaFuncSetAttribute(flash_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
-    flash_bwd_kernel<true><<<grid, kThreadsB, BwdSmem::TOTAL, STREAM>>>(tmA, tmB, tmC, tmD, p);
+    MB_CUDA(launch_pdl(flash_bwd_kernel<true>, dim3(grid), dim3(kThreadsB), BwdSmem::TOTAL, STREAM, tmA, tmB, tmC, tmD, p));
   } else {
     static DeviceOnce once;
     if (once.first()) MB_CUDA(cudaFuncSetAttribute(flash_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
-    flash_bwd_kernel<false><<<grid, kThreadsB, BwdSmem::TOTAL, STREAM>>>(tmA, tmB, tmC, tmD, p);
+    MB_CUDA(launch_pdl(flash_bwd_kernel<false>, dim3(grid), dim3(kThreadsB), BwdSmem::TOTAL, STREAM, tmA, tmB, tmC, tmD, p));
   }
   MB_LAUNCH_CHECK();
   return 0;

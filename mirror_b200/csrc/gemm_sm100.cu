@@ -555,6 +555,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // everything above overlapped the previous grid's tail; global memory is touched only below
+  pdl_launch_dependents();  // the next grid may be scheduled as our CTAs retire (it waits for our completion itself)
 
   const int tiles = p.tiles_m * p.tiles_n * p.batch1 * p.batch2;
   const int total = tiles * p.split_k;
@@ -908,6 +910,8 @@ gemm_tcgen05_multi_kernel(const __grid_constant__ MultiMaps maps, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // see gemm_tcgen05_kernel
+  pdl_launch_dependents();
   const int total = p.tiles_m * p.tiles_n * p.batch1 * p.batch2;
 
   if (warp == 0) {
@@ -1074,8 +1078,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.batch1 * p.batch2 * p.split_k;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC32, tmC16, p, vec_ok);
-  MB_LAUNCH_CHECK();
+  MB_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, tmA, tmB, tmC32, tmC16, p, vec_ok));
   return 0;
 }
 
@@ -1164,8 +1167,7 @@ int launch_multi(const MultiMaps& maps, const KParams& p, const MultiInfo& mi, i
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.batch1 * p.batch2;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(maps, p, mi, vec_ok);
-  MB_LAUNCH_CHECK();
+  MB_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, maps, p, mi, vec_ok));
   return 0;
 }
 
