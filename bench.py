@@ -558,8 +558,8 @@ def main():
                 "kernel": ("gemm_tcgen05_kernel<192,0,1,true,2> " if is_pinv else "gemm_tcgen05_kernel ") +
                           f"[batch {dom_sig[0]} x {dom_sig[1]}x{dom_sig[2]}x{dom_sig[3]} {dom_sig[4]}{dom_sig[5]}, {dom_sig[9]} term(s)]: the launch signature with the largest share of the step",
                 "achieved": dom_ach, "peak": sustained, "unit": "TFLOP/s", "frac": dom_ach / sustained,
-                "traffic": 262e6 if is_pinv and dom_sig[0] == 512 else None,
-                "traffic_source": "profiles/r1_ncu_epilogue_and_pinv.md §3: dram read+write per launch of this instantiation (ncu --set full), vs 453 MB operands+result" if is_pinv and dom_sig[0] == 512 else None,
+                "traffic": 261.5e6 if is_pinv and dom_sig[0] == 512 else None,
+                "traffic_source": "profiles/r2_ncu_pinv_gemm.md: dram read+write per launch of this instantiation (ncu --set full), vs 453 MB operands+result" if is_pinv and dom_sig[0] == 512 else None,
                 "flop_per_launch": dom_f / dom_c, "avg_launch_ms": dom_ms / dom_c, "launches_per_step": dom_c,
                 "share_of_step": dom_ms / inst_ms,
                 "peak_source": f"{src} sustained bf16 (MEASURED_PEAKS.json)",
