@@ -10,8 +10,9 @@
 and captures the whole sequence into one CUDA graph, so a step costs one ``cudaGraphLaunch`` on the host instead of ~630
 kernel launches (36 ms of Python / driver time per step: smaller per-GPU batches were host-bound).  What makes the capture
 valid:
-  * parameters, gradients and Adam moments live in flat fp32 buffers (``FlatParams``); ``p.data`` / ``p.grad`` are views, so
-    the optimizer is one HBM-bound kernel (csrc/optim.cu) and the gradient exchange one NCCL call;
+  * parameters and Adam moments live in flat fp32 buffers (``FlatParams``; ``p.data`` are views) and the gradients are gathered
+    into one with a multi-tensor copy, so the optimizer is one HBM-bound kernel (csrc/optim.cu) and the gradient exchange one
+    NCCL call;
   * every per-step scalar (learning rate, step count, clip coefficient) is read from device memory;
   * dropout masks are counter-based hashes of (seed, element); a device-side epoch counter is mixed into the seeds of the
     captured launches and bumped once per replay (``kernels.set_dropout_epoch``), torch's own generator (mask noise, the
@@ -47,12 +48,24 @@ class FlatParams:
         self.numel = n
         self.data = torch.zeros(n, device=dev, dtype=F32)
         self.grad = torch.zeros(n, device=dev, dtype=F32)
+        self.grad_views = []
         with torch.no_grad():
             for p, o in zip(self.params, self.offsets):
                 v = self.data[o:o + p.numel()].view(p.shape)
                 v.copy_(p.data)
                 p.data = v
-                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+                self.grad_views.append(self.grad[o:o + p.numel()].view(p.shape))
+
+    def gather_grads(self):
+        """flat.grad <- the parameters' .grad tensors, as one multi-tensor copy (parameters without a gradient: zeros).  Autograd
+        ASSIGNS a fresh gradient when .grad is None; accumulating into flat views instead would cost one add kernel per parameter
+        (~230 launches per step)."""
+        with torch.no_grad():
+            dst = [v for v, p in zip(self.grad_views, self.params) if p.grad is not None]
+            src = [p.grad for p in self.params if p.grad is not None]
+            if len(dst) != len(self.params):
+                self.grad.zero_()
+            torch._foreach_copy_(dst, src)
 
     def view_of(self, p, flat):
         i = next(i for i, q in enumerate(self.params) if q is p)
@@ -113,7 +126,8 @@ class GraphedStep:
         with torch.no_grad():
             if self.opt is not None and not self.dual and hasattr(model, "normalize_prototypes"):
                 model.normalize_prototypes()  # train_mirror.py:1133-1136
-            flat.grad.zero_()
+        for p in flat.params:
+            p.grad = None  # autograd then assigns (no accumulate kernels); under capture the new tensors come from the graph's pool
         if self.dual:
             we, re_ = model(self.wsi, self.rna)
             losses = (self.loss_fn(we, re_),)
@@ -123,10 +137,15 @@ class GraphedStep:
             losses = self.loss_fn(*out)
         losses[0].backward()
         with torch.no_grad():
+            if self.group is not None or self.opt is not None:
+                flat.gather_grads()
             if self.group is not None:  # DDP's gradient averaging as one flat all-reduce
                 import torch.distributed as dist
                 dist.all_reduce(flat.grad, group=self.group)
                 flat.grad.mul_(1.0 / self.world)
+                if self.opt is None:  # the caller's own optimizer reads p.grad: hand back the averaged gradient, like DDP
+                    torch._foreach_copy_([p.grad for p in flat.params if p.grad is not None],
+                                         [v for v, p in zip(flat.grad_views, flat.params) if p.grad is not None])
             sumsq = None
             if self.opt is not None:
                 if self.clip_grad is not None:
