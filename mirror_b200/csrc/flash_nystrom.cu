@@ -4,8 +4,11 @@
 //     attn3 = softmax(q_l k^T)   [m x n]   ->  kv  = attn3 v
 // never exist in HBM -- nor in shared memory: the probabilities are written back into TENSOR MEMORY as bf16 and consumed as
 // the A operand of the second tcgen05.mma (the "TS" form: A from TMEM, B from shared memory).
-// Forward: O = softmax(alpha X Y^T) V, logits tile in TMEM, two passes over the (cheap, K = head_dim) logits -- row maxima
-// first, then exp / row sums / P V -- so the accumulator never has to be rescaled.  Backward (flash_bwd below): logits and
+// Forward: O = softmax(alpha X Y^T) V, logits tile in TMEM, ONE pass over the key blocks: tensor-memory reads (~57 B/clk per SM,
+// tools/tmem_bw.cu) are what bounds these kernels, so every logit is read exactly once.  The exponentials are taken relative to
+// the running row maximum of the FIRST block and the reference is only moved (accumulator and row sums rescaled, a rare path)
+// when a later block exceeds it by more than 2^20: P = 2^(a2 (S - m_ref)) <= 2^20 is exact enough in bf16 / fp32 at any offset,
+// and O / l does not depend on the reference.  Backward (flash_bwd below): logits and
 // dP = dO V^T are recomputed per 128 x 64 block, dS = alpha P (dP - D) overwrites the logits in TMEM and feeds
 // dX += dS Y (row-stationary) or dY += dS^T X, dV += P^T dO (column-stationary).
 //
@@ -68,13 +71,16 @@ struct FwdSmem {
   static constexpr int X = 2 * 2 * kTB;   // two row tiles in flight x two K blocks
   static constexpr int Y = 2 * 2 * kTB;   // ring of two key blocks x two K blocks
   static constexpr int V = 2 * 2 * kTB;   // ring of two value blocks: two 64-column chunks [128 keys x 64] each
-  static constexpr int ROWS = 2 * 2 * 128 * 4;  // row maxima / row sums of the two column halves
+  static constexpr int ROWS = (2 * 2 * 128 + 2 * 128) * 4;  // block maxima of the two column halves (two parities), row sums of the halves
   static constexpr int BARS = 32 * 8 + 16;
   static constexpr int TOTAL = X + Y + V + ROWS + BARS + 1024;
 };
 
+// Two-pass variant (row maxima first, then exp / row sums / P V; the logits products are issued twice): faster when a row tile
+// has only a few key blocks (K-C: 3 blocks of landmarks per 128 tokens), where the single-pass kernel's per-block maximum exchange
+// and shorter software pipeline cost more than the second tensor-memory read (measured 0.44 vs 0.53 ms at the benchmark shape).
 __global__ void __launch_bounds__(kThreadsF, 1)
-flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmV,
+flash_fwd_twopass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmV,
                  const __grid_constant__ FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -336,6 +342,354 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       rowsum[hf * 128 + rl] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       named_bar_sync(1, 256);
+      if (warp == 2 && lane == 0) tr.ev(27);
+      const float l = rowsum[rl] + rowsum[128 + rl];
+      const float inv = 1.f / l;
+      // ---- epilogue: out = O / l (+ residual), bf16.  The accumulator is drained in 16-column pieces; the two warps of a lane
+      // quarter take alternate pieces, so both finish together.  Everything with a latency is issued up front: the residual
+      // pieces travel while the last P V products retire, the accumulator pieces are fetched with ONE wait.
+      bf16* orow = p.out + b * p.o_bs + h * p.o_hs + (long long)row * p.o_ld;
+      constexpr int kPieces = 4;  // d <= 128: at most four 16-column pieces per warp
+      uint4 rpre[kPieces][2];
+#pragma unroll
+      for (int i = 0; i < kPieces; ++i) {
+        const int c0 = hf * 16 + i * 32;
+        rpre[i][0] = rpre[i][1] = make_uint4(0u, 0u, 0u, 0u);
+        if (rrow && row_ok && c0 < p.d) {
+          rpre[i][0] = ldg_v4(rrow + c0);
+          if (c0 + 8 < p.d) rpre[i][1] = ldg_v4(rrow + c0 + 8);
+        }
+      }
+      mbar_wait(o_full, ti & 1);
+      tc_fence_after();
+      if (warp == 2 && lane == 0) tr.ev(28);
+      uint32_t oacc[kPieces][16];
+#pragma unroll
+      for (int i = 0; i < kPieces; ++i)
+        if (hf * 16 + i * 32 < p.d) tmem_ld_32x32_x16(lane_base + kColO + hf * 16 + i * 32, oacc[i]);
+      tmem_ld_wait();
+      if (warp == 2 && lane == 0) tr.ev(31);
+      tc_fence_before();  // the accumulator is in registers: the next tile's P V products may overwrite it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < kPieces; ++i) {
+          const int c0 = hf * 16 + i * 32;
+          if (c0 < p.d) {
+            const uint32_t rw[8] = {rpre[i][0].x, rpre[i][0].y, rpre[i][0].z, rpre[i][0].w, rpre[i][1].x, rpre[i][1].y, rpre[i][1].z, rpre[i][1].w};
+            uint32_t o[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              o[u] = pack_bf16(fmaf(__uint_as_float(oacc[i][2 * u]), inv, __uint_as_float(rw[u] << 16)),
+                               fmaf(__uint_as_float(oacc[i][2 * u + 1]), inv, __uint_as_float(rw[u] & 0xffff0000u)));
+            stg_v4(orow + c0, make_uint4(o[0], o[1], o[2], o[3]));
+            if (c0 + 8 < p.d) stg_v4(orow + c0 + 8, make_uint4(o[4], o[5], o[6], o[7]));
+          }
+        }
+      }
+      if (hf == 0 && row_ok && p.lse2) p.lse2[((long long)b * p.heads + h) * p.R + row] = m2 + fast_log2(l);
+      if (warp == 2 && lane == 0) tr.ev(29);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// Single-pass variant (see the header): long rows of key blocks (K-A: 18+ blocks of tokens per 128 landmarks).
+__global__ void __launch_bounds__(kThreadsF, 1)
+flash_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmV,
+                 const __grid_constant__ FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX = smem;
+  uint8_t* sY = sX + FwdSmem::X;
+  uint8_t* sV = sY + FwdSmem::Y;
+  float* pairmax = reinterpret_cast<float*>(sV + FwdSmem::V);  // [parity][half][128]
+  float* rowsum = pairmax + 512;                                // [half][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FwdSmem::V + FwdSmem::ROWS);
+  uint64_t* x_full = bars;          // [2]
+  uint64_t* x_empty = bars + 2;     // [2]
+  uint64_t* y_full = bars + 4;      // [2]
+  uint64_t* y_empty = bars + 6;     // [2]
+  uint64_t* s_full = bars + 8;      // [2]
+  uint64_t* s_empty = bars + 10;    // [2]
+  uint64_t* v_full = bars + 12;     // [2]
+  uint64_t* v_empty = bars + 14;    // [2]
+  uint64_t* p_full = bars + 16;     // [2]
+  uint64_t* p_empty = bars + 18;    // [2]
+  uint64_t* o_full = bars + 20;
+  uint64_t* o_empty = bars + 21;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.d + 63) / 64;      // 64-column K blocks of the head dim
+  const int nks = (p.d + 15) / 16;      // UMMA k-steps of the logits products
+  const int nvc = (p.dpad + 63) / 64;   // 64-column chunks of the value tile
+  const int total = p.batch * p.heads * p.tiles_r;
+  const int ns = p.nb;                  // S tiles per row tile: one per key block
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&x_full[i], 1);
+        mbar_init(&x_empty[i], 1);
+        mbar_init(&y_full[i], 1);
+        mbar_init(&y_empty[i], 1);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&s_empty[i], 8);
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_empty[i], 1);
+        mbar_init(&p_full[i], 8);
+        mbar_init(&p_empty[i], 1);
+      }
+      mbar_init(o_full, 1);
+      mbar_init(o_empty, 8);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // programmatic dependent launch (common.cuh): the setup above overlapped the previous grid's tail
+  pdl_launch_dependents();
+  // TMEM columns: logits S[2] at 0 / 128, output accumulator at 256 (dpad <= 128), probabilities P[2] (bf16 pairs) at 384 / 448
+  constexpr uint32_t kColO = 256, kColP = 384;
+
+  if (warp == 0) {
+    // ----------------------------------------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      Tracer tr;
+      tr.init(0);
+      uint32_t ycount = 0, vcount = 0, ti = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
+        const int rt = w % p.tiles_r;
+        const int bh = w / p.tiles_r;
+        const int h = bh % p.heads, b = bh / p.heads;
+        const int xb = ti & 1;
+        mbar_wait(&x_empty[xb], ((ti >> 1) & 1) ^ 1);
+        mbar_expect_tx(&x_full[xb], nkb * kTB);
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb) tma_load_4d(&tmX, &x_full[xb], sX + (xb * 2 + kb) * kTB, kb * 64, rt * 128, h, b);
+        tr.ev(1);
+        // loads are issued in the order the MMA warp consumes them: S(0), S(1), then per step [P V(s)], S(s+2).  ONE load site per
+        // operand and no unrolling: this warp's code shares the 32 KB instruction cache with the softmax warps' hot loops.
+#pragma unroll 1
+        for (int s = -2; s < ns; ++s) {
+          if (s >= 0) {
+            const int jb = s, st = vcount & 1;
+            mbar_wait(&v_empty[st], ((vcount >> 1) & 1) ^ 1);
+            mbar_expect_tx(&v_full[st], nvc * kTB);
+#pragma unroll 1
+            for (int c = 0; c < nvc; ++c) tma_load_4d(&tmV, &v_full[st], sV + (st * 2 + c) * kTB, c * 64, jb * 128, h, b);
+            tr.ev(3);
+            ++vcount;
+          }
+          if (s + 2 < ns) {
+            const int jb = s + 2, st = ycount & 1;
+            mbar_wait(&y_empty[st], ((ycount >> 1) & 1) ^ 1);
+            mbar_expect_tx(&y_full[st], nkb * kTB);
+#pragma unroll 1
+            for (int kb = 0; kb < nkb; ++kb) tma_load_4d(&tmY, &y_full[st], sY + (st * 2 + kb) * kTB, kb * 64, jb * 128, h, b);
+            tr.ev(2);
+            ++ycount;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ----------------------------------------------------------------------------------------------- MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_pv = make_idesc_bf16(128, p.dpad, 0, 1);
+      Tracer tr;
+      tr.init(1);
+      uint32_t scount = 0, pvcount = 0, ti = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
+        const int xb = ti & 1;
+        mbar_wait(&x_full[xb], (ti >> 1) & 1);
+        tc_fence_after();
+        const uint32_t xa = smem_u32(sX + xb * 2 * kTB);
+        tr.ev(10);
+#pragma unroll 1
+        for (int s = -2; s < ns; ++s) {  // S(0), S(1), then per step [P V(s)], S(s+2): one issue site each (code size)
+          if (s >= 0) {
+            const int pb = pvcount & 1;
+            if (s == 0) mbar_wait(o_empty, (ti & 1) ^ 1);  // the previous tile's epilogue has read the accumulator
+            mbar_wait(&p_full[pb], (pvcount >> 1) & 1);
+            tr.ev(15);
+            mbar_wait(&v_full[pb], (pvcount >> 1) & 1);
+            tc_fence_after();
+            tr.ev(12);
+            const uint32_t va = smem_u32(sV + pb * 2 * kTB);
+#pragma unroll 2
+            for (int kk = 0; kk < 8; ++kk)  // contraction over the block's 128 keys: 8 TMEM columns (16 bf16) of P per step
+              umma_f16_ts(tmem_base + kColO, tmem_base + kColP + pb * 64 + kk * 8, desc_mnmajor(va, kTB, kk), idesc_pv,
+                          (s > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(&p_empty[pb]);
+            umma_commit(&v_empty[pb]);
+            ++pvcount;
+          }
+          if (s + 2 < ns) {
+            const int sb = scount & 1;  // logits buffer and Y ring stage advance together
+            mbar_wait(&s_empty[sb], ((scount >> 1) & 1) ^ 1);
+            tr.ev(14);
+            mbar_wait(&y_full[sb], (scount >> 1) & 1);
+            tc_fence_after();
+            tr.ev(11);
+            const uint32_t ya = smem_u32(sY + sb * 2 * kTB);
+#pragma unroll 2
+            for (int ks = 0; ks < nks; ++ks)
+              umma_f16(tmem_base + sb * 128, desc_kmajor(xa + (ks >> 2) * kTB, ks & 3), desc_kmajor(ya + (ks >> 2) * kTB, ks & 3), idesc_s,
+                       ks > 0 ? 1u : 0u);
+            umma_commit(&y_empty[sb]);
+            umma_commit(&s_full[sb]);
+            ++scount;
+          }
+          if (s + 3 == ns) umma_commit(&x_empty[xb]);  // every logits product of this row tile has been issued
+        }
+        umma_commit(o_full);
+        tr.ev(13);
+      }
+    }
+  } else {
+    // ----------------------------------------------------------------------------------------------- softmax / epilogue warps
+    // eight warps: two per TMEM lane quarter, each owning 64 of a key block's 128 columns (thread = row x column half)
+    const int q = warp & 3, hf = (warp - 2) >> 2;
+    const int rl = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
+    const float a2 = p.alpha * kLog2e;
+    Tracer tr;
+    tr.init(2);
+    uint32_t scount = 0, pvcount = 0, ti = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
+      const int rt = w % p.tiles_r;
+      const int bh = w / p.tiles_r;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const int row = rt * 128 + rl;
+      const bool row_ok = row < p.R;
+      const bf16* rrow = p.res ? p.res + b * p.r_bs + h * p.r_hs + (long long)row * p.r_ld : nullptr;
+      if (rrow && row_ok) prefetch_l2(rrow + (hf * 64 < p.d ? hf * 64 : 0));
+      if (warp == 2 && lane == 0) tr.ev(33);
+      // ---- one pass over the key blocks: logits -> registers (the ONLY tensor-memory read of a logit), block maximum exchanged
+      // with the partner warp of the lane quarter, P = 2^(a2 (S - m_ref)) -> bf16 -> tensor memory, row sums.
+      float m_ref = -INFINITY;  // reference maximum (raw logits; alpha > 0 commutes with max)
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      const int pair_bar = 2 + q;  // named barrier of the two warps that share this lane quarter
+      for (int jb = 0; jb < p.nb; ++jb, ++scount, ++pvcount) {
+        const int sb = scount & 1, pb = pvcount & 1;
+        mbar_wait(&s_full[sb], (scount >> 1) & 1);
+        tc_fence_after();
+        if (warp == 2 && lane == 0) tr.ev(23);
+        const int cvalid = p.C - jb * 128 - hf * 64;  // keys of this warp's half that exist
+        uint32_t a0[32], a1[32];
+        if (cvalid > 0) tmem_ld_32x32(lane_base + sb * 128 + hf * 64, a0);
+        if (cvalid > 32) tmem_ld_32x32(lane_base + sb * 128 + hf * 64 + 32, a1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sb]);  // the logits are in registers: the buffer may take S(jb + 2)
+        float mloc = -INFINITY;
+        if (cvalid >= 64) {  // full half block (every block of the model's shapes): no per-element masks
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            mloc = fmaxf(mloc, fmaxf(__uint_as_float(a0[e]), __uint_as_float(a0[e + 1])));
+            mloc = fmaxf(mloc, fmaxf(__uint_as_float(a1[e]), __uint_as_float(a1[e + 1])));
+          }
+        } else {  // ragged tail of the last key block (cold)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (e < cvalid) mloc = fmaxf(mloc, __uint_as_float(a0[e]));
+            if (e + 32 < cvalid) mloc = fmaxf(mloc, __uint_as_float(a1[e]));
+          }
+        }
+        float* pm = pairmax + (jb & 1) * 256;  // parity-double-buffered: the slot is rewritten two blocks (= one pair barrier) later
+        pm[hf * 128 + rl] = mloc;
+        named_bar_sync(pair_bar, 64);
+        const float mblk = fmaxf(pm[rl], pm[128 + rl]);
+        // the reference only moves when a block exceeds it by more than 2^20 (or at the first block)
+        const bool move = jb == 0 || (mblk - m_ref) * a2 > 20.f;
+        if (jb > 0 && __any_sync(0xffffffffu, move)) {
+          // rare path: rescale this warp's half of the accumulator columns and the row sums.  All P V products issued so far
+          // (blocks < jb) must have retired: the last one releases p_empty of its buffer.
+          const uint32_t prev = pvcount - 1;
+          mbar_wait(&p_empty[prev & 1], (prev >> 1) & 1);
+          tc_fence_after();
+          const float f = move ? fast_exp2((m_ref - mblk) * a2) : 1.f;
+#pragma unroll 1
+          for (int c0 = hf * 16; c0 < p.dpad; c0 += 32) {
+            uint32_t r[16];
+            tmem_ld_32x32_x16(lane_base + kColO + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * f);
+            tmem_st_32x32_x16(lane_base + kColO + c0, r);
+          }
+          tmem_st_wait();
+#pragma unroll
+          for (int e = 0; e < 4; ++e) l4[e] *= f;
+        }
+        if (move) m_ref = mblk;
+        const float m2 = m_ref * a2;
+        mbar_wait(&p_empty[pb], ((pvcount >> 1) & 1) ^ 1);  // P V of two blocks ago has consumed this probability buffer
+        tc_fence_after();
+        uint32_t wd[16];
+        if (cvalid >= 64) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float x0 = fast_exp2(fmaf(a2, __uint_as_float(a0[2 * u]), -m2)), x1 = fast_exp2(fmaf(a2, __uint_as_float(a0[2 * u + 1]), -m2));
+            l4[u & 3] += x0 + x1;
+            wd[u] = pack_bf16(x0, x1);
+          }
+          tmem_st_32x32_x16(lane_base + kColP + pb * 64 + hf * 32, wd);
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float x0 = fast_exp2(fmaf(a2, __uint_as_float(a1[2 * u]), -m2)), x1 = fast_exp2(fmaf(a2, __uint_as_float(a1[2 * u + 1]), -m2));
+            l4[u & 3] += x0 + x1;
+            wd[u] = pack_bf16(x0, x1);
+          }
+          tmem_st_32x32_x16(lane_base + kColP + pb * 64 + hf * 32 + 16, wd);
+        } else {  // ragged tail of the last key block (cold)
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float x0 = 2 * u < cvalid ? fast_exp2(fmaf(a2, __uint_as_float(a0[2 * u]), -m2)) : 0.f;
+            const float x1 = 2 * u + 1 < cvalid ? fast_exp2(fmaf(a2, __uint_as_float(a0[2 * u + 1]), -m2)) : 0.f;
+            l4[u & 3] += x0 + x1;
+            wd[u] = pack_bf16(x0, x1);
+          }
+          tmem_st_32x32_x16(lane_base + kColP + pb * 64 + hf * 32, wd);
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float x0 = 2 * u + 32 < cvalid ? fast_exp2(fmaf(a2, __uint_as_float(a1[2 * u]), -m2)) : 0.f;
+            const float x1 = 2 * u + 33 < cvalid ? fast_exp2(fmaf(a2, __uint_as_float(a1[2 * u + 1]), -m2)) : 0.f;
+            l4[u & 3] += x0 + x1;
+            wd[u] = pack_bf16(x0, x1);
+          }
+          tmem_st_32x32_x16(lane_base + kColP + pb * 64 + hf * 32 + 16, wd);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[pb]);
+        if (warp == 2 && lane == 0) tr.ev(26);
+      }
+      const float m2 = m_ref * a2;
+      rowsum[hf * 128 + rl] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      named_bar_sync(pair_bar, 64);
       if (warp == 2 && lane == 0) tr.ev(27);
       const float l = rowsum[rl] + rowsum[128 + rl];
       const float inv = 1.f / l;
@@ -813,7 +1167,13 @@ extern "C" int mirror_flash_softmax_pv(const mirror_flash_args* a, mirror_stream
   if (once.first()) MB_CUDA(cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
   const long long total = (long long)p.batch * p.heads * p.tiles_r;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  MB_CUDA(launch_pdl(flash_fwd_kernel, dim3(grid), dim3(kThreadsF), FwdSmem::TOTAL, STREAM, tmX, tmY, tmV, p));
+  if (p.nb <= 4) {
+    static DeviceOnce once2;
+    if (once2.first()) MB_CUDA(cudaFuncSetAttribute(flash_fwd_twopass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+    MB_CUDA(launch_pdl(flash_fwd_twopass_kernel, dim3(grid), dim3(kThreadsF), FwdSmem::TOTAL, STREAM, tmX, tmY, tmV, p));
+  } else {
+    MB_CUDA(launch_pdl(flash_fwd_kernel, dim3(grid), dim3(kThreadsF), FwdSmem::TOTAL, STREAM, tmX, tmY, tmV, p));
+  }
   return 0;
 }
 

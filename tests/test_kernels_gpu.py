@@ -281,6 +281,28 @@ def test_flash_softmax_pv(B, E, n, m):
         close(a_gpu[4], a_cpu[4], 8e-3, "out")
 
 
+@pytest.mark.parametrize("keys,d", [(640, 96), (400, 48)])
+def test_flash_softmax_pv_moving_reference(keys, d):
+    """The single-pass forward takes exponentials relative to the first key block's row maximum and rescales accumulator and row
+    sums only when a later block exceeds it by more than 2^20: keys whose magnitude grows 8x per block of 128 force that path in
+    every block (and a shrinking sequence never takes it); both must equal the exact two-pass softmax."""
+    B, h, R = 2, 3, 300
+    for grow in (8.0, 0.125):
+        x = (rn(B, h, R, d, seed=21) * 0.5).to(BF16)
+        scale = torch.tensor([grow ** (j // 128) for j in range(keys)]).view(1, 1, keys, 1)
+        y = (rn(B, h, keys, d, seed=22) * 0.5 * scale).to(BF16)
+        v = rn(B, h, keys, d, seed=23).to(BF16)
+        alpha = d ** -0.5
+        a_cpu = (x, y, v, alpha, torch.zeros(B, h, R, d, dtype=BF16), None)
+        a_gpu = to_dev(a_cpu)
+        l_cpu = EMU.flash_softmax_pv(*a_cpu)
+        l_gpu = K.flash_softmax_pv(*a_gpu)
+        torch.cuda.synchronize()
+        assert torch.isfinite(a_gpu[4].float()).all()
+        close(l_gpu, l_cpu, 2e-5, "lse2")
+        close(a_gpu[4], a_cpu[4], 8e-3, "out")
+
+
 @pytest.mark.parametrize("B,E,n,m", [(2, 768, 2304, 384), (1, 768, 768, 384), (3, 192, 192, 96), (2, 192, 96, 96), (1, 384, 960, 192)])
 def test_flash_bwd(B, E, n, m):
     """csrc/flash_nystrom.cu backward, both orientations, for both Nystrom products: recomputed probabilities, dS through shared
