@@ -838,7 +838,10 @@ __device__ __forceinline__ void bwd_store_out(const BwdOut& o, uint32_t taddr, i
   }
 }
 
-template <bool COLS>
+// NKS: k-steps (of 16) of the head dim when known at compile time (6: the model's d = 96), 0 = run-time count.  The issue loops of
+// the MMA warp are on the critical path of every block AND the kernel has to stay inside the 32 KB instruction cache: an exact
+// unroll is shorter than a predicated unroll by eight.
+template <bool COLS, int NKS>
 __global__ void __launch_bounds__(kThreadsB, 1)
 flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ BwdParams p) {
@@ -860,7 +863,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.d + 63) / 64;
-  const int nks = (p.d + 15) / 16;
+  const int nks = NKS ? NKS : (p.d + 15) / 16;
   const int total = p.batch * p.heads * p.tiles;
   const int ntb = p.ntb, nst = p.nst;
 
@@ -958,13 +961,13 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t dB0 = desc_kmajor(ba, 0), dD0 = desc_kmajor(da, 0);
           const uint32_t ts = tmem_base + buf * 128;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            if (ks < nks)
+          for (int ks = 0; ks < (NKS ? NKS : 8); ++ks)
+            if (NKS || ks < nks)
               umma_f16(ts, dA0 + ((((ks >> 2) * kTB) + (ks & 3) * 32) >> 4), dB0 + ((((ks >> 2) * kHB) + (ks & 3) * 32) >> 4), idesc_s,
                        ks > 0 ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            if (ks < nks)
+          for (int ks = 0; ks < (NKS ? NKS : 8); ++ks)
+            if (NKS || ks < nks)
               umma_f16(ts + 64, dC0 + ((((ks >> 2) * kTB) + (ks & 3) * 32) >> 4), dD0 + ((((ks >> 2) * kHB) + (ks & 3) * 32) >> 4), idesc_s,
                        ks > 0 ? 1u : 0u);
           umma_commit(&s_full[buf]);
@@ -1210,16 +1213,15 @@ extern "C" int mirror_flash_bwd(const mirror_flash_bwd_args* a, mirror_stream_t 
   p.nst = 4;
   const long long total = (long long)p.batch * p.heads * p.tiles;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  if (a->cols) {
-    static DeviceOnce once;
-    if (once.first()) MB_CUDA(cudaFuncSetAttribute(flash_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
-    MB_CUDA(launch_pdl(flash_bwd_kernel<true>, dim3(grid), dim3(kThreadsB), BwdSmem::TOTAL, STREAM, tmA, tmB, tmC, tmD, p));
-  } else {
-    static DeviceOnce once;
-    if (once.first()) MB_CUDA(cudaFuncSetAttribute(flash_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
-    MB_CUDA(launch_pdl(flash_bwd_kernel<false>, dim3(grid), dim3(kThreadsB), BwdSmem::TOTAL, STREAM, tmA, tmB, tmC, tmD, p));
-  }
-  MB_LAUNCH_CHECK();
+  auto go = [&](auto kern) -> int {
+    MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));  // idempotent, cheap
+    MB_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreadsB), BwdSmem::TOTAL, STREAM, tmA, tmB, tmC, tmD, p));
+    return 0;
+  };
+  const bool k6 = (p.d + 15) / 16 == 6;
+  rc = a->cols ? (k6 ? go(flash_bwd_kernel<true, 6>) : go(flash_bwd_kernel<true, 0>))
+               : (k6 ? go(flash_bwd_kernel<false, 6>) : go(flash_bwd_kernel<false, 0>));
+  if (rc) return rc;
   return 0;
 }
 
