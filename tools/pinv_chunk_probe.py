@@ -33,7 +33,7 @@ def chain(chunk):
 
 
 flop = 24 * 2.0 * BH * m ** 3
-for chunk in (BH, 256, 148, 128, 99, 74, 64, 49, 37, 25):
+for chunk in [int(c) for c in __import__("os").environ.get("CHUNKS", "512,256,148,128,99,74,64,49,37,25").split(",")]:
     if chunk > BH:
         continue
     chain(chunk)
