@@ -5,18 +5,17 @@ allocator), extracts raw pointers / strides and enqueues the kernel on the
 current CUDA stream.  There is no CPU or eager fallback: a missing library or a
 non-CUDA tensor raises.
 
-``_TEST_BACKEND`` exists for the CPU unit tests only (tests/emu_backend.py
-injects a torch re-statement of each entry point so the host logic and the
-hand-written backward passes can be checked against the oracle without a GPU).
-Product code never sets it.
+(The CPU unit tests replace these functions from the outside --
+tests/emu_backend.py monkeypatches a torch re-statement of each entry point
+onto this module -- so that the host logic and the hand-written backward passes
+can be checked against the oracle without a GPU.  Nothing in this package
+knows about that.)
 """
 import ctypes
 
 import torch
 
 from . import _lib
-
-_TEST_BACKEND = None  # set by tests/emu_backend.py only
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 LAUNCHES = [0]  # number of kernels enqueued (bench.py reports it as gpu_launches)
@@ -76,8 +75,6 @@ GEMM_NORMAL, GEMM_ROWSTATS, GEMM_SOFTMAX, GEMM_ROWDOT, GEMM_SOFTMAX_BWD, GEMM_SO
 
 def gemm_nparts(n):
     """Partial-statistics slots per row of an N-column product (two per N tile of the tcgen05 kernel)."""
-    if _TEST_BACKEND is not None:
-        return _TEST_BACKEND.gemm_nparts(n)
     return int(_lib.fn("mirror_gemm_nparts")(n))
 
 
@@ -96,11 +93,6 @@ def gemm(a, b, *, out_f32=None, out_bf16=None, alpha=1.0, bias=None, act=ACT_NON
     five further operand pairs with the same M, N and batch dims, accumulated into the same tile (one epilogue pass).
     ``mode`` / ``stats``: fused row-softmax epilogues (GEMM_ROWSTATS .. GEMM_SOFTMAX_BWD), stats = softmax_stats(...).
     """
-    if _TEST_BACKEND is not None:
-        return _TEST_BACKEND.gemm(a, b, out_f32=out_f32, out_bf16=out_bf16, alpha=alpha, bias=bias, act=act,
-                                  drop_p=drop_p, drop_seed=drop_seed, res=res, gamma=gamma, beta=beta, split_k=split_k,
-                                  diag=diag, more=more, res2=res2, gamma2=gamma2, res_row_div=res_row_div, mode=mode,
-                                  stats=stats)
     nterms = 1 + (len(more) if more else 0)
     terms = (_lib.GemmArgs * nterms)()
     g = terms[0]
@@ -162,12 +154,8 @@ import functools
 
 
 def _op(f):
-    @functools.wraps(f)
-    def wrapper(*a, **k):
-        if _TEST_BACKEND is not None:
-            return getattr(_TEST_BACKEND, f.__name__)(*a, **k)
-        return f(*a, **k)
-    return wrapper
+    """marks a tensor-level entry point (one C-ABI call each); no behaviour of its own"""
+    return f
 
 
 def _p(t, dtype=None):
@@ -691,8 +679,6 @@ def loss_combine(terms5, weights):
 # ---- step tail (csrc/optim.cu) and graph-safe dropout -------------------------------------------------------------------
 def set_dropout_epoch(counter):
     """Install (or, with None, remove) the int64 DEVICE counter that every dropout launch mixes into its seed (graph replay)."""
-    if _TEST_BACKEND is not None:
-        return _TEST_BACKEND.set_dropout_epoch(counter)
     if counter is not None:
         _cuda(counter, torch.int64)
     _lib.check(_lib.fn("mirror_set_dropout_epoch")(counter.data_ptr() if counter is not None else None), "set_dropout_epoch")
