@@ -1061,7 +1061,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (COLS) {
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            const float2 c0 = cs[2 * u], c1 = cs[2 * u + 1];
+            const float4 cc = reinterpret_cast<const float4*>(cs)[u];  // (lse, alpha dot) of two columns in one 16-byte broadcast load
+            const float2 c0 = make_float2(cc.x, cc.y), c1 = make_float2(cc.z, cc.w);
             const float p0 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u]), -c0.x));
             const float p1 = fast_exp2(fmaf(a2, __uint_as_float(sa[2 * u + 1]), -c1.x));
             wpp[u] = pack_bf16(p0, p1);
