@@ -502,6 +502,16 @@ def main():
     e2e_ms = float(t) / args.steps
     e2e_val = world * B / (e2e_ms / 1e3)
 
+    kernels_per_replay = gs.kernels_per_replay if args.graph else 0
+    if args.graph:  # the timed arms are done: release the graph and its private memory pool (at 16 384 patches x 64 slides it holds
+        gs.close()  # 87 GB, and the eagerly launched instrumented step below needs as much again)
+        for p_ in model.parameters():
+            p_.grad = None
+        del gs, step, loss
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
     # ---- roofline: one instrumented (eager-launched) step with CUDA events around every tcgen05 GEMM launch
     sustained, burst, hbm, src = peaks()
     rec = []
@@ -592,9 +602,7 @@ def main():
                                     "sample": f"1 warm-up + 3 timed steps of {args.cpu_batch} slides (same N/Dw/Dr, fp32 oracle port, dropout off, "
                                               f"{time.time() - t0:.0f} s of CPU work)"}
         print(json.dumps(line), flush=True)
-    if args.graph:
-        gs.close()  # before the communicator goes away: the graph holds NCCL kernels
-    if world > 1:
+    if world > 1:  # (the graph, which holds NCCL kernels, was released above: before the communicator goes away)
         dist.barrier()
         torch.cuda.synchronize()
         dist.destroy_process_group()

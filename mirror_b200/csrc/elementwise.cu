@@ -289,6 +289,93 @@ __global__ void rank_mask_kernel(const float* __restrict__ noise, int N, int kee
   }
 }
 
+// The same mask in O(N) per slide for long bags (N = 16 384: the counting kernel above needs N^2 = 2.7e8 compares per slide):
+// radix select of the keep-th smallest noise value (four 8-bit passes over order-preserving integer keys, histogram in shared
+// memory), then one pass that keeps everything below it and the first `quota` elements EQUAL to it in index order -- exactly
+// the stable double argsort of the reference, ties included.
+__device__ __forceinline__ unsigned int order_key(float x) {
+  const unsigned int u = __float_as_uint(x + 0.f);  // -0 -> +0: equal as floats, so equal as keys
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending float order == ascending unsigned order
+}
+__global__ void __launch_bounds__(1024)
+rank_mask_select_kernel(const float* __restrict__ noise, int N, int keep, float* __restrict__ mask) {
+  extern __shared__ unsigned int sk[];  // N keys (later: the 0/1 results)
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_k, s_less;
+  __shared__ unsigned int wsum[32];
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const float* nb = noise + (long long)b * N;
+  float* mb_ = mask + (long long)b * N;
+  if (keep <= 0 || keep >= N) {
+    for (int i = tid; i < N; i += nt) mb_[i] = keep <= 0 ? 1.f : 0.f;
+    return;
+  }
+  for (int i = tid; i < N; i += nt) sk[i] = order_key(nb[i]);
+  if (tid == 0) { s_prefix = 0u; s_k = (unsigned int)(keep - 1); s_less = 0u; }
+  __syncthreads();
+  unsigned int pmask = 0u;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 256; i += nt) hist[i] = 0u;
+    __syncthreads();
+    const unsigned int prefix = s_prefix;
+    for (int i = tid; i < N; i += nt) {
+      const unsigned int key = sk[i];
+      if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {  // 256 bins: a serial walk is ~1 us per pass
+      unsigned int k = s_k, cum = 0u;
+      int bin = 0;
+      for (; bin < 256; ++bin) {
+        if (cum + hist[bin] > k) break;
+        cum += hist[bin];
+      }
+      s_prefix = prefix | ((unsigned int)bin << shift);
+      s_k = k - cum;
+      s_less += cum;
+    }
+    pmask |= 0xFFu << shift;
+    __syncthreads();
+  }
+  const unsigned int vstar = s_prefix;                       // key of the element of rank keep - 1
+  const unsigned int quota = (unsigned int)keep - s_less;    // how many elements equal to it are kept (>= 1)
+  // order of the equal elements by index: contiguous chunk per thread, exclusive block scan of the per-chunk counts
+  const int chunk = (N + nt - 1) / nt;
+  const int i0 = min(N, tid * chunk), i1 = min(N, i0 + chunk);
+  unsigned int cnt = 0u;
+  for (int i = i0; i < i1; ++i) cnt += sk[i] == vstar;
+  unsigned int incl = cnt;
+  const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    unsigned int v = lane < (nt >> 5) ? wsum[lane] : 0u, iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, iv, o);
+      if (lane >= o) iv += t;
+    }
+    wsum[lane] = iv - v;  // exclusive prefix of the warp sums
+  }
+  __syncthreads();
+  unsigned int seen = wsum[w] + incl - cnt;  // equal elements before this thread's chunk
+  for (int i = i0; i < i1; ++i) {
+    const unsigned int key = sk[i];
+    unsigned int m;
+    if (key == vstar) m = seen++ >= quota;
+    else m = key > vstar;
+    sk[i] = m;
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += nt) mb_[i] = sk[i] ? 1.f : 0.f;
+}
+
 // r[b,t,e] = (t >= first && mask[b,t-first] ? tok[e*tok_stride] : r[b,t,e]) + pos[t,e]
 __global__ void mask_pos_fwd_kernel(float* __restrict__ r, const float* __restrict__ mask, const float* __restrict__ tok,
                                     int tok_stride, const float* __restrict__ pos, int B, int T, int E, int first) {
@@ -587,7 +674,13 @@ extern "C" int mirror_rank_mask(const float* noise, int32_t B, int32_t N, int32_
   if (once.first()) {
     MB_CUDA(cudaFuncSetAttribute(rank_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
-  rank_mask_kernel<<<B, 512, smem, STREAM>>>(noise, N, keep, mask);
+  if (N >= 1024) {  // long rows: O(N) radix select; short rows: the N^2 counting kernel is faster than four histogram passes
+    static DeviceOnce once2;
+    if (once2.first()) MB_CUDA(cudaFuncSetAttribute(rank_mask_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    rank_mask_select_kernel<<<B, 1024, smem, STREAM>>>(noise, N, keep, mask);
+  } else {
+    rank_mask_kernel<<<B, 512, smem, STREAM>>>(noise, N, keep, mask);
+  }
   MB_LAUNCH_CHECK();
   return 0;
 }

@@ -126,6 +126,18 @@ def test_rank_mask(N, keep):
     assert int(m.sum()) == 4 * (N - keep)
 
 
+@pytest.mark.parametrize("N,keep", [(1024, 256), (2048, 512), (4099, 1024), (16384, 4096), (3000, 0), (3000, 3000), (2048, 1), (2048, 2047)])
+def test_rank_mask_radix_select_long_rows(N, keep):
+    """N >= 1024 takes the O(N) radix-select kernel: bit-equal to the stable double argsort, with heavy ties (quantised noise:
+    the tie quota and the index order of the equal elements decide), negative values and the keep = 0 / N edges"""
+    g = torch.Generator().manual_seed(N + keep)
+    cases = [torch.rand(3, N, generator=g), torch.randint(0, 7, (3, N), generator=g).float() / 7.0, torch.randn(3, N, generator=g),
+             torch.zeros(2, N)]
+    for noise in cases:
+        m, _ = both("rank_mask", (noise, keep), tol=0)
+        assert int(m.sum()) == noise.shape[0] * (N - keep)
+
+
 def test_rank_mask_ties_are_stable():
     noise = torch.zeros(2, 64)
     m, _ = both("rank_mask", (noise, 16), tol=0)
