@@ -10,7 +10,7 @@ from mirror_b200.losses import MIRRORLoss  # noqa: E402
 from mirror_b200.models import MIRROR  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-N, Dw, Dr = 2048, 768, 10234
+N, Dw, Dr = (int(sys.argv[2]) if len(sys.argv) > 2 else 2048), 768, 10234
 dev = torch.device("cuda")
 torch.manual_seed(0)
 model = MIRROR(wsi_embed_dim=Dw, rna_embed_dim=Dr, embed_dim=768, wsi_num_tokens=N, rna_mlp_ratio=4.0, rna_norm_layer="layernorm",
