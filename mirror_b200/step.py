@@ -3,7 +3,8 @@
 ``GraphedStep`` runs, in the reference trainer's order (train_mirror.py:1133-1136, 1144-1230, 1254-1274):
 
     prototype row-normalisation -> forward (autocast-free: the kernels own their precision plan) -> loss -> backward
-    -> gradient averaging over the data-parallel group (one flat all-reduce) -> clip_grad (mode "norm") -> Adam
+    -> gradient averaging over the data-parallel group (bucketed all-reduces of a flat buffer on a side stream, launched by
+    parameter hooks while the backward is still running) -> clip_grad (mode "norm") -> Adam
     -> logit_scale clamp -> the six loss scalars + exp(logit_scale) + gradient norm packed into one tensor (one D2H copy
     instead of the trainer's seven ``.item()`` syncs)
 
@@ -77,7 +78,9 @@ class GraphedStep:
 
     model      : ``MIRROR`` (loss_fn = ``MIRRORLoss``) or ``MIRRORDualEncoder`` with ``dual=True`` (loss_fn = ``InfoNCE``)
     example    : (wsi [B,N,Dw], rna [B,Dr]) device tensors fixing the static shapes
-    group      : data-parallel process group (None = single process); gradients are averaged over it like DDP does
+    group      : data-parallel process group (None = single process); gradients are averaged over it like DDP does: buckets of
+                 ``bucket_mb`` MB of the flat gradient buffer (last parameters first) are all-reduced on a side stream as soon as
+                 the backward has produced their gradients, overlapping the rest of the backward -- also inside the graph
     optimizer  : None (forward + backward only, the benchmark's "optimizer excluded" step) or a dict
                  ``lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False`` (torch.optim.Adam / AdamW semantics)
     clip_grad  : max gradient norm (clip_mode "norm") or None
@@ -87,7 +90,7 @@ class GraphedStep:
     STATS = ("total", "alignment", "wsi_retention", "rna_retention", "style", "cluster", "logit_scale_exp", "grad_norm")
 
     def __init__(self, model, loss_fn, example, dual=False, group=None, optimizer=None, clip_grad=None, mask_ratios=(0.75, 0.75),
-                 noise=None, graph=True, warmup=3):
+                 noise=None, graph=True, warmup=3, bucket_mb=50):
         self.model, self.loss_fn, self.dual, self.group = model, loss_fn, dual, group
         self.opt, self.clip_grad, self.ratios, self.noise = optimizer, clip_grad, mask_ratios, noise
         wsi, rna = example
@@ -112,12 +115,85 @@ class GraphedStep:
         self.epoch = torch.zeros(1, device=dev, dtype=torch.int64) if dev.type == "cuda" else None
         self.graph = None
         self.kernels_per_replay = 0
+        self._hooks = []
+        if group is not None:
+            self._make_buckets(bucket_mb)
         if graph:
             if dev.type != "cuda":
                 raise RuntimeError("CUDA graph capture needs CUDA tensors")
             self._capture(example, warmup)
 
     # ------------------------------------------------------------------------------------------------------------
+    def _make_buckets(self, bucket_mb):
+        """Contiguous slices of the flat gradient buffer, filled from the LAST parameter backwards (the order the backward produces
+        gradients in, roughly), each reduced as soon as all of its parameters have their gradient."""
+        import torch.distributed as dist
+        flat = self.flat
+        cap = max(1, int(bucket_mb)) * (1 << 20) // 4
+        self.buckets = []  # dicts: lo, hi (element range of flat.grad), idx (parameter indices)
+        hi = flat.numel
+        idx = []
+        for i in range(len(flat.params) - 1, -1, -1):
+            idx.append(i)
+            lo = flat.offsets[i]
+            if hi - lo >= cap or i == 0:
+                self.buckets.append(dict(lo=lo, hi=hi, idx=idx))
+                hi, idx = lo, []
+        self._bucket_of = {}
+        for b, bk in enumerate(self.buckets):
+            for i in bk["idx"]:
+                self._bucket_of[i] = b
+        self._pending = [0] * len(self.buckets)
+        self._done = [True] * len(self.buckets)
+        dev = flat.data.device
+        self._side = torch.cuda.Stream(dev) if dev.type == "cuda" else None
+        self._avg = dist.get_backend(self.group) == "nccl"  # ReduceOp.AVG exists for NCCL only
+        for i, p in enumerate(flat.params):
+            self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, i=i: self._grad_ready(i)))
+
+    def _grad_ready(self, i):
+        b = self._bucket_of[i]
+        if self._done[b]:
+            return  # a backward outside step(): nothing to do
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._reduce_bucket(b)
+
+    def _reduce_bucket(self, b):
+        """gather the bucket's gradients into the flat buffer (one multi-tensor copy on the backward's stream), then all-reduce the
+        slice on the side stream"""
+        import torch.distributed as dist
+        bk, flat = self.buckets[b], self.flat
+        with torch.no_grad():
+            have = [i for i in bk["idx"] if flat.params[i].grad is not None]
+            if len(have) != len(bk["idx"]):
+                flat.grad[bk["lo"]:bk["hi"]].zero_()
+            if have:
+                torch._foreach_copy_([flat.grad_views[i] for i in have], [flat.params[i].grad for i in have])
+            sl = flat.grad[bk["lo"]:bk["hi"]]
+            op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+            if self._side is None:
+                dist.all_reduce(sl, op=op, group=self.group)
+            else:
+                cur = torch.cuda.current_stream()
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(ev)
+                    dist.all_reduce(sl, op=op, group=self.group)
+        self._done[b] = True
+
+    def _finish_reduction(self):
+        for b in range(len(self.buckets)):
+            if not self._done[b]:  # parameters without a gradient in this step
+                self._reduce_bucket(b)
+        if self._side is not None:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream().wait_event(ev)
+        if not self._avg:
+            self.flat.grad.mul_(1.0 / self.world)
+
     def set_lr(self, lr: float):
         self.lr.fill_(float(lr))  # device scalar: the captured Adam launch reads it at replay time
 
@@ -135,14 +211,17 @@ class GraphedStep:
             out = model(self.wsi, self.rna, self.ratios[0], self.ratios[1], noise=self.noise) if self.noise is not None else \
                 model(self.wsi, self.rna, self.ratios[0], self.ratios[1])
             losses = self.loss_fn(*out)
+        if self.group is not None:  # arm the buckets: the parameters' post-accumulate hooks launch the all-reduces during the backward
+            for b, bk in enumerate(self.buckets):
+                self._pending[b] = len(bk["idx"])
+                self._done[b] = False
         losses[0].backward()
         with torch.no_grad():
-            if self.group is not None or self.opt is not None:
+            if self.group is not None:
+                self._finish_reduction()
+            elif self.opt is not None:
                 flat.gather_grads()
-            if self.group is not None:  # DDP's gradient averaging as one flat all-reduce
-                import torch.distributed as dist
-                dist.all_reduce(flat.grad, group=self.group)
-                flat.grad.mul_(1.0 / self.world)
+            if self.group is not None:
                 if self.opt is None:  # the caller's own optimizer reads p.grad: hand back the averaged gradient, like DDP
                     torch._foreach_copy_([p.grad for p in flat.params if p.grad is not None],
                                          [v for v, p in zip(flat.grad_views, flat.params) if p.grad is not None])
@@ -210,6 +289,9 @@ class GraphedStep:
     def close(self):
         """Drop the captured graph.  Call it before ``destroy_process_group``: a live graph that holds NCCL kernels keeps the
         communicator busy and the teardown waits for it forever."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
         if self.graph is not None:
             torch.cuda.synchronize()
             self.graph.reset()
