@@ -195,6 +195,8 @@ class GraphedStep:
             self.flat.grad.mul_(1.0 / self.world)
 
     def set_lr(self, lr: float):
+        if self.opt is None:
+            raise RuntimeError("GraphedStep was built without an optimizer")
         self.lr.fill_(float(lr))  # device scalar: the captured Adam launch reads it at replay time
 
     def _body(self):
