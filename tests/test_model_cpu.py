@@ -51,3 +51,18 @@ def test_state_dict_keys_match_oracle_contract():
     assert set(got) == set(sd)
     for k in sd:
         assert tuple(got[k].shape) == tuple(sd[k].shape), k
+
+
+def test_factories_accept_timm_injected_kwargs(caplog):
+    """train_mirror.py:689-694 builds the model through timm's create_model, which injects pretrained / pretrained_cfg /
+    pretrained_cfg_overlay (and passes checkpoint_path / scriptable separately): the factories filter unknown kwargs with the same
+    warning as the reference (models/mirror.py:1045-1053) instead of failing"""
+    import logging
+    from mirror_b200.models import mirror, mirror_dual_encoder
+    with caplog.at_level(logging.WARNING):
+        m = mirror(wsi_embed_dim=16, rna_embed_dim=20, embed_dim=24, wsi_num_tokens=9, num_prototypes=5, pretrained=False,
+                   pretrained_cfg=None, pretrained_cfg_overlay=None)
+    assert "Filtered model kwargs" in caplog.text and "pretrained" in caplog.text
+    assert m.wsi_encoder.retention_gene_embed.shape == (1, 10, 24) and m.prototypes.weight.shape == (5, 24)
+    d = mirror_dual_encoder(wsi_embed_dim=16, rna_embed_dim=20, embed_dim=24, pretrained=False)
+    assert hasattr(d, "wsi_encoder") and hasattr(d, "rna_encoder")
