@@ -105,3 +105,17 @@ class SlidePrefetcher:
                 wsi_d = gather_bags(wsi_d[0], wsi_d[1], out)
             yield wsi_d, rna_d
             slot["free"].record(cur)  # everything the consumer enqueued on these buffers precedes this event
+
+
+def length_bucketed_batches(lengths, batch_size, rng=None, drop_last=False):
+    """Batches of slide indices for ``MIRROR.forward_varlen``: slides of EQUAL length are placed next to each other (the varlen path
+    runs every group of equal length as one dense batch, so the number of distinct lengths per batch is the number of passes through
+    the fixed-length kernels), batches are then shuffled.  ``lengths``: patches per slide (e.g. after rounding the bags down to a
+    multiple of 256 patches, which keeps every patch but the remainder).  Returns a list of index lists."""
+    rng = rng if rng is not None else np.random
+    order = np.lexsort((rng.permutation(len(lengths)), np.asarray(lengths)))  # by length, ties in random order
+    batches = [order[i:i + batch_size].tolist() for i in range(0, len(order), batch_size)]
+    if drop_last and batches and len(batches[-1]) < batch_size:
+        batches.pop()
+    perm = rng.permutation(len(batches))
+    return [batches[i] for i in perm]

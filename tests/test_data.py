@@ -73,3 +73,17 @@ def test_prefetcher_overlaps_copies_and_keeps_batches_intact():
     assert len(got) == 7 and pf.h2d_bytes > 0
     for (a, b), (wa, wb) in zip(got, want):
         assert torch.equal(a, wa) and torch.equal(b, wb)
+
+
+def test_length_bucketed_batches_minimise_distinct_lengths():
+    from mirror_b200.data import length_bucketed_batches
+    rng = np.random.RandomState(0)
+    lengths = (rng.randint(4, 12, size=203) * 256).tolist()
+    batches = length_bucketed_batches(lengths, 16, np.random.RandomState(1))
+    flat = sorted(i for b in batches for i in b)
+    assert flat == list(range(203))                                    # a partition of the dataset
+    distinct = [len({lengths[i] for i in b}) for b in batches]
+    assert max(distinct) <= 3 and np.mean(distinct) < 2.0              # vs ~6.5 distinct lengths in a random batch of 16
+    naive = [len({lengths[i] for i in rng.permutation(203)[:16]}) for _ in range(20)]
+    assert np.mean(naive) > 2 * np.mean(distinct)
+    assert all(len(b) == 16 for b in length_bucketed_batches(lengths, 16, np.random.RandomState(2), drop_last=True))
